@@ -1,0 +1,924 @@
+// amx_api.cu -- the C ABI of libamx (include/amx.h): descriptor validation, workspace
+// layout, the control kernels that keep dt / t / the fixed-point flag on the device, and
+// the step / integrate drivers.  Compiled with -fmad=false: the scalar dt arithmetic here
+// follows the reference's operation order in both arithmetic flavours.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/amx.h"
+#include "amx_internal.h"
+
+using namespace amx;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+  return fail(AMX_ECUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CK(expr)                                        \
+  do {                                                  \
+    cudaError_t e__ = (expr);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+  } while (0)
+
+struct Layout {
+  int nd, ng, nv;          // dims, gas rows, total rows
+  long long cells;         // active cells
+  size_t esz;              // element size
+  size_t row_bytes;        // cells * esz rounded up to 256
+  // byte offsets into ws
+  size_t off_ctl, off_S[2], off_A, off_G, off_X[2], total;
+};
+
+size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+int validate(const amx_desc* d) {
+  if (!d) return fail(AMX_EINVAL, "null descriptor");
+  if (d->abi_version != AMX_ABI_VERSION) return fail(AMX_EINVAL, "amx_desc.abi_version mismatch");
+  if (d->ndim < 1 || d->ndim > 3) return fail(AMX_EINVAL, "ndim must be 1, 2 or 3");
+  for (int a = 0; a < 3; ++a) {
+    if (a < d->ndim ? d->n[a] < 4 : d->n[a] != 1)
+      return fail(AMX_EINVAL, "n[a] must be >= 4 on active axes and 1 on absent ones");
+  }
+  if (d->dtype != AMX_F32 && d->dtype != AMX_F64) return fail(AMX_EINVAL, "dtype must be AMX_F32 or AMX_F64");
+  if (d->mhd && d->ndim == 1) return fail(AMX_EUNSUPPORTED, "MHD currently not supported in 1D.");
+  if (d->riemann < AMX_HLL || d->riemann > 5) return fail(AMX_EINVAL, "Riemann solver not supported.");
+  if (d->riemann > AMX_LAX_FRIEDRICHS)
+    return fail(AMX_EUNSUPPORTED, "HYBRID_HLLC / AM_HLLC fluxes are not built yet (SURVEY.md f2)");
+  if (d->limiter < 0 || d->limiter > 5) return fail(AMX_EINVAL, "Unknown limiter.");
+  if (d->limiter == 5)
+    return fail(AMX_EUNSUPPORTED, "VAN_ALBADA_PP reconstruction is not built yet (SURVEY.md a14)");
+  if (d->split == AMX_UNSPLIT) {
+    if (d->time_integrator != AMX_RK2_SSP)
+      return fail(AMX_EINVAL, "Only the RK2 SSP time integrator is currently supported for the unsplit scheme.");
+  } else if (d->split == AMX_SPLIT) {
+    if (d->time_integrator != AMX_MUSCL && !d->first_order_fallback)
+      return fail(AMX_EINVAL, "Only MUSCL is supported for split reconstruction.");
+  } else {
+    return fail(AMX_EINVAL, "split must be UNSPLIT or SPLIT");
+  }
+  if (d->boundary_handling != AMX_GHOST_CELLS && d->boundary_handling != AMX_PERIODIC_ROLL)
+    return fail(AMX_EINVAL, "unknown boundary_handling");
+  if (d->num_ghost != 2) return fail(AMX_EUNSUPPORTED, "num_ghost must be 2 (the reference pads by 2, Q8)");
+  for (int a = 0; a < d->ndim; ++a) {
+    for (int s = 0; s < 2; ++s) {
+      const int b = d->bc[a][s];
+      if (b != AMX_BC_OPEN && b != AMX_BC_REFLECTIVE && b != AMX_BC_PERIODIC && b != AMX_BC_HALO)
+        return fail(b == 3 ? AMX_EUNSUPPORTED : AMX_EINVAL, "boundary code not supported (MHD jet boundary: SURVEY.md f4)");
+      if (b == AMX_BC_HALO && a != 0) return fail(AMX_EINVAL, "AMX_BC_HALO is only valid on axis 0");
+    }
+    if ((d->bc[a][0] == AMX_BC_PERIODIC) != (d->bc[a][1] == AMX_BC_PERIODIC))
+      return fail(AMX_EUNSUPPORTED, "periodic boundaries must be set on both sides of an axis");
+    if (d->boundary_handling == AMX_PERIODIC_ROLL && d->bc[a][0] != AMX_BC_PERIODIC && d->bc[a][0] != AMX_BC_HALO)
+      return fail(AMX_EINVAL, "PERIODIC_ROLL implies periodic boundaries");
+  }
+  if (!(d->dx > 0) || !(d->gamma > 1) || !(d->C_cfl > 0)) return fail(AMX_EINVAL, "dx, gamma-1, C_cfl must be positive");
+  if (d->arithmetic != AMX_ARITH_FAST && d->arithmetic != AMX_ARITH_STRICT) return fail(AMX_EINVAL, "unknown arithmetic mode");
+  return AMX_OK;
+}
+
+Layout make_layout(const amx_desc* d) {
+  Layout L;
+  L.nd = d->ndim;
+  L.ng = d->ndim + 2;
+  L.nv = L.ng + (d->mhd ? 3 : 0);
+  L.cells = 1;
+  // slab mode keeps the x ghost planes resident in every internal buffer
+  const int gx = (d->bc[0][0] == AMX_BC_HALO || d->bc[0][1] == AMX_BC_HALO) ? 2 * d->num_ghost : 0;
+  L.cells = (long long)(d->n[0] + gx) * d->n[1] * d->n[2];
+  L.esz = d->dtype == AMX_F32 ? 4 : 8;
+  L.row_bytes = align256((size_t)L.cells * L.esz);
+  size_t off = 0;
+  L.off_ctl = off; off += align256(sizeof(Ctl));
+  for (int k = 0; k < 2; ++k) { L.off_S[k] = off; off += L.row_bytes * L.nv; }
+  L.off_A = off; off += L.row_bytes * L.ng;
+  L.off_G = off; off += L.row_bytes * L.ng;
+  for (int k = 0; k < 2; ++k) { L.off_X[k] = off; off += d->mhd ? L.row_bytes * 6 : 0; }
+  L.total = off;
+  return L;
+}
+
+Geom geom_of(const amx_desc* d) {
+  Geom g;
+  g.nd = d->ndim;
+  for (int a = 0; a < 3; ++a) {
+    g.n[a] = d->n[a];
+    g.bc[a][0] = d->bc[a][0];
+    g.bc[a][1] = d->bc[a][1];
+  }
+  return g;
+}
+
+NumPar numpar_of(const amx_desc* d) {
+  NumPar p;
+  p.dtype = d->dtype;
+  p.rs = d->riemann;
+  p.lim = d->limiter;
+  p.dx = d->dx;
+  // params.gamma enters the jitted loop as a scalar of the working dtype (Q20)
+  p.gamma = d->dtype == AMX_F32 ? (double)(float)d->gamma : d->gamma;
+  return p;
+}
+
+// View of `rows` rows over a buffer whose per-axis extents are n[a] + 2*pad[a]; p is moved to
+// the first active cell.  row_stride_elems = 0 -> dense rows.
+View make_view(void* base, const amx_desc* d, const int pad[3], size_t row_stride_elems, int first_row = 0) {
+  View v;
+  const long long e2 = d->n[2] + 2 * pad[2], e1 = d->n[1] + 2 * pad[1], e0 = d->n[0] + 2 * pad[0];
+  long long s[3] = {e1 * e2, e2, 1};
+  // strides follow the array rank: 1-D arrays are [rows][x], 2-D [rows][x][y]
+  if (d->ndim == 1) { s[0] = 1; s[1] = 0; s[2] = 0; }
+  else if (d->ndim == 2) { s[0] = e1; s[1] = 1; s[2] = 0; }
+  for (int a = 0; a < 3; ++a) v.s[a] = s[a];
+  long long vol = 1;
+  if (d->ndim == 1) vol = e0; else if (d->ndim == 2) vol = e0 * e1; else vol = e0 * e1 * e2;
+  v.vs = row_stride_elems ? (long long)row_stride_elems : vol;
+  long long off = 0;
+  for (int a = 0; a < d->ndim; ++a) off += (long long)pad[a] * v.s[a];
+  const size_t esz = d->dtype == AMX_F32 ? 4 : 8;
+  v.p = static_cast<char*>(base) + ((size_t)first_row * v.vs + off) * esz;
+  return v;
+}
+
+View rows_of(const View& v, int first_row, size_t esz) {
+  View r = v;
+  r.p = static_cast<char*>(v.p) + (size_t)first_row * v.vs * esz;
+  return r;
+}
+
+void seam_pad(const amx_desc* d, int pad[3]) {
+  for (int a = 0; a < 3; ++a) pad[a] = (a < d->ndim && d->boundary_handling == AMX_GHOST_CELLS) ? d->num_ghost : 0;
+}
+void internal_pad(const amx_desc* d, int pad[3]) {
+  for (int a = 0; a < 3; ++a) pad[a] = 0;
+  if (d->bc[0][0] == AMX_BC_HALO || d->bc[0][1] == AMX_BC_HALO) pad[0] = d->num_ghost;
+}
+
+// ---------------------------------------------------------------- control kernels
+template <typename T> __device__ inline T from_bits(unsigned long long b);
+template <> __device__ inline float from_bits<float>(unsigned long long b) { return __uint_as_float((unsigned)b); }
+template <> __device__ inline double from_bits<double>(unsigned long long b) { return __longlong_as_double((long long)b); }
+
+// slots[NV][kAlphaSlots] -> NV maxima (widened to double in dst_d, and as T in dst_t if given); slots zeroed
+template <typename T, int NV>
+__global__ void finalize_slots_kernel(unsigned long long* slots, double* dst_d, float* dst_f, T* dst_t,
+                                      const Ctl* ctl_ro) {
+  if (ctl_ro && ctl_ro->done) return;
+  __shared__ T red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = 0; k < NV; ++k) {
+    T m = T(0);
+    for (int i = threadIdx.x; i < kAlphaSlots; i += blockDim.x) {
+      const T v = from_bits<T>(slots[(size_t)k * kAlphaSlots + i]);
+      m = v > m ? v : m;  // NaN never wins a comparison; a NaN state shows up in the state itself
+      slots[(size_t)k * kAlphaSlots + i] = 0ull;
+    }
+    for (int o = 16; o > 0; o >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, m, o); m = w > m ? w : m; }
+    if (lane == 0) red[wid] = m;
+    __syncthreads();
+    if (wid == 0) {
+      m = lane < (int)(blockDim.x >> 5) ? red[lane] : T(0);
+      for (int o = 16; o > 0; o >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, m, o); m = w > m ? w : m; }
+      if (lane == 0) {
+        if (dst_d) dst_d[k] = (double)m;
+        if (dst_f) dst_f[k] = (float)m;
+        if (dst_t) dst_t[k] = m;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct DtPar {
+  int nd, split, use_max, exact_end;
+  double C_cfl, dx, dt_max, t_end;
+};
+
+// _timestep_estimator.py:118-128 (unsplit) / :131-218 (split), time_integration.py:677-678
+template <typename T>
+__device__ T dt_from_alpha(const double* alpha, const DtPar& p, T time) {
+  const T C = (T)p.C_cfl;
+  T dt;
+  if (p.split == AMX_UNSPLIT) {
+    T sum = T(0);
+    for (int k = 0; k < p.nd; ++k) sum = sum + (T)alpha[k] / (T)p.dx;
+    dt = (C * T(1)) / sum;
+  } else {
+    T m = (T)alpha[0];
+    for (int k = 1; k < p.nd; ++k) m = (T)alpha[k] > m ? (T)alpha[k] : m;
+    dt = (C * (T)p.dx) / m;
+    if (p.use_max) dt = dt < (T)p.dt_max ? dt : (T)p.dt_max;
+  }
+  if (p.exact_end) {
+    const T rem = (T)p.t_end - time;
+    dt = dt < rem ? dt : rem;
+  }
+  return dt;
+}
+
+template <typename T>
+__global__ void step_begin_kernel(Ctl* ctl, DtPar p, long long max_steps) {
+  if (ctl->done) return;
+  const T time = (T)ctl->time_d;
+  if (!(time < (T)p.t_end) || (max_steps >= 0 && ctl->steps >= max_steps)) {
+    ctl->done = 1;
+    return;
+  }
+  const T dt = dt_from_alpha<T>(ctl->alpha, p, time);
+  ctl->dt_d = (double)dt;
+  ctl->dt_f = (float)dt;
+  ctl->mag_active = 1;
+  ctl->mag_iter = 0;
+}
+
+template <typename T>
+__global__ void step_end_kernel(Ctl* ctl) {
+  if (ctl->done) return;
+  const T t = (T)ctl->time_d + (T)ctl->dt_d;
+  ctl->time_d = (double)t;
+  ctl->time_f = (float)t;
+  ctl->steps += 1;
+  ctl->mag_iters_total += ctl->mag_iter;
+}
+
+template <typename T>
+__global__ void dt_only_kernel(const T* alpha_t, const T* time_t, DtPar p, T* dt_out) {
+  double a[3] = {0, 0, 0};
+  for (int k = 0; k < p.nd; ++k) a[k] = (double)alpha_t[k];
+  const T time = time_t ? *time_t : T(0);
+  DtPar q = p;
+  if (!time_t) q.exact_end = 0;
+  *dt_out = dt_from_alpha<T>(a, q, time);
+}
+
+// _magnetic_field_update.py:127-141 while_condition, evaluated after launch j of the fixed point
+template <typename T>
+__global__ void mag_check_kernel(Ctl* ctl, double tol, int j) {
+  if (ctl->done || !ctl->mag_active) return;
+  const T m = (T)ctl->change[0] > (T)ctl->change[1] ? (T)ctl->change[0] : (T)ctl->change[1];
+  if (m > (T)tol && ctl->mag_iter < 1000) {
+    ctl->mag_iter += 1;
+  } else {
+    ctl->mag_active = 0;
+    ctl->mag_final = j & 1;
+    if (m > (T)tol) ctl->not_converged = 1;
+  }
+}
+
+template <typename T>
+__global__ void set_dt_kernel(Ctl* ctl, const T* dt_dev) {
+  ctl->dt_d = (double)*dt_dev;
+  ctl->dt_f = (float)*dt_dev;
+  ctl->done = 0;
+  ctl->mag_active = 1;
+  ctl->mag_iter = 0;
+}
+
+// ---------------------------------------------------------------- layout kernels
+// dst (padded by ng on active axes) <- src (unpadded).  Gas rows take the boundary rule of
+// their side, the other rows are edge-padded (np.pad mode="edge", Q9).
+template <typename T>
+__global__ void pad_kernel(Geom g, int ng, int rows, int gas_rows, View src, View dst) {
+  long long e[3], tot = 1;
+  for (int a = 0; a < 3; ++a) { e[a] = a < g.nd ? g.n[a] + 2 * ng : 1; tot *= e[a]; }
+  const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lin >= tot) return;
+  long long r = lin;
+  int i[3];
+  i[2] = (int)(r % e[2]); r /= e[2];
+  i[1] = (int)(r % e[1]); r /= e[1];
+  i[0] = (int)r;
+  long long od = 0, os_gas = 0, os_edge = 0;
+  int flip_row = -1;  // at most the last reflective axis flips; several flips handled below
+  unsigned flipmask = 0;
+  for (int a = 0; a < g.nd; ++a) {
+    const int ia = i[a] - ng;
+    od += (long long)ia * dst.s[a];
+    int ie = ia < 0 ? 0 : (ia >= g.n[a] ? g.n[a] - 1 : ia);
+    os_edge += (long long)ie * src.s[a];
+    int ig = ia;
+    if (ia < 0) {
+      const int b = g.bc[a][0];
+      ig = b == BC_PERIODIC ? ia + g.n[a] : (b == BC_REFLECTIVE ? (g.nd == 1 ? 0 : -1 - ia) : 0);
+      if (b == BC_REFLECTIVE) flipmask |= 1u << (a + 1);
+    } else if (ia >= g.n[a]) {
+      const int b = g.bc[a][1];
+      ig = b == BC_PERIODIC ? ia - g.n[a] : (b == BC_REFLECTIVE ? (g.nd == 1 ? g.n[a] - 1 : 2 * g.n[a] - 1 - ia) : g.n[a] - 1);
+      if (b == BC_REFLECTIVE) flipmask |= 1u << (a + 1);
+    }
+    os_gas += (long long)ig * src.s[a];
+  }
+  (void)flip_row;
+  const T* ps = static_cast<const T*>(src.p);
+  T* pd = static_cast<T*>(dst.p);
+  for (int k = 0; k < rows; ++k) {
+    T v;
+    if (k < gas_rows) {
+      v = ps[k * src.vs + os_gas];
+      if (flipmask & (1u << k)) v = -v;
+    } else {
+      v = ps[k * src.vs + os_edge];
+    }
+    pd[k * dst.vs + od] = v;
+  }
+}
+
+template <typename T>
+__global__ void copy_rows_kernel(Geom g, int rows, View src, View dst) {
+  const long long tot = (long long)g.n[0] * g.n[1] * g.n[2];
+  const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lin >= tot) return;
+  long long r = lin;
+  int i[3];
+  i[2] = (int)(r % g.n[2]); r /= g.n[2];
+  i[1] = (int)(r % g.n[1]); r /= g.n[1];
+  i[0] = (int)r;
+  long long os = 0, od = 0;
+  for (int a = 0; a < g.nd; ++a) { os += (long long)i[a] * src.s[a]; od += (long long)i[a] * dst.s[a]; }
+  const T* ps = static_cast<const T*>(src.p);
+  T* pd = static_cast<T*>(dst.p);
+  for (int k = 0; k < rows; ++k) pd[k * dst.vs + od] = ps[k * src.vs + os];
+}
+
+// _boundary_handler on a padded array, in place: every ghost cell <- its source cell under the
+// per-axis rules (open, reflective, periodic compose axis by axis exactly like the reference's
+// sequential fills).  type_handled 0: gas rows (flip row `axis`); 1/2: 3-vectors (flip row
+// `axis` when < rows, i.e. the reference's Q12 behaviour).
+template <typename T>
+__global__ void ghost_fill_kernel(Geom g, int ng, int rows, int type_handled, View a) {
+  long long e[3], tot = 1;
+  for (int ax = 0; ax < 3; ++ax) { e[ax] = ax < g.nd ? g.n[ax] + 2 * ng : 1; tot *= e[ax]; }
+  const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lin >= tot) return;
+  long long r = lin;
+  int i[3];
+  i[2] = (int)(r % e[2]); r /= e[2];
+  i[1] = (int)(r % e[1]); r /= e[1];
+  i[0] = (int)r;
+  long long od = 0, os = 0;
+  unsigned flipmask = 0;
+  bool ghost = false;
+  for (int ax = 0; ax < g.nd; ++ax) {
+    const int ia = i[ax] - ng;
+    od += (long long)ia * a.s[ax];
+    int ig = ia;
+    if (ia < 0) {
+      ghost = true;
+      const int b = g.bc[ax][0];
+      ig = b == BC_PERIODIC ? ia + g.n[ax] : (b == BC_REFLECTIVE ? (g.nd == 1 ? 0 : -1 - ia) : (b == BC_OPEN ? 0 : ia));
+      if (b == BC_REFLECTIVE) flipmask |= 1u << (ax + 1);
+    } else if (ia >= g.n[ax]) {
+      ghost = true;
+      const int b = g.bc[ax][1];
+      ig = b == BC_PERIODIC ? ia - g.n[ax]
+                            : (b == BC_REFLECTIVE ? (g.nd == 1 ? g.n[ax] - 1 : 2 * g.n[ax] - 1 - ia) : (b == BC_OPEN ? g.n[ax] - 1 : ia));
+      if (b == BC_REFLECTIVE) flipmask |= 1u << (ax + 1);
+    }
+    os += (long long)ig * a.s[ax];
+  }
+  if (!ghost || os == od) return;
+  (void)type_handled;
+  T* p = static_cast<T*>(a.p);
+  for (int k = 0; k < rows; ++k) {
+    T v = p[k * a.vs + os];
+    if (flipmask & (1u << k)) v = -v;
+    p[k * a.vs + od] = v;
+  }
+}
+
+unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
+
+// ---------------------------------------------------------------- engine
+#define CKE(expr)                                  \
+  do {                                             \
+    cudaError_t e__ = (expr);                      \
+    if (e__ != cudaSuccess) return e__;            \
+  } while (0)
+
+struct Engine {
+  const amx_desc* d;
+  Layout L;
+  Geom g;
+  NumPar np;
+  char* ws;
+  Ctl* ctl;
+  cudaStream_t st;
+  long long launches = 0;
+  bool strict, is32, lf;
+
+  Engine(const amx_desc* d_, void* ws_, void* stream)
+      : d(d_), L(make_layout(d_)), g(geom_of(d_)), np(numpar_of(d_)), ws(static_cast<char*>(ws_)),
+        ctl(reinterpret_cast<Ctl*>(static_cast<char*>(ws_) + L.off_ctl)), st(static_cast<cudaStream_t>(stream)),
+        strict(d_->arithmetic == AMX_ARITH_STRICT), is32(d_->dtype == AMX_F32),
+        lf(d_->riemann == AMX_LAX_FRIEDRICHS) {}
+
+  // view over an internal workspace buffer (x ghost planes resident in slab mode)
+  View internal(size_t off, int first_row = 0) const {
+    int pad[3];
+    internal_pad(d, pad);
+    return make_view(ws + off, d, pad, L.row_bytes / L.esz, first_row);
+  }
+  // view over a caller array in the internal layout (dense rows)
+  View user_internal(const void* p, int first_row = 0) const {
+    int pad[3];
+    internal_pad(d, pad);
+    return make_view(const_cast<void*>(p), d, pad, 0, first_row);
+  }
+  View user_seam(const void* p, int first_row = 0) const {
+    int pad[3];
+    seam_pad(d, pad);
+    if (d->bc[0][0] == AMX_BC_HALO || d->bc[0][1] == AMX_BC_HALO) internal_pad(d, pad);
+    return make_view(const_cast<void*>(p), d, pad, 0, first_row);
+  }
+  View user_unpadded(const void* p, int first_row = 0) const {
+    int pad[3] = {0, 0, 0};
+    return make_view(const_cast<void*>(p), d, pad, 0, first_row);
+  }
+  const void* dt_ptr() const { return is32 ? (const void*)&ctl->dt_f : (const void*)&ctl->dt_d; }
+  const void* alpha_ptr() const { return is32 ? (const void*)ctl->alpha_f : (const void*)ctl->alpha; }
+  unsigned long long* aslots() const { return &ctl->alpha_slots[0][0]; }
+  unsigned long long* cslots() const { return &ctl->change_slots[0][0]; }
+  DtPar dtpar(double t_end) const {
+    DtPar p;
+    p.nd = d->ndim; p.split = d->split; p.use_max = d->use_max_adaptive_timestep; p.exact_end = d->exact_end_time;
+    p.C_cfl = is32 ? (double)(float)d->C_cfl : d->C_cfl;
+    p.dx = d->dx;
+    p.dt_max = is32 ? (double)(float)d->dt_max : d->dt_max;
+    p.t_end = is32 ? (double)(float)t_end : t_end;
+    return p;
+  }
+
+  cudaError_t finalize_alpha(void* alpha_t_out, bool guarded) {
+    ++launches;
+    const Ctl* c = guarded ? ctl : nullptr;
+    if (is32) finalize_slots_kernel<float, 3><<<1, 256, 0, st>>>(aslots(), ctl->alpha, ctl->alpha_f, (float*)alpha_t_out, c);
+    else finalize_slots_kernel<double, 3><<<1, 256, 0, st>>>(aslots(), ctl->alpha, ctl->alpha_f, (double*)alpha_t_out, c);
+    return cudaGetLastError();
+  }
+  cudaError_t finalize_change(void* change_t_out, bool guarded) {
+    ++launches;
+    const Ctl* c = guarded ? ctl : nullptr;
+    if (is32) finalize_slots_kernel<float, 2><<<1, 256, 0, st>>>(cslots(), ctl->change, nullptr, (float*)change_t_out, c);
+    else finalize_slots_kernel<double, 2><<<1, 256, 0, st>>>(cslots(), ctl->change, nullptr, (double*)change_t_out, c);
+    return cudaGetLastError();
+  }
+
+  cudaError_t alpha_of(const View& gas, void* alpha_t_out, bool guarded) {
+    AlphaArgs a{g, np, gas, guarded ? ctl : nullptr, aslots()};
+    ++launches;
+    CKE(strict ? amx_strict::launch_alpha(a, st) : amx_fast::launch_alpha(a, st));
+    return finalize_alpha(alpha_t_out, guarded);
+  }
+
+  cudaError_t stage(const View& in, const View* in0, const View& out, const void* dt, double dt_scale,
+                    const void* alpha_lf, bool want_alpha, void* alpha_t_out, bool guarded) {
+    StageArgs a;
+    a.g = g; a.np = np; a.in = in; a.out = out;
+    a.in0 = in0 ? *in0 : in;
+    if (!in0) a.in0.p = nullptr;
+    a.ctl_ro = guarded ? ctl : nullptr;
+    a.dt = dt; a.dt_scale = dt_scale; a.alpha_lf = alpha_lf;
+    a.alpha_slots = want_alpha ? aslots() : nullptr;
+    ++launches;
+    CKE(strict ? amx_strict::launch_hydro_stage(a, st) : amx_fast::launch_hydro_stage(a, st));
+    return want_alpha ? finalize_alpha(alpha_t_out, guarded) : cudaSuccess;
+  }
+
+  cudaError_t sweep(const View& in, const View& out, int axis, const void* dt, double dt_scale,
+                    const void* alpha_lf, bool want_alpha, void* alpha_t_out, bool guarded) {
+    SweepArgs a;
+    a.g = g; a.np = np; a.in = in; a.out = out; a.ctl_ro = guarded ? ctl : nullptr;
+    a.dt = dt; a.dt_scale = dt_scale; a.axis = axis; a.first_order = d->first_order_fallback;
+    a.alpha_lf = alpha_lf; a.alpha_slots = want_alpha ? aslots() : nullptr;
+    ++launches;
+    CKE(strict ? amx_strict::launch_split_sweep(a, st) : amx_fast::launch_split_sweep(a, st));
+    return want_alpha ? finalize_alpha(alpha_t_out, guarded) : cudaSuccess;
+  }
+
+  // evolve_state.py:419-488 / :168-325: gas_in -> gas_out with time step dt*scale.
+  // tmpA / tmpB are scratch gas buffers (internal layout).  final_alpha: also produce the wave
+  // bounds of gas_out (next CFL; always needed by Lax-Friedrichs).
+  cudaError_t hydro(const View& gas_in, const View& gas_out, const View& tmpA, const View& tmpB,
+                    double scale, bool final_alpha) {
+    if (d->split == AMX_UNSPLIT) {
+      CKE(stage(gas_in, nullptr, tmpA, dt_ptr(), scale, alpha_ptr(), lf, nullptr, true));
+      return stage(tmpA, &gas_in, gas_out, dt_ptr(), scale, alpha_ptr(), final_alpha || lf, nullptr, true);
+    }
+    // Strang sequences of evolve_state.py:168-325
+    int axes[5];
+    double frac[5];
+    int ns;
+    if (d->ndim == 1) { ns = 1; axes[0] = 1; frac[0] = 1; }
+    else if (d->ndim == 2) { ns = 3; axes[0] = 1; axes[1] = 2; axes[2] = 1; frac[0] = 0.5; frac[1] = 1; frac[2] = 0.5; }
+    else { ns = 5; const int ax[5] = {1, 2, 3, 2, 1}; const double fr[5] = {0.5, 0.5, 1, 0.5, 0.5};
+           for (int k = 0; k < 5; ++k) { axes[k] = ax[k]; frac[k] = fr[k]; } }
+    const View* src = &gas_in;
+    for (int k = 0; k < ns; ++k) {
+      const bool last = k == ns - 1;
+      const View* dst = last ? &gas_out : ((k & 1) ? &tmpB : &tmpA);
+      CKE(sweep(*src, *dst, axes[k], dt_ptr(), scale * frac[k], alpha_ptr(), (last && final_alpha) || lf, nullptr, true));
+      src = dst;
+    }
+    return cudaSuccess;
+  }
+
+  cudaError_t mag_iter(const View& B0, const View& gas0, const View* Xk, const View& Xk1, const void* dt,
+                       int j, bool guarded) {
+    MagIterArgs a;
+    a.g = g; a.np = np; a.B0 = B0; a.gas0 = gas0;
+    if (Xk) { a.Bk = *Xk; a.vk = rows_of(*Xk, 3, L.esz); }
+    else { a.Bk = B0; a.Bk.p = nullptr; a.vk = B0; a.vk.p = nullptr; }
+    a.Bk1 = Xk1; a.vk1 = rows_of(Xk1, 3, L.esz);
+    a.ctl_ro = guarded ? ctl : nullptr;
+    a.first = (j == 0);
+    a.midpoint = d->magnetic_integrator == AMX_IMPLICIT_MIDPOINT;
+    a.dt = dt; a.change_slots = cslots();
+    ++launches;
+    return strict ? amx_strict::launch_mag_iter(a, st) : amx_fast::launch_mag_iter(a, st);
+  }
+
+  cudaError_t mag_check(int j) {
+    ++launches;
+    const double tol = d->fp_tol;
+    if (is32) mag_check_kernel<float><<<1, 1, 0, st>>>(ctl, tol, j);
+    else mag_check_kernel<double><<<1, 1, 0, st>>>(ctl, tol, j);
+    return cudaGetLastError();
+  }
+
+  cudaError_t mag_final(const View& gas, const View& B_out, const View X[2], int fixed_final, bool want_alpha,
+                        void* alpha_t_out, bool guarded) {
+    MagFinalArgs a;
+    a.g = g; a.np = np; a.gas = gas; a.B_out = B_out; a.X[0] = X[0]; a.X[1] = X[1];
+    a.ctl_ro = ctl; a.fixed_final = fixed_final; a.alpha_slots = want_alpha ? aslots() : nullptr;
+    (void)guarded;
+    ++launches;
+    CKE(strict ? amx_strict::launch_mag_final(a, st) : amx_fast::launch_mag_final(a, st));
+    return want_alpha ? finalize_alpha(alpha_t_out, true) : cudaSuccess;
+  }
+};
+
+struct HostMirror {
+  Ctl* pinned = nullptr;  // only the head of Ctl (before the slots) is mirrored
+  ~HostMirror() { if (pinned) cudaFreeHost(pinned); }
+};
+thread_local HostMirror g_mirror;
+constexpr size_t kCtlHead = offsetof(Ctl, alpha_slots);
+
+int read_ctl(Engine& E, Ctl** out) {
+  if (!g_mirror.pinned) CK(cudaMallocHost(&g_mirror.pinned, sizeof(Ctl)));
+  CK(cudaMemcpyAsync(g_mirror.pinned, E.ctl, kCtlHead, cudaMemcpyDeviceToHost, E.st));
+  CK(cudaStreamSynchronize(E.st));
+  *out = g_mirror.pinned;
+  return AMX_OK;
+}
+
+// One full step state_in -> state_out (views of nv rows) with dt already in ctl.
+// evolve_state.py:497-600.  kspec = fixed-point launches to enqueue before the host looks.
+int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
+  const amx_desc* d = E.d;
+  const Layout& L = E.L;
+  const View A = E.internal(L.off_A), G = E.internal(L.off_G);
+  if (!d->mhd) {
+    CK(E.hydro(sin, sout, A, G, 1.0, true));
+    return AMX_OK;
+  }
+  // Strang: hydro(dt/2) on the gas rows . magnetic(dt) . hydro(dt/2)
+  const View X[2] = {E.internal(L.off_X[0]), E.internal(L.off_X[1])};
+  const View Bin = rows_of(sin, L.ng, L.esz), Bout = rows_of(sout, L.ng, L.esz);
+  // second half-step needs two scratch buffers besides G: A and the gas rows of ... X is free by then
+  CK(E.hydro(sin, G, A, X[0], 0.5, false));
+  int j = 0;
+  CK(E.mag_iter(Bin, G, nullptr, X[0], E.dt_ptr(), 0, true));
+  CK(E.finalize_change(nullptr, true));
+  CK(E.mag_check(0));
+  for (j = 1; j < *kspec; ++j) {
+    CK(E.mag_iter(Bin, G, &X[(j - 1) & 1], X[j & 1], E.dt_ptr(), j, true));
+    CK(E.finalize_change(nullptr, true));
+    CK(E.mag_check(j));
+  }
+  Ctl* m;
+  int rc = read_ctl(E, &m);
+  if (rc) return rc;
+  while (m->mag_active && !m->done) {
+    for (int e = 0; e < 2; ++e, ++j) {
+      CK(E.mag_iter(Bin, G, &X[(j - 1) & 1], X[j & 1], E.dt_ptr(), j, true));
+      CK(E.finalize_change(nullptr, true));
+      CK(E.mag_check(j));
+    }
+    rc = read_ctl(E, &m);
+    if (rc) return rc;
+  }
+  if (!m->done) *kspec = std::max(2, m->mag_iter + 2);  // launches needed = while-iterations + 1, plus slack
+  CK(E.mag_final(G, Bout, X, -1, E.lf, nullptr, true));
+  // X buffers are free again: reuse X[0] rows as sweep scratch
+  CK(E.hydro(G, sout, A, X[0], 0.5, true));
+  return AMX_OK;
+}
+
+int check_common(const amx_desc* d, const void* a, const void* b) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!a || !b) return fail(AMX_EINVAL, "null array pointer");
+  return AMX_OK;
+}
+
+template <typename F>
+int launch_by_dtype(const amx_desc* d, F&& f) {
+  return d->dtype == AMX_F32 ? f(float{}) : f(double{});
+}
+
+}  // namespace
+
+// ================================================================ exported C ABI
+extern "C" {
+
+int amx_abi_version(void) { return AMX_ABI_VERSION; }
+const char* amx_last_error(void) { return g_err.c_str(); }
+
+int amx_device_check(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (n == 0) return fail(AMX_ECUDA, "no CUDA device visible; libamx has no CPU path");
+  return AMX_OK;
+}
+
+int amx_workspace_bytes(const amx_desc* d, size_t* bytes_out) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!bytes_out) return fail(AMX_EINVAL, "bytes_out is null");
+  *bytes_out = make_layout(d).total;
+  return AMX_OK;
+}
+
+int amx_pad(const amx_desc* d, const void* unpadded_in, void* seam_out, void* stream) {
+  int rc = check_common(d, unpadded_in, seam_out);
+  if (rc) return rc;
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, nullptr, stream);
+  const View src = E.user_unpadded(unpadded_in), dst = E.user_seam(seam_out);
+  if (d->boundary_handling != AMX_GHOST_CELLS) {
+    const long long tot = (long long)d->n[0] * d->n[1] * d->n[2];
+    if (E.is32) copy_rows_kernel<float><<<blocks_for(tot), 256, 0, E.st>>>(E.g, E.L.nv, src, dst);
+    else copy_rows_kernel<double><<<blocks_for(tot), 256, 0, E.st>>>(E.g, E.L.nv, src, dst);
+  } else {
+    long long tot = 1;
+    for (int a = 0; a < d->ndim; ++a) tot *= d->n[a] + 2 * d->num_ghost;
+    if (E.is32) pad_kernel<float><<<blocks_for(tot), 256, 0, E.st>>>(E.g, d->num_ghost, E.L.nv, E.L.ng, src, dst);
+    else pad_kernel<double><<<blocks_for(tot), 256, 0, E.st>>>(E.g, d->num_ghost, E.L.nv, E.L.ng, src, dst);
+  }
+  CK(cudaGetLastError());
+  return AMX_OK;
+}
+
+int amx_unpad(const amx_desc* d, const void* seam_in, void* unpadded_out, void* stream) {
+  int rc = check_common(d, seam_in, unpadded_out);
+  if (rc) return rc;
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, nullptr, stream);
+  const View src = E.user_seam(seam_in), dst = E.user_unpadded(unpadded_out);
+  const long long tot = (long long)d->n[0] * d->n[1] * d->n[2];
+  if (E.is32) copy_rows_kernel<float><<<blocks_for(tot), 256, 0, E.st>>>(E.g, E.L.nv, src, dst);
+  else copy_rows_kernel<double><<<blocks_for(tot), 256, 0, E.st>>>(E.g, E.L.nv, src, dst);
+  CK(cudaGetLastError());
+  return AMX_OK;
+}
+
+int amx_boundary_fill(const amx_desc* d, void* seam_inout, int nrows, int type_handled, void* stream) {
+  int rc = check_common(d, seam_inout, seam_inout);
+  if (rc) return rc;
+  if (nrows < 1 || nrows > 8 || type_handled < 0 || type_handled > 2) return fail(AMX_EINVAL, "bad nrows / type_handled");
+  if (d->boundary_handling != AMX_GHOST_CELLS) return AMX_OK;  // nothing to fill (PERIODIC_ROLL)
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, nullptr, stream);
+  int pad[3];
+  seam_pad(d, pad);
+  const View a = make_view(seam_inout, d, pad, 0, 0);
+  long long tot = 1;
+  for (int ax = 0; ax < d->ndim; ++ax) tot *= d->n[ax] + 2 * d->num_ghost;
+  // 3-vectors flip row `axis` (1-based) like the gas state does: the kernel's rule is the same
+  if (E.is32) ghost_fill_kernel<float><<<blocks_for(tot), 256, 0, E.st>>>(E.g, d->num_ghost, nrows, type_handled, a);
+  else ghost_fill_kernel<double><<<blocks_for(tot), 256, 0, E.st>>>(E.g, d->num_ghost, nrows, type_handled, a);
+  CK(cudaGetLastError());
+  return AMX_OK;
+}
+
+int amx_cfl(const amx_desc* d, const void* seam_state, void* dt_out, void* ws, void* stream) {
+  int rc = check_common(d, seam_state, dt_out);
+  if (rc) return rc;
+  if (!ws) return fail(AMX_EINVAL, "ws is null");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  CK(cudaMemsetAsync(E.ctl, 0, sizeof(Ctl), E.st));
+  CK(E.alpha_of(E.user_seam(seam_state), nullptr, false));
+  DtPar p = E.dtpar(0.0);
+  if (E.is32) dt_only_kernel<float><<<1, 1, 0, E.st>>>(E.ctl->alpha_f, nullptr, p, (float*)dt_out);
+  else dt_only_kernel<double><<<1, 1, 0, E.st>>>(E.ctl->alpha, nullptr, p, (double*)dt_out);
+  CK(cudaGetLastError());
+  return AMX_OK;
+}
+
+int amx_step(const amx_desc* d, const void* seam_in, void* seam_out, const void* dt_dev, void* ws,
+             void* stream, amx_stats* stats) {
+  int rc = check_common(d, seam_in, seam_out);
+  if (rc) return rc;
+  if (!ws || !dt_dev) return fail(AMX_EINVAL, "ws / dt_dev is null");
+  if (seam_in == seam_out) return fail(AMX_EINVAL, "in and out must not alias");
+  if (d->bc[0][0] == AMX_BC_HALO || d->bc[0][1] == AMX_BC_HALO)
+    return fail(AMX_EUNSUPPORTED, "amx_step needs whole-domain boundaries; slab ranks use the stage-level entry points");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  CK(cudaMemsetAsync(E.ctl, 0, sizeof(Ctl), E.st));
+  if (E.is32) set_dt_kernel<float><<<1, 1, 0, E.st>>>(E.ctl, (const float*)dt_dev);
+  else set_dt_kernel<double><<<1, 1, 0, E.st>>>(E.ctl, (const double*)dt_dev);
+  CK(cudaGetLastError());
+  const View sin = E.user_seam(seam_in), sout = E.user_seam(seam_out);
+  if (E.lf) CK(E.alpha_of(sin, nullptr, false));
+  int kspec = d->dtype == AMX_F32 ? 4 : 8;
+  if ((rc = run_step(E, sin, sout, &kspec))) return rc;
+  if (d->boundary_handling == AMX_GHOST_CELLS) {
+    // ghosts of the result: what the reference's trailing _boundary_handler calls leave behind
+    if ((rc = amx_boundary_fill(d, seam_out, E.L.ng, 0, stream))) return rc;
+    if (d->mhd) {
+      int pad[3];
+      seam_pad(d, pad);
+      View b = make_view(seam_out, d, pad, 0, E.L.ng);
+      long long tot = 1;
+      for (int ax = 0; ax < d->ndim; ++ax) tot *= d->n[ax] + 2 * d->num_ghost;
+      if (E.is32) ghost_fill_kernel<float><<<blocks_for(tot), 256, 0, E.st>>>(E.g, d->num_ghost, 3, 2, b);
+      else ghost_fill_kernel<double><<<blocks_for(tot), 256, 0, E.st>>>(E.g, d->num_ghost, 3, 2, b);
+      CK(cudaGetLastError());
+    }
+  }
+  if (stats) {
+    Ctl* m;
+    if ((rc = read_ctl(E, &m))) return rc;
+    stats->steps = 1;
+    stats->magnetic_iterations = m->mag_iter;
+    stats->time = 0;
+    stats->last_dt = m->dt_d;
+    stats->kernel_launches = E.launches;
+    if (m->not_converged) return fail(AMX_ENOTCONVERGED, "magnetic fixed point hit the 1000-iteration cap");
+  }
+  return AMX_OK;
+}
+
+int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpadded_out, double t_end,
+                  int64_t max_steps, void* ws, void* stream, amx_stats* stats) {
+  int rc = check_common(d, unpadded_in, unpadded_out);
+  if (rc) return rc;
+  if (!ws) return fail(AMX_EINVAL, "ws is null");
+  if (d->bc[0][0] == AMX_BC_HALO || d->bc[0][1] == AMX_BC_HALO)
+    return fail(AMX_EUNSUPPORTED, "amx_integrate needs whole-domain boundaries; slab ranks use the stage-level entry points");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  const Layout& L = E.L;
+  CK(cudaMemsetAsync(E.ctl, 0, sizeof(Ctl), E.st));
+  const View vin = E.user_unpadded(unpadded_in);
+  const View S[2] = {E.internal(L.off_S[0]), E.internal(L.off_S[1])};
+  // wave bounds of the initial state (time_integration.py:643-653 on the first pass)
+  CK(E.alpha_of(vin, nullptr, false));
+  const DtPar p = E.dtpar(t_end);
+  int kspec = d->dtype == AMX_F32 ? 4 : 8;
+  long long issued = 0;
+  const int lookahead = d->mhd ? 1 : 8;  // hydro steps enqueued between host looks at the loop state
+  Ctl* m = nullptr;
+  for (;;) {
+    for (int k = 0; k < lookahead; ++k, ++issued) {
+      ++E.launches;
+      if (E.is32) step_begin_kernel<float><<<1, 1, 0, E.st>>>(E.ctl, p, (long long)max_steps);
+      else step_begin_kernel<double><<<1, 1, 0, E.st>>>(E.ctl, p, (long long)max_steps);
+      CK(cudaGetLastError());
+      const View& sin = issued == 0 ? vin : S[(issued - 1) & 1];
+      if ((rc = run_step(E, sin, S[issued & 1], &kspec))) return rc;
+      ++E.launches;
+      if (E.is32) step_end_kernel<float><<<1, 1, 0, E.st>>>(E.ctl);
+      else step_end_kernel<double><<<1, 1, 0, E.st>>>(E.ctl);
+      CK(cudaGetLastError());
+    }
+    if ((rc = read_ctl(E, &m))) return rc;
+    if (m->done || !(m->time_d < p.t_end) || (max_steps >= 0 && m->steps >= max_steps)) break;
+  }
+  // a step that found the loop finished wrote nothing: the state lives where step `steps` put it
+  const long long steps = m->steps;
+  const size_t bytes = (size_t)L.cells * L.esz;
+  if (steps == 0) {
+    for (int r = 0; r < L.nv; ++r)
+      CK(cudaMemcpyAsync((char*)unpadded_out + r * bytes, (const char*)unpadded_in + r * bytes, bytes,
+                         cudaMemcpyDeviceToDevice, E.st));
+  } else {
+    const char* src = E.ws + L.off_S[(steps - 1) & 1];
+    for (int r = 0; r < L.nv; ++r)
+      CK(cudaMemcpyAsync((char*)unpadded_out + r * bytes, src + r * L.row_bytes, bytes, cudaMemcpyDeviceToDevice, E.st));
+  }
+  CK(cudaStreamSynchronize(E.st));
+  if (stats) {
+    stats->steps = steps;
+    stats->magnetic_iterations = m->mag_iters_total;
+    stats->time = m->time_d;
+    stats->last_dt = m->dt_d;
+    stats->kernel_launches = E.launches;
+  }
+  if (m->not_converged) return fail(AMX_ENOTCONVERGED, "magnetic fixed point hit the 1000-iteration cap");
+  return AMX_OK;
+}
+
+// ---- slab-decomposed building blocks ---------------------------------------------------------
+int amx_alpha(const amx_desc* d, const void* gas, void* alpha_out, void* ws, void* stream) {
+  int rc = check_common(d, gas, alpha_out);
+  if (rc) return rc;
+  if (!ws) return fail(AMX_EINVAL, "ws is null");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  CK(E.alpha_of(E.user_internal(gas), alpha_out, false));
+  return AMX_OK;
+}
+
+int amx_dt_from_alpha(const amx_desc* d, const void* alpha_dev, const void* time_dev, double t_end,
+                      void* dt_out, void* stream) {
+  int rc = check_common(d, alpha_dev, dt_out);
+  if (rc) return rc;
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, nullptr, stream);
+  const DtPar p = E.dtpar(t_end);
+  if (E.is32) dt_only_kernel<float><<<1, 1, 0, E.st>>>((const float*)alpha_dev, (const float*)time_dev, p, (float*)dt_out);
+  else dt_only_kernel<double><<<1, 1, 0, E.st>>>((const double*)alpha_dev, (const double*)time_dev, p, (double*)dt_out);
+  CK(cudaGetLastError());
+  return AMX_OK;
+}
+
+int amx_hydro_stage(const amx_desc* d, const void* gas_in, const void* gas0_or_null, void* gas_out,
+                    const void* dt_dev, double dt_scale, const void* alpha_lf, void* alpha_out, void* ws,
+                    void* stream) {
+  int rc = check_common(d, gas_in, gas_out);
+  if (rc) return rc;
+  if (!ws || !dt_dev) return fail(AMX_EINVAL, "ws / dt_dev is null");
+  if (d->riemann == AMX_LAX_FRIEDRICHS && !alpha_lf) return fail(AMX_EINVAL, "Lax-Friedrichs needs alpha_lf");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  const View in = E.user_internal(gas_in), out = E.user_internal(gas_out);
+  View in0;
+  if (gas0_or_null) in0 = E.user_internal(gas0_or_null);
+  CK(E.stage(in, gas0_or_null ? &in0 : nullptr, out, dt_dev, dt_scale, alpha_lf, alpha_out != nullptr, alpha_out, false));
+  return AMX_OK;
+}
+
+int amx_split_sweep(const amx_desc* d, const void* gas_in, void* gas_out, int axis, const void* dt_dev,
+                    double dt_scale, const void* alpha_lf, void* alpha_out, void* ws, void* stream) {
+  int rc = check_common(d, gas_in, gas_out);
+  if (rc) return rc;
+  if (!ws || !dt_dev) return fail(AMX_EINVAL, "ws / dt_dev is null");
+  if (axis < 1 || axis > d->ndim) return fail(AMX_EINVAL, "axis out of range");
+  if (d->riemann == AMX_LAX_FRIEDRICHS && !alpha_lf) return fail(AMX_EINVAL, "Lax-Friedrichs needs alpha_lf");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  CK(E.sweep(E.user_internal(gas_in), E.user_internal(gas_out), axis, dt_dev, dt_scale, alpha_lf,
+             alpha_out != nullptr, alpha_out, false));
+  return AMX_OK;
+}
+
+int amx_magnetic_iter(const amx_desc* d, const void* B0, const void* gas0, const void* bvk_or_null, void* bvk1,
+                      const void* dt_dev, void* change_out, void* ws, void* stream) {
+  int rc = check_common(d, B0, bvk1);
+  if (rc) return rc;
+  if (!ws || !dt_dev || !gas0 || !change_out) return fail(AMX_EINVAL, "null pointer");
+  if (!d->mhd) return fail(AMX_EINVAL, "descriptor is not MHD");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  const View vB0 = E.user_internal(B0), vg = E.user_internal(gas0), vk1 = E.user_internal(bvk1);
+  View vk;
+  if (bvk_or_null) vk = E.user_internal(bvk_or_null);
+  CK(E.mag_iter(vB0, vg, bvk_or_null ? &vk : nullptr, vk1, dt_dev, bvk_or_null ? 1 : 0, false));
+  CK(E.finalize_change(change_out, false));
+  return AMX_OK;
+}
+
+int amx_magnetic_final(const amx_desc* d, void* gas_inout, const void* bv_final, void* B_out, void* alpha_out,
+                       void* ws, void* stream) {
+  int rc = check_common(d, gas_inout, bv_final);
+  if (rc) return rc;
+  if (!ws || !B_out) return fail(AMX_EINVAL, "null pointer");
+  if (!d->mhd) return fail(AMX_EINVAL, "descriptor is not MHD");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  const View X[2] = {E.user_internal(bv_final), E.user_internal(bv_final)};
+  MagFinalArgs a;
+  a.g = E.g; a.np = E.np; a.gas = E.user_internal(gas_inout); a.B_out = E.user_internal(B_out);
+  a.X[0] = X[0]; a.X[1] = X[1]; a.ctl_ro = nullptr; a.fixed_final = 0;
+  a.alpha_slots = alpha_out ? E.aslots() : nullptr;
+  CK(E.strict ? amx_strict::launch_mag_final(a, E.st) : amx_fast::launch_mag_final(a, E.st));
+  if (alpha_out) CK(E.finalize_alpha(alpha_out, false));
+  return AMX_OK;
+}
+
+}  // extern "C"

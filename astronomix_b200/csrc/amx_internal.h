@@ -1,0 +1,141 @@
+// amx_internal.h -- plain structs shared by the C-ABI layer (amx_api.cu) and the two
+// arithmetic flavours of the kernel translation unit (amx_kernels.cu compiled with
+// AMX_STRICT=0 -> namespace amx_fast, AMX_STRICT=1 -> namespace amx_strict).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace amx {
+
+constexpr int kAlphaSlots = 1024;  // spread of the per-block wave-bound atomics
+
+// boundary codes (include/amx.h)
+enum : int { BC_OPEN = 0, BC_REFLECTIVE = 1, BC_PERIODIC = 2, BC_HALO = 4 };
+
+// Strided view of a [rows][x][y][z] array; p points at row 0, FIRST ACTIVE cell.
+struct View {
+  void* p;
+  long long s[3];  // element strides of x, y, z (absent axes: 0)
+  long long vs;    // element stride between rows
+};
+
+struct Geom {
+  int nd;
+  int n[3];      // active cells per axis (absent axes: 1)
+  int bc[3][2];  // boundary code per axis and side
+};
+
+struct NumPar {
+  int dtype;  // 0 f32, 1 f64
+  int rs, lim;
+  double dx, gamma;
+};
+
+// Device-resident loop control.  Scalars are stored as double AND in the working type where
+// the arithmetic must be done in the working type (time, dt); see amx_kernels.cu.
+struct Ctl {
+  double time_d, dt_d;       // mirrors for the host (exact conversions of the T values)
+  float time_f, dt_f;        // working-type copies when dtype == f32
+  double alpha[3];           // finalised wave bounds of the latest gas state (T values, widened)
+  float alpha_f[3];          // the same as float (what fp32 Lax-Friedrichs stages read)
+  float pad1;
+  double change[2];          // finalised fixed-point change norms
+  int done;                  // time loop ended (t >= t_end or step cap reached)
+  int mag_active;            // fixed point still iterating
+  int mag_iter;              // while-body iterations executed this step
+  int mag_final;             // buffer index holding the converged iterate
+  int not_converged;         // sticky: 1000-iteration cap was hit
+  int pad0;
+  long long steps;
+  long long mag_iters_total;
+  unsigned long long alpha_slots[3][kAlphaSlots];  // bit patterns of non-negative T values
+  unsigned long long change_slots[2][kAlphaSlots];
+};
+
+struct StageArgs {
+  Geom g;
+  NumPar np;
+  View in;          // primitive gas state entering the stage
+  View in0;         // p == nullptr: plain stage; else RK2 combine with this state (Q11)
+  View out;
+  const Ctl* ctl_ro;  // nullable: skip the launch's work when ctl->done
+  const void* dt;     // device scalar of the working type
+  double dt_scale;    // 1 or 0.5 (exact)
+  const void* alpha_lf;  // device, 3 values of the working type (Lax-Friedrichs only)
+  unsigned long long* alpha_slots;  // nullable: [3][kAlphaSlots] wave bounds of the result
+};
+
+struct SweepArgs {
+  Geom g;
+  NumPar np;
+  View in, out;
+  const Ctl* ctl_ro;
+  const void* dt;
+  double dt_scale;
+  int axis;  // 1-based sweep axis
+  int first_order;
+  const void* alpha_lf;
+  unsigned long long* alpha_slots;
+};
+
+struct MagIterArgs {
+  Geom g;
+  NumPar np;
+  View B0;    // 3 rows
+  View gas0;  // ND+2 rows: rho (row 0) and v0 (rows 1..ND; v_z = 0 in 2-D)
+  View Bk, vk;    // 3 rows each; Bk.p == nullptr: first iterate (R_k = R_0)
+  View Bk1, vk1;  // 3 rows each
+  const Ctl* ctl_ro;  // nullable: skip when done or !mag_active
+  int first;          // launch 0 of the fixed point never skips on mag_active
+  int midpoint;       // IMPLICIT_MIDPOINT (1) or IMPLICIT_EULER (0)
+  const void* dt;
+  unsigned long long* change_slots;  // [2][kAlphaSlots]
+};
+
+struct MagFinalArgs {
+  Geom g;
+  NumPar np;
+  View gas;       // in/out: v rows and p row are rewritten
+  View B_out;     // 3 rows
+  View X[2];      // the two iterate buffers, 6 rows each (B then v)
+  const Ctl* ctl_ro;
+  int fixed_final;  // >= 0: use this buffer index instead of ctl->mag_final
+  unsigned long long* alpha_slots;
+};
+
+struct AlphaArgs {
+  Geom g;
+  NumPar np;
+  View gas;
+  const Ctl* ctl_ro;
+  unsigned long long* alpha_slots;
+};
+
+struct FillArgs {  // ghost fill of a padded array (GHOST_CELLS seam arrays)
+  Geom g;
+  int dtype;
+  int ng;
+  int rows;
+  int type_handled;  // 0 gas, 1 velocity-only, 2 magnetic-only (Q12 flip rule)
+  View a;            // p at first ACTIVE cell of the padded array
+};
+
+struct CopyArgs {  // strided row copy (pad / unpad / concatenate)
+  Geom g;
+  int dtype;
+  int rows;
+  View src, dst;
+  int edge_pad;  // >0: dst is padded by this many cells, fill them edge-mode (np.pad 'edge')
+};
+
+#define AMX_DECLARE_LAUNCHERS                                                             \
+  cudaError_t launch_hydro_stage(const amx::StageArgs&, cudaStream_t);                    \
+  cudaError_t launch_split_sweep(const amx::SweepArgs&, cudaStream_t);                    \
+  cudaError_t launch_mag_iter(const amx::MagIterArgs&, cudaStream_t);                     \
+  cudaError_t launch_mag_final(const amx::MagFinalArgs&, cudaStream_t);                   \
+  cudaError_t launch_alpha(const amx::AlphaArgs&, cudaStream_t);
+
+}  // namespace amx
+
+namespace amx_fast { AMX_DECLARE_LAUNCHERS }
+namespace amx_strict { AMX_DECLARE_LAUNCHERS }

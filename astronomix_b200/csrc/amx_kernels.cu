@@ -1,0 +1,507 @@
+// amx_kernels.cu -- sm_100a kernels of the finite-volume (M)HD step, generic ("v1") set:
+// one thread per active cell, boundary conditions applied by index mapping on the halo
+// reads (so no ghost cells have to exist in memory), every stage fused into one launch:
+//   hydro_stage_kernel   BC -> cons -> per axis {limited slopes, L/R states, Riemann flux,
+//                        flux difference} -> prim [-> RK2 combine] -> wave-bound max
+//                        (reference: evolve_state.py:339-414, :456-469)
+//   split_sweep_kernel   one MUSCL-Hancock sweep (evolve_state.py:53-163)
+//   mag_iter_kernel      one evaluation of the Pang-Wu fixed point + change norms
+//                        (_magnetic_field_update.py:82-165)
+//   mag_final_kernel     velocity / pressure write-back (:208-240)
+//   alpha_kernel         max |u|+c per axis (_timestep_estimator.py:118-128)
+// The plane-streaming shared-memory kernels for the 3-D/2-D hot configurations live in
+// amx_tiled.cu and are selected by the API layer when the layout allows.
+//
+// Compiled twice: -DAMX_STRICT=0 (namespace amx_fast) and -DAMX_STRICT=1 -fmad=false
+// (namespace amx_strict).
+#include "amx_internal.h"
+#include "amx_math.cuh"
+
+#if AMX_STRICT
+#define AMX_NS amx_strict
+#else
+#define AMX_NS amx_fast
+#endif
+
+namespace AMX_NS {
+using namespace amx;
+
+// ---------------------------------------------------------------- indexing
+struct Idx3 { int i[3]; };
+
+// ghost index -> source index for boundary code bc; flip = the normal component changes sign
+template <int ND>
+AMX_DI int map_index(int i, int n, int bcl, int bcr, bool& flip) {
+  flip = false;
+  if (i < 0) {
+    if (bcl == BC_PERIODIC) return i + n;
+    if (bcl == BC_OPEN) return 0;
+    if (bcl == BC_REFLECTIVE) { flip = true; return (ND == 1) ? 0 : (-1 - i); }
+    return i;  // BC_HALO: ghost planes are resident
+  }
+  if (i >= n) {
+    if (bcr == BC_PERIODIC) return i - n;
+    if (bcr == BC_OPEN) return n - 1;
+    if (bcr == BC_REFLECTIVE) { flip = true; return (ND == 1) ? (n - 1) : (2 * n - 1 - i); }
+    return i;
+  }
+  return i;
+}
+
+template <typename T, int ND>
+AMX_DI Gas<T, ND> load_gas(const View& v, long long off) {
+  Gas<T, ND> s;
+  const T* p = static_cast<const T*>(v.p) + off;
+#pragma unroll
+  for (int k = 0; k < ND + 2; ++k) s.q[k] = __ldg(p + k * v.vs);
+  return s;
+}
+
+template <typename T, int ND>
+AMX_DI void store_gas(const View& v, long long off, const Gas<T, ND>& s) {
+  T* p = static_cast<T*>(v.p) + off;
+#pragma unroll
+  for (int k = 0; k < ND + 2; ++k) p[k * v.vs] = s.q[k];
+}
+
+template <int ND>
+AMX_DI long long offset_of(const View& v, const Idx3& c) {
+  long long o = (long long)c.i[0] * v.s[0];
+  if constexpr (ND > 1) o += (long long)c.i[1] * v.s[1];
+  if constexpr (ND > 2) o += (long long)c.i[2] * v.s[2];
+  return o;
+}
+
+// gas state of the cell `d` steps from c along axis a (0-based), boundary rules applied
+template <typename T, int ND>
+AMX_DI Gas<T, ND> load_neighbor(const View& v, const Geom& g, const Idx3& c, int a, int d) {
+  Idx3 q = c;
+  bool flip;
+  q.i[a] = map_index<ND>(c.i[a] + d, g.n[a], g.bc[a][0], g.bc[a][1], flip);
+  Gas<T, ND> s = load_gas<T, ND>(v, offset_of<ND>(v, q));
+  if (flip) s.q[a + 1] = -s.q[a + 1];
+  return s;
+}
+
+template <int ND>
+AMX_DI bool decode_cell(const Geom& g, Idx3& c) {
+  const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = g.n[0];
+  if constexpr (ND > 1) total *= g.n[1];
+  if constexpr (ND > 2) total *= g.n[2];
+  if (lin >= total) return false;
+  long long r = lin;
+  if constexpr (ND == 3) { c.i[2] = (int)(r % g.n[2]); r /= g.n[2]; }
+  if constexpr (ND >= 2) { c.i[1] = (int)(r % g.n[1]); r /= g.n[1]; }
+  c.i[0] = (int)r;
+  if constexpr (ND < 3) c.i[2] = 0;
+  if constexpr (ND < 2) c.i[1] = 0;
+  return true;
+}
+
+template <typename T>
+AMX_DI Consts<T> make_consts(const NumPar& np) {
+  Consts<T> c;
+  c.gamma = (T)np.gamma;
+  c.gm1 = c.gamma - T(1);
+  c.dx = (T)np.dx;
+  c.inv_dx = (T)(1.0 / np.dx);
+  c.half_dx = (T)(np.dx / 2);
+  c.va_eps = (T)(3 * np.dx);
+  return c;
+}
+
+// ---------------------------------------------------------------- block max -> slots
+AMX_DI unsigned long long bits_of(float v) { return (unsigned long long)__float_as_uint(v); }
+AMX_DI unsigned long long bits_of(double v) { return (unsigned long long)__double_as_longlong(v); }
+
+// max over the block of NV non-negative values per thread, one atomicMax per value into
+// slot (blockIdx mod kAlphaSlots).  All threads of the block must call.
+template <typename T, int NV>
+AMX_DI void block_max_to_slots(T (&v)[NV], unsigned long long* slots) {
+  __shared__ T red[NV][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] = rmax(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+    if (lane == 0) red[k][wid] = v[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      T m = lane < nw ? red[k][lane] : T(0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) atomicMax(slots + (size_t)k * kAlphaSlots + (blockIdx.x % kAlphaSlots), bits_of(m));
+    }
+  }
+}
+
+// ---------------------------------------------------------------- unsplit stage
+template <typename T, int ND, int RS, int LIM>
+__global__ void __launch_bounds__(256) hydro_stage_kernel(const StageArgs a) {
+  if (a.ctl_ro && a.ctl_ro->done) return;
+  const Consts<T> c = make_consts<T>(a.np);
+  Idx3 cell;
+  const bool active = decode_cell<ND>(a.g, cell);
+  T wb[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) wb[k] = T(0);
+  if (active) {
+    const T dt = *static_cast<const T*>(a.dt) * (T)a.dt_scale;
+    const Gas<T, ND> sc = load_gas<T, ND>(a.in, offset_of<ND>(a.in, cell));
+    Gas<T, ND> U = cons_from_prim(sc, c);
+#pragma unroll
+    for (int ax = 0; ax < ND; ++ax) {
+      const Gas<T, ND> sm2 = load_neighbor<T, ND>(a.in, a.g, cell, ax, -2);
+      const Gas<T, ND> sm1 = load_neighbor<T, ND>(a.in, a.g, cell, ax, -1);
+      const Gas<T, ND> sp1 = load_neighbor<T, ND>(a.in, a.g, cell, ax, +1);
+      const Gas<T, ND> sp2 = load_neighbor<T, ND>(a.in, a.g, cell, ax, +2);
+      T alpha = T(0);
+      if constexpr (RS == RS_LF) alpha = static_cast<const T*>(a.alpha_lf)[ax];
+      Gas<T, ND> lo_m, hi_m, lo_c, hi_c, lo_p, hi_p;
+      faces_unsplit(sm1, slopes<T, ND, LIM>(sm2, sm1, sc, a.np.lim, c), c, lo_m, hi_m);
+      faces_unsplit(sc, slopes<T, ND, LIM>(sm1, sc, sp1, a.np.lim, c), c, lo_c, hi_c);
+      faces_unsplit(sp1, slopes<T, ND, LIM>(sc, sp1, sp2, a.np.lim, c), c, lo_p, hi_p);
+      const Gas<T, ND> Fl = riemann<T, ND, RS>(hi_m, lo_c, ax + 1, alpha, c);  // interface i-1/2
+      const Gas<T, ND> Fr = riemann<T, ND, RS>(hi_c, lo_p, ax + 1, alpha, c);  // interface i+1/2
+#pragma unroll
+      for (int k = 0; k < ND + 2; ++k) U.q[k] = U.q[k] + (c.inv_dx * (Fl.q[k] - Fr.q[k])) * dt;
+    }
+    Gas<T, ND> s = prim_from_cons(U, c);
+    if (a.in0.p) {  // RK2-SSP combine: prim(0.5*(cons(s0) + cons(s2)))
+      const Gas<T, ND> s0 = load_gas<T, ND>(a.in0, offset_of<ND>(a.in0, cell));
+      const Gas<T, ND> U0 = cons_from_prim(s0, c), U2 = cons_from_prim(s, c);
+      Gas<T, ND> Um;
+#pragma unroll
+      for (int k = 0; k < ND + 2; ++k) Um.q[k] = T(0.5) * (U0.q[k] + U2.q[k]);
+      s = prim_from_cons(Um, c);
+    }
+    store_gas<T, ND>(a.out, offset_of<ND>(a.out, cell), s);
+    if (a.alpha_slots) {
+#pragma unroll
+      for (int k = 0; k < ND; ++k) wb[k] = wave_bound(s, k + 1, c);
+    }
+  }
+  if (a.alpha_slots) block_max_to_slots<T, ND>(wb, a.alpha_slots);
+}
+
+// ---------------------------------------------------------------- split MUSCL-Hancock sweep
+template <typename T, int ND, int RS, int LIM>
+__global__ void __launch_bounds__(256) split_sweep_kernel(const SweepArgs a) {
+  if (a.ctl_ro && a.ctl_ro->done) return;
+  const Consts<T> c = make_consts<T>(a.np);
+  Idx3 cell;
+  const bool active = decode_cell<ND>(a.g, cell);
+  T wb[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) wb[k] = T(0);
+  if (active) {
+    const T dt = *static_cast<const T*>(a.dt) * (T)a.dt_scale;
+    const int ax = a.axis - 1;
+    const Gas<T, ND> sc = load_gas<T, ND>(a.in, offset_of<ND>(a.in, cell));
+    Gas<T, ND> U = cons_from_prim(sc, c);
+    const Gas<T, ND> sm1 = load_neighbor<T, ND>(a.in, a.g, cell, ax, -1);
+    const Gas<T, ND> sp1 = load_neighbor<T, ND>(a.in, a.g, cell, ax, +1);
+    T alpha = T(0);
+    if constexpr (RS == RS_LF) alpha = static_cast<const T*>(a.alpha_lf)[ax];
+    Gas<T, ND> Fl, Fr;
+    if (a.first_order) {  // evolve_state.py:72-74
+      Fl = riemann<T, ND, RS>(sm1, sc, a.axis, alpha, c);
+      Fr = riemann<T, ND, RS>(sc, sp1, a.axis, alpha, c);
+    } else {
+      const Gas<T, ND> sm2 = load_neighbor<T, ND>(a.in, a.g, cell, ax, -2);
+      const Gas<T, ND> sp2 = load_neighbor<T, ND>(a.in, a.g, cell, ax, +2);
+      const T hdt = dt / T(2);
+      Gas<T, ND> lo_m, hi_m, lo_c, hi_c, lo_p, hi_p;
+      faces_muscl(sm1, slopes<T, ND, LIM>(sm2, sm1, sc, a.np.lim, c), a.axis, hdt, c, lo_m, hi_m);
+      faces_muscl(sc, slopes<T, ND, LIM>(sm1, sc, sp1, a.np.lim, c), a.axis, hdt, c, lo_c, hi_c);
+      faces_muscl(sp1, slopes<T, ND, LIM>(sc, sp1, sp2, a.np.lim, c), a.axis, hdt, c, lo_p, hi_p);
+      Fl = riemann<T, ND, RS>(hi_m, lo_c, a.axis, alpha, c);
+      Fr = riemann<T, ND, RS>(hi_c, lo_p, a.axis, alpha, c);
+    }
+#pragma unroll
+    for (int k = 0; k < ND + 2; ++k) U.q[k] = U.q[k] + (c.inv_dx * (Fl.q[k] - Fr.q[k])) * dt;
+    const Gas<T, ND> s = prim_from_cons(U, c);
+    store_gas<T, ND>(a.out, offset_of<ND>(a.out, cell), s);
+    if (a.alpha_slots) {
+#pragma unroll
+      for (int k = 0; k < ND; ++k) wb[k] = wave_bound(s, k + 1, c);
+    }
+  }
+  if (a.alpha_slots) block_max_to_slots<T, ND>(wb, a.alpha_slots);
+}
+
+// ---------------------------------------------------------------- wave bounds of a state
+template <typename T, int ND>
+__global__ void __launch_bounds__(256) alpha_kernel(const AlphaArgs a) {
+  if (a.ctl_ro && a.ctl_ro->done) return;
+  const Consts<T> c = make_consts<T>(a.np);
+  Idx3 cell;
+  const bool active = decode_cell<ND>(a.g, cell);
+  T wb[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) wb[k] = T(0);
+  if (active) {
+    const Gas<T, ND> s = load_gas<T, ND>(a.gas, offset_of<ND>(a.gas, cell));
+#pragma unroll
+    for (int k = 0; k < ND; ++k) wb[k] = wave_bound(s, k + 1, c);
+  }
+  block_max_to_slots<T, ND>(wb, a.alpha_slots);
+}
+
+// ---------------------------------------------------------------- magnetic fixed point
+template <typename T> struct V3 { T x[3]; };
+
+// _vector_maths.py:6-12
+template <typename T>
+AMX_DI T cross_c(const V3<T>& a, const V3<T>& b, int comp) {
+  if (comp == 0) return a.x[1] * b.x[2] - a.x[2] * b.x[1];
+  if (comp == 1) return a.x[2] * b.x[0] - a.x[0] * b.x[2];
+  return a.x[0] * b.x[1] - a.x[1] * b.x[0];
+}
+
+// B and v of the fixed-point argument at one (mapped) cell: (R_k + R_0)/2 or R_k.
+// Reflective sides flip 3-vector component `axis` (1-based) -- i.e. the wrong one, and none
+// for the z axis -- exactly like the reference (Q12).
+template <typename T, int ND>
+AMX_DI void load_arg(const MagIterArgs& a, const Idx3& c, int ax, int d, V3<T>& B, V3<T>& v) {
+  Idx3 q = c;
+  bool flip = false;
+  if (d != 0) q.i[ax] = map_index<ND>(c.i[ax] + d, a.g.n[ax], a.g.bc[ax][0], a.g.bc[ax][1], flip);
+  const int fc = ax + 1;  // flipped component index
+  const long long o0 = offset_of<ND>(a.B0, q), og = offset_of<ND>(a.gas0, q);
+  const T* pB0 = static_cast<const T*>(a.B0.p) + o0;
+  const T* pg = static_cast<const T*>(a.gas0.p) + og;
+  V3<T> B0, v0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    B0.x[k] = __ldg(pB0 + k * a.B0.vs);
+    v0.x[k] = (k < ND) ? __ldg(pg + (k + 1) * a.gas0.vs) : T(0);
+  }
+  if (flip && fc < 3) { B0.x[fc] = -B0.x[fc]; v0.x[fc] = -v0.x[fc]; }
+  if (a.Bk.p == nullptr) {  // first iterate: (R_0 + R_0)/2 == R_0 exactly
+    B = B0; v = v0;
+    return;
+  }
+  const long long ok = offset_of<ND>(a.Bk, q);
+  const T* pBk = static_cast<const T*>(a.Bk.p) + ok;
+  const T* pvk = static_cast<const T*>(a.vk.p) + offset_of<ND>(a.vk, q);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    T bk = __ldg(pBk + k * a.Bk.vs), vk = __ldg(pvk + k * a.vk.vs);
+    if (flip && k == fc) { bk = -bk; vk = -vk; }
+    if (a.midpoint) { B.x[k] = (bk + B0.x[k]) / T(2); v.x[k] = (vk + v0.x[k]) / T(2); }
+    else { B.x[k] = bk; v.x[k] = vk; }
+  }
+}
+
+// central difference 0.5*(f[+1]-f[-1])/dx (_vector_maths.py:55-100)
+template <typename T>
+AMX_DI T cdiff(T fp, T fm, const Consts<T>& c) {
+#if AMX_STRICT
+  return (T(0.5) * (fp - fm)) / c.dx;
+#else
+  return (T(0.5) * (fp - fm)) * c.inv_dx;
+#endif
+}
+
+template <typename T, int ND>
+__global__ void __launch_bounds__(256) mag_iter_kernel(const MagIterArgs a) {
+  if (a.ctl_ro && (a.ctl_ro->done || (!a.first && !a.ctl_ro->mag_active))) return;
+  const Consts<T> c = make_consts<T>(a.np);
+  Idx3 cell;
+  const bool active = decode_cell<ND>(a.g, cell);
+  T ch[2] = {T(0), T(0)};
+  if (active) {
+    const T dt = *static_cast<const T*>(a.dt);
+    V3<T> Bc, vc;
+    load_arg<T, ND>(a, cell, 0, 0, Bc, vc);
+    // E = B x v and B at the two neighbours of every axis
+    T dE[3][3], dB[3][3];  // [axis][component] central differences
+#pragma unroll
+    for (int ax = 0; ax < ND; ++ax) {
+      V3<T> Bp, vp, Bm, vm;
+      load_arg<T, ND>(a, cell, ax, +1, Bp, vp);
+      load_arg<T, ND>(a, cell, ax, -1, Bm, vm);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        dE[ax][k] = cdiff(cross_c(Bp, vp, k), cross_c(Bm, vm, k), c);
+        dB[ax][k] = cdiff(Bp.x[k], Bm.x[k], c);
+      }
+    }
+    V3<T> curlE, curlB;
+    if constexpr (ND == 3) {  // curl3D
+      curlE.x[0] = dE[1][2] - dE[2][1]; curlE.x[1] = dE[2][0] - dE[0][2]; curlE.x[2] = dE[0][1] - dE[1][0];
+      curlB.x[0] = dB[1][2] - dB[2][1]; curlB.x[1] = dB[2][0] - dB[0][2]; curlB.x[2] = dB[0][1] - dB[1][0];
+    } else {  // curl2D
+      curlE.x[0] = dE[1][2]; curlE.x[1] = -dE[0][2]; curlE.x[2] = dE[0][1] - dE[1][0];
+      curlB.x[0] = dB[1][2]; curlB.x[1] = -dB[0][2]; curlB.x[2] = dB[0][1] - dB[1][0];
+    }
+    // R_0 at the centre and rho
+    const long long o0 = offset_of<ND>(a.B0, cell), og = offset_of<ND>(a.gas0, cell);
+    const T* pB0 = static_cast<const T*>(a.B0.p) + o0;
+    const T* pg = static_cast<const T*>(a.gas0.p) + og;
+    const T rho = __ldg(pg);
+    T Bn[3], vn[3], dBk = T(0), dvk = T(0);
+    const long long ob = offset_of<ND>(a.Bk1, cell), ov = offset_of<ND>(a.vk1, cell);
+    T* pB1 = static_cast<T*>(a.Bk1.p) + ob;
+    T* pv1 = static_cast<T*>(a.vk1.p) + ov;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const T B0k = __ldg(pB0 + k * a.B0.vs);
+      const T v0k = (k < ND) ? __ldg(pg + (k + 1) * a.gas0.vs) : T(0);
+      const T phiB = rdiv(cross_c(Bc, curlB, k), rho);
+      Bn[k] = B0k - dt * curlE.x[k];
+      vn[k] = v0k - dt * phiB;
+      T bk = B0k, vk = v0k;  // R_k at the centre (R_0 on the first iterate)
+      if (a.Bk.p) {
+        bk = __ldg(static_cast<const T*>(a.Bk.p) + offset_of<ND>(a.Bk, cell) + k * a.Bk.vs);
+        vk = __ldg(static_cast<const T*>(a.vk.p) + offset_of<ND>(a.vk, cell) + k * a.vk.vs);
+      }
+      dBk = dBk + sq(rabs(bk - Bn[k]));
+      dvk = dvk + sq(rabs(vk - vn[k]));
+      pB1[k * a.Bk1.vs] = Bn[k];
+      pv1[k * a.vk1.vs] = vn[k];
+    }
+    ch[0] = rsqrt_(dBk);
+    ch[1] = rsqrt_(dvk);
+  }
+  block_max_to_slots<T, 2>(ch, a.change_slots);
+}
+
+// _magnetic_field_update.py:208-240 (gamma hard-coded 5/3, Q4; 2-D drops v_z, Q5)
+template <typename T, int ND>
+__global__ void __launch_bounds__(256) mag_final_kernel(const MagFinalArgs a) {
+  if (a.ctl_ro && a.ctl_ro->done) return;
+  const Consts<T> c = make_consts<T>(a.np);
+  Idx3 cell;
+  const bool active = decode_cell<ND>(a.g, cell);
+  T wb[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) wb[k] = T(0);
+  if (active) {
+    const int fin = a.fixed_final >= 0 ? a.fixed_final : a.ctl_ro->mag_final;
+    const View& X = a.X[fin];
+    const long long ox = offset_of<ND>(X, cell), og = offset_of<ND>(a.gas, cell), ob = offset_of<ND>(a.B_out, cell);
+    const T* px = static_cast<const T*>(X.p) + ox;
+    T* pg = static_cast<T*>(a.gas.p) + og;
+    T* pb = static_cast<T*>(a.B_out.p) + ob;
+    Gas<T, ND> s = load_gas<T, ND>(a.gas, og);
+    T n0 = T(0), nn = T(0), vn[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      pb[k * a.B_out.vs] = px[k * X.vs];
+      vn[k] = px[(3 + k) * X.vs];
+      const T v0k = (k < ND) ? s.q[k + 1] : T(0);
+      n0 = n0 + sq(rabs(v0k));
+      nn = nn + sq(rabs(vn[k]));
+    }
+    const T g53m1 = (T)(5.0 / 3.0 - 1.0);
+    const T rho = s.q[0];
+#if AMX_STRICT
+    n0 = sq(rsqrt_(n0));
+    nn = sq(rsqrt_(nn));
+#endif
+    const T E = rdiv(s.q[ND + 1], g53m1) + (T(0.5) * rho) * n0;
+    const T E2 = E - (T(0.5) * rho) * n0 + (T(0.5) * rho) * nn;
+    const T p2 = (g53m1 * rho) * (rdiv(E2, rho) - T(0.5) * nn);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) { s.q[k + 1] = vn[k]; pg[(k + 1) * a.gas.vs] = vn[k]; }
+    s.q[ND + 1] = p2;
+    pg[(ND + 1) * a.gas.vs] = p2;
+    if (a.alpha_slots) {
+#pragma unroll
+      for (int k = 0; k < ND; ++k) wb[k] = wave_bound(s, k + 1, c);
+    }
+  }
+  if (a.alpha_slots) block_max_to_slots<T, ND>(wb, a.alpha_slots);
+}
+
+// ---------------------------------------------------------------- launchers
+template <int ND>
+static inline unsigned grid_for(const Geom& g) {
+  long long total = g.n[0];
+  if (ND > 1) total *= g.n[1];
+  if (ND > 2) total *= g.n[2];
+  return (unsigned)((total + 255) / 256);
+}
+
+#define AMX_DISPATCH_ND(ND_, ...)            \
+  switch (ND_) {                              \
+    case 1: { constexpr int ND = 1; __VA_ARGS__ } break; \
+    case 2: { constexpr int ND = 2; __VA_ARGS__ } break; \
+    case 3: { constexpr int ND = 3; __VA_ARGS__ } break; \
+    default: return cudaErrorInvalidValue;    \
+  }
+
+#define AMX_DISPATCH_RS(RS_, ...)                         \
+  switch (RS_) {                                           \
+    case RS_HLL: { constexpr int RS = RS_HLL; __VA_ARGS__ } break;        \
+    case RS_HLLC: { constexpr int RS = RS_HLLC; __VA_ARGS__ } break;      \
+    case RS_HLLC_LM: { constexpr int RS = RS_HLLC_LM; __VA_ARGS__ } break; \
+    case RS_LF: { constexpr int RS = RS_LF; __VA_ARGS__ } break;          \
+    default: return cudaErrorInvalidValue;                 \
+  }
+
+template <typename T>
+static cudaError_t launch_hydro_stage_t(const StageArgs& a, cudaStream_t st) {
+  AMX_DISPATCH_ND(a.g.nd, AMX_DISPATCH_RS(a.np.rs, {
+    const unsigned grid = grid_for<ND>(a.g);
+    if (a.np.lim == LIM_MINMOD) hydro_stage_kernel<T, ND, RS, LIM_MINMOD><<<grid, 256, 0, st>>>(a);
+    else hydro_stage_kernel<T, ND, RS, -1><<<grid, 256, 0, st>>>(a);
+  }))
+  return cudaGetLastError();
+}
+cudaError_t launch_hydro_stage(const StageArgs& a, cudaStream_t st) {
+  return a.np.dtype == 0 ? launch_hydro_stage_t<float>(a, st) : launch_hydro_stage_t<double>(a, st);
+}
+
+template <typename T>
+static cudaError_t launch_split_sweep_t(const SweepArgs& a, cudaStream_t st) {
+  AMX_DISPATCH_ND(a.g.nd, AMX_DISPATCH_RS(a.np.rs, {
+    const unsigned grid = grid_for<ND>(a.g);
+    if (a.np.lim == LIM_MINMOD) split_sweep_kernel<T, ND, RS, LIM_MINMOD><<<grid, 256, 0, st>>>(a);
+    else split_sweep_kernel<T, ND, RS, -1><<<grid, 256, 0, st>>>(a);
+  }))
+  return cudaGetLastError();
+}
+cudaError_t launch_split_sweep(const SweepArgs& a, cudaStream_t st) {
+  return a.np.dtype == 0 ? launch_split_sweep_t<float>(a, st) : launch_split_sweep_t<double>(a, st);
+}
+
+template <typename T>
+static cudaError_t launch_mag_iter_t(const MagIterArgs& a, cudaStream_t st) {
+  if (a.g.nd == 2) mag_iter_kernel<T, 2><<<grid_for<2>(a.g), 256, 0, st>>>(a);
+  else if (a.g.nd == 3) mag_iter_kernel<T, 3><<<grid_for<3>(a.g), 256, 0, st>>>(a);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+cudaError_t launch_mag_iter(const MagIterArgs& a, cudaStream_t st) {
+  return a.np.dtype == 0 ? launch_mag_iter_t<float>(a, st) : launch_mag_iter_t<double>(a, st);
+}
+
+template <typename T>
+static cudaError_t launch_mag_final_t(const MagFinalArgs& a, cudaStream_t st) {
+  if (a.g.nd == 2) mag_final_kernel<T, 2><<<grid_for<2>(a.g), 256, 0, st>>>(a);
+  else if (a.g.nd == 3) mag_final_kernel<T, 3><<<grid_for<3>(a.g), 256, 0, st>>>(a);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+cudaError_t launch_mag_final(const MagFinalArgs& a, cudaStream_t st) {
+  return a.np.dtype == 0 ? launch_mag_final_t<float>(a, st) : launch_mag_final_t<double>(a, st);
+}
+
+template <typename T>
+static cudaError_t launch_alpha_t(const AlphaArgs& a, cudaStream_t st) {
+  AMX_DISPATCH_ND(a.g.nd, { alpha_kernel<T, ND><<<grid_for<ND>(a.g), 256, 0, st>>>(a); })
+  return cudaGetLastError();
+}
+cudaError_t launch_alpha(const AlphaArgs& a, cudaStream_t st) {
+  return a.np.dtype == 0 ? launch_alpha_t<float>(a, st) : launch_alpha_t<double>(a, st);
+}
+
+}  // namespace AMX_NS

@@ -1,0 +1,217 @@
+"""Host-side mirror of the reference's public entry point and its two per-step seams.
+
+``time_integration(primitive_state, config, params, registered_variables, ...)`` keeps
+the reference's signature (astronomix/time_stepping/time_integration.py:61-68) and
+returns the unpadded primitive state; ``_evolve_state_fv`` and ``_cfl_time_step`` keep
+the signatures of the functions the loop body calls
+(_finite_volume/_state_evolution/evolve_state.py:496-506,
+_finite_volume/_timestep_estimation/_timestep_estimator.py:94-103) and operate on the
+same (padded, in GHOST_CELLS mode) arrays.  All arithmetic happens in libamx (CUDA);
+PyTorch only owns device memory and the stream.  NumPy arrays are staged through pinned
+host memory; torch CUDA tensors are used in place.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import option_classes as oc
+from .registered_variables import RegisteredVariables
+
+
+class StateStruct(NamedTuple):
+    """data_classes/simulation_snapshot_data.py:218 (only the field the FV path touches)."""
+
+    primitive_state: object = None
+
+
+class IntegrationInfo(NamedTuple):
+    steps: int
+    time: float
+    last_dt: float
+    magnetic_iterations: int
+    kernel_launches: int
+
+
+#: statistics of the most recent time_integration call on this process
+last_info: Optional[IntegrationInfo] = None
+
+_TORCH_DTYPES = {torch.float32: _lib.AMX_F32, torch.float64: _lib.AMX_F64}
+
+
+def _reject_unsupported(config, registered_variables=None):
+    """Options that leave the hot path of SURVEY.md §8 raise instead of being ignored."""
+    if config.solver_mode != oc.FINITE_VOLUME:
+        raise NotImplementedError("only solver_mode=FINITE_VOLUME is built (SURVEY.md §8)")
+    if config.geometry != oc.CARTESIAN:
+        raise NotImplementedError("only CARTESIAN geometry is built (spherical 1-D is out of scope)")
+    off = {
+        "self_gravity": config.self_gravity,
+        "return_snapshots": config.return_snapshots,
+        "activate_snapshot_callback": config.activate_snapshot_callback,
+        "fixed_timestep": config.fixed_timestep,
+        "source_term_aware_timestep": config.source_term_aware_timestep,
+        "runtime_debugging": config.runtime_debugging,
+        "turbulent_forcing": config.turbulent_forcing_config.turbulent_forcing,
+        "stellar_wind": config.wind_config.stellar_wind,
+        "cosmic_rays": config.cosmic_ray_config.cosmic_rays,
+        "cooling": config.cooling_config.cooling,
+        "neural_net_force": config.neural_net_force_config.neural_net_force,
+        "cnn_mhd_corrector": config.cnn_mhd_corrector_config.cnn_mhd_corrector,
+    }
+    on = [k for k, v in off.items() if v]
+    if on:
+        raise NotImplementedError(f"options outside the finite-volume hot path are not built: {on}")
+    if registered_variables is not None and (
+        registered_variables.wind_density_active or registered_variables.cosmic_ray_n_active
+    ):
+        raise NotImplementedError("extra registered variables (wind density, cosmic rays) are not built")
+
+
+def _to_device(state):
+    """-> (contiguous CUDA tensor, kind) ; kind remembers how to hand the result back."""
+    if isinstance(state, torch.Tensor):
+        if not state.is_cuda:
+            t = state.contiguous().pin_memory().cuda(non_blocking=True)
+            return t, "torch_cpu"
+        return state.contiguous(), "torch_cuda"
+    arr = np.ascontiguousarray(state)
+    if arr.dtype not in (np.float32, np.float64):
+        raise TypeError(f"state dtype must be float32 or float64, got {arr.dtype}")
+    t = torch.from_numpy(arr).pin_memory().cuda(non_blocking=True)
+    return t, "numpy"
+
+
+def _from_device(t, kind):
+    if kind == "torch_cuda":
+        return t
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy().copy() if kind == "numpy" else host.clone()
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_ws_cache = {}
+
+
+def _workspace(desc, device):
+    """Device scratch for a descriptor, cached by size (allocation is not part of a step)."""
+    lib = _lib.load()
+    nbytes = C.c_size_t()
+    _lib.check(lib.amx_workspace_bytes(C.byref(desc), C.byref(nbytes)))
+    key = (device, nbytes.value)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        _ws_cache.clear()
+        ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    base = ws.data_ptr()
+    return ws, C.c_void_p((base + 255) & ~255)
+
+
+def _check_state(t, nrows, ndim):
+    if t.dtype not in _TORCH_DTYPES:
+        raise TypeError(f"state dtype must be float32 or float64, got {t.dtype}")
+    if t.dim() != ndim + 1 or t.shape[0] != nrows:
+        raise ValueError(f"state must be [{nrows}, " + ", ".join(["n"] * ndim) + f"], got {tuple(t.shape)}")
+
+
+def time_integration(primitive_state, config, params, registered_variables: RegisteredVariables,
+                     snapshot_callable=None, sharding=None):
+    """Integrate to ``params.t_end``; drop-in for astronomix.time_integration (FV path)."""
+    global last_info
+    _lib.require_device()
+    _reject_unsupported(config, registered_variables)
+    if snapshot_callable is not None:
+        raise NotImplementedError("snapshot_callable is not built (SURVEY.md f3)")
+    if sharding is not None:
+        raise NotImplementedError(
+            "jax shardings do not exist here; multi-GPU runs use astronomix_b200.slab.SlabDriver"
+        )
+    struct = config.state_struct
+    state = primitive_state.primitive_state if struct else primitive_state
+    t, kind = _to_device(state)
+    _check_state(t, registered_variables.num_vars, config.dimensionality)
+    desc = _lib.make_desc(config, params, t.shape[1:], _TORCH_DTYPES[t.dtype])
+    ws, ws_ptr = _workspace(desc, t.device)
+    out = torch.empty_like(t)
+    stats = _lib.AmxStats()
+    lib = _lib.load()
+    with torch.cuda.device(t.device):
+        _lib.check(lib.amx_integrate(C.byref(desc), C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()),
+                                     float(params.t_end), -1, ws_ptr, _stream_ptr(), C.byref(stats)))
+    last_info = IntegrationInfo(stats.steps, stats.time, stats.last_dt, stats.magnetic_iterations,
+                                stats.kernel_launches)
+    res = _from_device(out, kind)
+    return StateStruct(primitive_state=res) if struct else res
+
+
+def integrate_steps(primitive_state, config, params, registered_variables, num_steps, arithmetic=None):
+    """time_integration truncated after ``num_steps`` steps (parity tests fix the step count)."""
+    global last_info
+    _lib.require_device()
+    _reject_unsupported(config, registered_variables)
+    t, kind = _to_device(primitive_state)
+    _check_state(t, registered_variables.num_vars, config.dimensionality)
+    desc = _lib.make_desc(config, params, t.shape[1:], _TORCH_DTYPES[t.dtype], arithmetic=arithmetic)
+    ws, ws_ptr = _workspace(desc, t.device)
+    out = torch.empty_like(t)
+    stats = _lib.AmxStats()
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().amx_integrate(C.byref(desc), C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()),
+                                             float(params.t_end), int(num_steps), ws_ptr, _stream_ptr(),
+                                             C.byref(stats)))
+    last_info = IntegrationInfo(stats.steps, stats.time, stats.last_dt, stats.magnetic_iterations,
+                                stats.kernel_launches)
+    return _from_device(out, kind)
+
+
+def _active_shape(config, seam_shape):
+    g = config.num_ghost_cells if config.boundary_handling == oc.GHOST_CELLS else 0
+    return tuple(int(s) - 2 * g for s in seam_shape)
+
+
+def _cfl_time_step(primitive_state, grid_spacing, dt_max, gamma, config, registered_variables, C_CFL=0.8):
+    """dt from the (padded) state; mirror of _timestep_estimator.py:94-218. Returns a 0-d tensor."""
+    _lib.require_device()
+    t, kind = _to_device(primitive_state)
+    params = oc.SimulationParams(C_cfl=float(C_CFL), gamma=float(gamma), dt_max=float(dt_max))
+    cfg = config._replace(grid_spacing=float(grid_spacing))
+    desc = _lib.make_desc(cfg, params, _active_shape(cfg, t.shape[1:]), _TORCH_DTYPES[t.dtype])
+    if t.shape[0] != registered_variables.num_vars:
+        # the MHD step calls the estimator with the full state; only the gas rows are read
+        pass
+    ws, ws_ptr = _workspace(desc, t.device)
+    dt = torch.empty((), dtype=t.dtype, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().amx_cfl(C.byref(desc), C.c_void_p(t.data_ptr()), C.c_void_p(dt.data_ptr()),
+                                       ws_ptr, _stream_ptr()))
+    return dt if kind == "torch_cuda" else dt.cpu().numpy()[()]
+
+
+def _evolve_state_fv(primitive_state, dt, gamma, gravitational_constant, config, params, helper_data,
+                     registered_variables):
+    """One step on the (padded) state; mirror of evolve_state.py:496-600."""
+    _lib.require_device()
+    _reject_unsupported(config, registered_variables)
+    t, kind = _to_device(primitive_state)
+    _check_state(t, registered_variables.num_vars, config.dimensionality)
+    desc = _lib.make_desc(config, params, _active_shape(config, t.shape[1:]), _TORCH_DTYPES[t.dtype], gamma=gamma)
+    ws, ws_ptr = _workspace(desc, t.device)
+    if isinstance(dt, torch.Tensor) and dt.is_cuda:
+        dt_dev = dt.to(t.dtype).reshape(())
+    else:
+        dt_dev = torch.tensor(float(dt), dtype=t.dtype).to(t.device)
+    out = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().amx_step(C.byref(desc), C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()),
+                                        C.c_void_p(dt_dev.data_ptr()), ws_ptr, _stream_ptr(), None))
+    return _from_device(out, kind)

@@ -1,0 +1,171 @@
+/* amx.h -- C ABI of libamx: the B200-native finite-volume (M)HD time step.
+ *
+ * This is the drop-in boundary.  The reference (leo1200/astronomix) has
+ * no FFI seam of its own: its step is a set of pure jitted Python functions.  Each entry
+ * point below names the reference function it replaces (paths relative to
+ * /root/reference/astronomix/).  A jax.ffi shim over exactly these symbols is shown in
+ * INTEGRATION.md; here the library is driven through ctypes (astronomix_b200/_lib.py).
+ *
+ * Conventions
+ *  - All state pointers are DEVICE pointers to C-contiguous arrays [var][x][y][z]
+ *    (z fastest; unused trailing axes absent) of desc->dtype.
+ *  - "unpadded" arrays have desc->n[a] cells per axis.  "seam" arrays are what the
+ *    reference's per-step functions see: padded by desc->num_ghost cells per side and
+ *    axis when desc->boundary_handling == AMX_GHOST_CELLS, unpadded for AMX_PERIODIC_ROLL.
+ *  - Nothing allocates, frees or synchronises unless stated; work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*).  `ws` is caller-owned scratch of
+ *    amx_workspace_bytes() bytes, 256-byte aligned.  `in` is never written; `in` and
+ *    `out` must not alias.
+ *  - Return value 0 = ok; otherwise an AMX_E* code and amx_last_error() holds a message
+ *    (thread-local).  No exceptions cross the ABI.  There is no CPU path: every compute
+ *    entry point fails with AMX_ECUDA when no CUDA device is usable.
+ */
+#ifndef AMX_H_
+#define AMX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMX_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define AMX_API __attribute__((visibility("default")))
+#else
+#define AMX_API
+#endif
+
+/* option codes = option_classes/simulation_config.py:20-93 */
+enum { AMX_F32 = 0, AMX_F64 = 1 };
+enum { AMX_MINMOD = 0, AMX_OSHER = 1, AMX_DOUBLE_MINMOD = 2, AMX_SUPERBEE = 3, AMX_VAN_ALBADA = 4 };
+enum { AMX_UNSPLIT = 0, AMX_SPLIT = 1 };
+enum { AMX_HLL = 0, AMX_HLLC = 1, AMX_HLLC_LM = 2, AMX_LAX_FRIEDRICHS = 3 };
+enum { AMX_RK2_SSP = 0, AMX_MUSCL = 1 };
+/* AMX_BC_HALO: the ghost planes on that side exist in memory and were filled by the caller
+ * (neighbour rank's cells in a slab decomposition); only valid on axis 0. */
+enum { AMX_BC_OPEN = 0, AMX_BC_REFLECTIVE = 1, AMX_BC_PERIODIC = 2, AMX_BC_HALO = 4 };
+enum { AMX_GHOST_CELLS = 0, AMX_PERIODIC_ROLL = 1 };
+enum { AMX_IMPLICIT_MIDPOINT = 0, AMX_IMPLICIT_EULER = 1 };
+/* arithmetic: FAST = contracted FMAs, reciprocal multiplies, approximate sqrt/div (fp32);
+ * STRICT = the reference's operation order with IEEE div/sqrt and no contraction. */
+enum { AMX_ARITH_FAST = 0, AMX_ARITH_STRICT = 1 };
+
+enum {
+  AMX_OK = 0,
+  AMX_EINVAL = 1,      /* malformed descriptor / null pointer */
+  AMX_EUNSUPPORTED = 2,/* valid reference option outside this library's scope */
+  AMX_ECUDA = 3,       /* CUDA runtime error (message has the cudaError string) */
+  AMX_ENOTCONVERGED = 4/* magnetic fixed point hit the 1000-iteration cap */
+};
+
+/* POD mirror of the static options (SimulationConfig + SimulationParams + registry). */
+typedef struct amx_desc {
+  int32_t abi_version;        /* AMX_ABI_VERSION */
+  int32_t ndim;               /* config.dimensionality: 1, 2, 3 */
+  int32_t n[3];               /* active cells per axis (x, y, z); 1 for absent axes */
+  int32_t dtype;              /* AMX_F32 / AMX_F64 (array dtype == JAX default dtype, Q13) */
+  int32_t mhd;                /* config.mhd; state rows = ndim+2 (+3 magnetic rows last) */
+  int32_t riemann;            /* config.riemann_solver */
+  int32_t limiter;            /* config.limiter */
+  int32_t split;              /* config.split */
+  int32_t time_integrator;    /* config.time_integrator */
+  int32_t boundary_handling;  /* config.boundary_handling */
+  int32_t bc[3][2];           /* config.boundary_settings: [axis][left,right] */
+  int32_t num_ghost;          /* config.num_ghost_cells (must be 2, Q8) */
+  int32_t magnetic_integrator;/* config.fv_magnetic_integrator */
+  int32_t first_order_fallback;/* config.first_order_fallback (split path only, Q7) */
+  int32_t exact_end_time;     /* config.exact_end_time */
+  int32_t use_max_adaptive_timestep; /* config.use_max_adaptive_timestep (split CFL only, Q3) */
+  int32_t arithmetic;         /* AMX_ARITH_* */
+  int32_t reserved[8];
+  double dx;                  /* config.grid_spacing */
+  double gamma, C_cfl, dt_max;/* params.* (rounded to dtype on entry, Q20) */
+  double fp_tol;              /* 1e-5 / 1e-10 from config.numerical_precision (Q6) */
+} amx_desc;
+
+/* step statistics, written by amx_integrate / amx_step into a host struct */
+typedef struct amx_stats {
+  int64_t steps;              /* time steps completed */
+  int64_t magnetic_iterations;/* while-body iterations executed, summed over steps */
+  double time;                /* simulation time reached */
+  double last_dt;
+  int64_t kernel_launches;    /* libamx kernels enqueued by the call */
+} amx_stats;
+
+AMX_API int amx_abi_version(void);
+AMX_API const char* amx_last_error(void);
+/* 0 when a CUDA device is usable from this process, else AMX_ECUDA (+ message) */
+AMX_API int amx_device_check(void);
+
+/* scratch needed by every entry point below for this descriptor */
+AMX_API int amx_workspace_bytes(const amx_desc* d, size_t* bytes_out);
+
+/* time_stepping/_utils.py:65-75 + time_integration.py:274-286: edge-pad by 2 and fill the
+ * gas rows' ghost cells (magnetic rows stay edge-padded, Q9).  unpadded -> seam array. */
+AMX_API int amx_pad(const amx_desc* d, const void* unpadded_in, void* seam_out, void* stream);
+/* time_stepping/_utils.py:19-61: seam array -> unpadded. */
+AMX_API int amx_unpad(const amx_desc* d, const void* seam_in, void* unpadded_out, void* stream);
+/* _geometry/boundaries.py:74-319 _boundary_handler(state, config, type_handled) on a seam
+ * array with `nrows` rows, in place.  type_handled: 0 gas, 1 velocity-only, 2 B-only. */
+AMX_API int amx_boundary_fill(const amx_desc* d, void* seam_inout, int nrows, int type_handled, void* stream);
+
+/* _finite_volume/_timestep_estimation/_timestep_estimator.py:95-218 _cfl_time_step:
+ * seam state -> dt (device scalar of desc->dtype at dt_out). */
+AMX_API int amx_cfl(const amx_desc* d, const void* seam_state, void* dt_out, void* ws, void* stream);
+
+/* _finite_volume/_state_evolution/evolve_state.py:497-600 _evolve_state_fv: one hydro step
+ * (RK2-SSP unsplit :419-488 over :339-414, or Strang-split MUSCL sweeps :168-325 over
+ * :53-163) or, for desc->mhd, hydro(dt/2) . magnetic_update(dt) . hydro(dt/2)
+ * (_magnetic_update/_magnetic_field_update.py:37-242).  dt is read from device memory. */
+AMX_API int amx_step(const amx_desc* d, const void* seam_in, void* seam_out, const void* dt_dev,
+             void* ws, void* stream, amx_stats* stats_or_null);
+
+/* time_stepping/time_integration.py:61,239 time_integration (FORWARDS, no snapshots):
+ * pad -> { dt = cfl; dt = min(dt, t_end - t); step; t += dt } while t < t_end -> unpad.
+ * unpadded in -> unpadded out.  The loop runs on the device (dt, t and the magnetic
+ * convergence flag live in `ws`); max_steps < 0 means no cap.  Blocks the calling host
+ * thread until the loop has ended (it polls a pinned mirror of t), then fills *stats. */
+AMX_API int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpadded_out, double t_end,
+                  int64_t max_steps, void* ws, void* stream, amx_stats* stats_or_null);
+
+/* ---- slab-decomposed building blocks (multi-GPU driver, astronomix_b200/slab.py) --------
+ * The local slab is [rows][n[0] + 2*num_ghost][n[1]][n[2]] with desc->bc[0] = {HALO, HALO};
+ * the caller exchanges the x ghost planes (NCCL send/recv) before each call that reads them. */
+
+/* max over active cells of |u_axis| + c per axis -> alpha_out[3] (device, desc->dtype):
+ * the per-rank part of _cfl_time_step (all-reduce MAX across ranks, then amx_dt_from_alpha). */
+AMX_API int amx_alpha(const amx_desc* d, const void* gas, void* alpha_out, void* ws, void* stream);
+/* dt = C/sum(alpha/dx) (unsplit) or min(C dx/max alpha, dt_max) (split); then, if
+ * exact_end_time, dt = min(dt, t_end - *time_dev).  All scalars device-resident. */
+AMX_API int amx_dt_from_alpha(const amx_desc* d, const void* alpha_dev, const void* time_dev, double t_end,
+                      void* dt_out, void* stream);
+/* evolve_state.py:339-414 one unsplit forward-Euler stage; with gas0 != NULL it also applies
+ * the RK2 combine prim(0.5*(cons(gas0)+cons(stage))) (:456-469).  alpha_lf (device, 3 values,
+ * global max |u|+c of gas_in per axis) is read by the Lax-Friedrichs flux only.  alpha_out
+ * (nullable) receives the per-axis max |u|+c of the result. dt_scale is 1 or 0.5. */
+AMX_API int amx_hydro_stage(const amx_desc* d, const void* gas_in, const void* gas0_or_null, void* gas_out,
+                    const void* dt_dev, double dt_scale, const void* alpha_lf, void* alpha_out,
+                    void* ws, void* stream);
+/* evolve_state.py:53-163 one split MUSCL-Hancock sweep along `axis` (1-based). */
+AMX_API int amx_split_sweep(const amx_desc* d, const void* gas_in, void* gas_out, int axis,
+                    const void* dt_dev, double dt_scale, const void* alpha_lf, void* alpha_out,
+                    void* ws, void* stream);
+/* _magnetic_field_update.py:82-165 one evaluation R_{k+1} = R_0 - dt*Psi(arg(R_k, R_0)) of the
+ * fixed point.  B0 is [3][...], gas0 the gas rows (rho and v_0 are read from it; v_z = 0 in
+ * 2-D), bvk / bvk1 are [6][...] iterates (B then v); bvk == NULL is the first iterate
+ * (R_k = R_0).  change_out (device, 2 values) receives max_cells |B_{k+1}-B_k|_2 and
+ * max_cells |v_{k+1}-v_k|_2 of this rank's active cells. */
+AMX_API int amx_magnetic_iter(const amx_desc* d, const void* B0, const void* gas0, const void* bvk_or_null,
+                      void* bvk1, const void* dt_dev, void* change_out, void* ws, void* stream);
+/* _magnetic_field_update.py:208-240: write the converged iterate back (v rows, pressure row of
+ * gas_inout; B_out <- B_n); alpha_out (nullable) = wave bounds of the updated gas. */
+AMX_API int amx_magnetic_final(const amx_desc* d, void* gas_inout, const void* bv_final, void* B_out,
+                       void* alpha_out, void* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMX_H_ */
