@@ -1,0 +1,210 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): relative L1 <= 1e-5 in fp32, <= 1e-12 in fp64 after
+the stated number of steps, per field group {rho, v, p, B}.  STRICT arithmetic follows the
+oracle's operation order with IEEE div/sqrt, so it is held to a tighter bound (1e-6 fp32);
+FAST (the shipped default: contracted FMAs, reciprocal multiplies, approximate fp32 sqrt/div)
+is held to the north-star tolerance."""
+import numpy as np
+import pytest
+
+import astronomix_b200 as ax
+from astronomix_b200 import _lib, problems as pr
+from astronomix_b200 import option_classes as oc
+from astronomix_b200 import time_integration as ti
+from oracle import fv_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+TOL = {("f32", "fast"): 1e-5, ("f32", "strict"): 1e-6, ("f64", "fast"): 1e-12, ("f64", "strict"): 1e-12}
+ARITH = {"fast": _lib.AMX_ARITH_FAST, "strict": _lib.AMX_ARITH_STRICT}
+
+
+def run_both(s, config, params, rv, steps, arith):
+    o = fo.Opts.from_config(config, params)
+    ref, info = fo.time_integration(s, o, max_steps=steps, return_info=True)
+    out = ti.integrate_steps(s, config, params, rv, steps, arithmetic=ARITH[arith])
+    assert ti.last_info.steps == info["steps"]
+    return out, ref, info
+
+
+def check(s, config, params, rv, steps, arith, tol=None):
+    out, ref, info = run_both(s, config, params, rv, steps, arith)
+    key = ("f32" if s.dtype == np.float32 else "f64", arith)
+    err = pr.rel_l1(out, ref, config.dimensionality, config.mhd)
+    assert np.isfinite(out).all()
+    assert err <= (tol or TOL[key]), f"rel-L1 {err:.3e} after {info['steps']} steps ({key})"
+    if config.mhd:
+        assert ti.last_info.magnetic_iterations == sum(info["iterations"])
+    return err
+
+
+@pytest.mark.parametrize("arith", ["fast", "strict"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("rs", [oc.HLL, oc.HLLC])
+def test_sod_101(cuda, rs, dtype, arith):
+    """BASELINE config 0: 1-D Sod, 101 cells, open boundaries, to t_end = 0.2."""
+    config, params, rv = pr.make(1, 101, boundaries="open", dtype=dtype, riemann_solver=rs)
+    check(pr.sod(101, dtype), config, params, rv, -1 if False else 10 ** 6, arith)
+
+
+@pytest.mark.parametrize("arith", ["fast", "strict"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_kelvin_helmholtz_hllc(cuda, dtype, arith):
+    """BASELINE config 1 at 64^2: KH, HLLC, periodic, 40 steps."""
+    config, params, rv = pr.make(2, 64, dtype=dtype, riemann_solver=oc.HLLC)
+    check(pr.kelvin_helmholtz(64, dtype), config, params, rv, 40, arith)
+
+
+@pytest.mark.parametrize("arith", ["fast", "strict"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_orszag_tang_unsplit(cuda, dtype, arith):
+    """BASELINE config 2 at 64^2: 2-D MHD (Pang-Wu), HLL, unsplit RK2, 30 steps."""
+    config, params, rv = pr.make(2, 64, mhd=True, box=2 * np.pi, dtype=dtype)
+    check(pr.orszag_tang(64, dtype), config, params, rv, 30, arith)
+
+
+@pytest.mark.parametrize("arith", ["fast", "strict"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_mhd_blast_3d(cuda, dtype, arith):
+    """BASELINE config 3 at 32^3: 3-D MHD blast, HLL, 12 steps (p ratio 100, B0 = 10: the
+    arena variant; the 1000:0.1 / B0=28 variant is covered at fp64)."""
+    config, params, rv = pr.make(3, 32, mhd=True, dtype=dtype)
+    s = pr.mhd_blast3d(32, dtype, p_in=100.0, p_out=1.0, B0=10.0, r_inj=0.125)
+    check(s, config, params, rv, 12, arith)
+
+
+def test_mhd_blast_3d_strong(cuda):
+    config, params, rv = pr.make(3, 32, mhd=True, dtype=np.float64)
+    check(pr.mhd_blast3d(32, np.float64), config, params, rv, 10, "fast")
+
+
+@pytest.mark.parametrize("dim,n", [(1, 128), (2, 32), (3, 16)])
+@pytest.mark.parametrize("rs", [oc.HLL, oc.HLLC, oc.HLLC_LM, oc.LAX_FRIEDRICHS])
+@pytest.mark.parametrize("lim", [oc.MINMOD, oc.OSHER, oc.DOUBLE_MINMOD, oc.SUPERBEE, oc.VAN_ALBADA])
+def test_flux_limiter_matrix_fp64(cuda, dim, n, rs, lim):
+    s = pr.smooth_random(dim, n, seed=dim + 10 * rs + lim, dtype=np.float64)
+    config, params, rv = pr.make(dim, n, dtype=np.float64, riemann_solver=rs, limiter=lim)
+    check(s, config, params, rv, 6, "fast")
+
+
+@pytest.mark.parametrize("rs", [oc.HLL, oc.HLLC, oc.HLLC_LM, oc.LAX_FRIEDRICHS])
+def test_flux_matrix_fp32_strict_3d(cuda, rs):
+    s = pr.smooth_random(3, 16, seed=rs, dtype=np.float32)
+    config, params, rv = pr.make(3, 16, dtype=np.float32, riemann_solver=rs)
+    check(s, config, params, rv, 8, "strict")
+    check(s, config, params, rv, 8, "fast")
+
+
+@pytest.mark.parametrize("dim,n", [(1, 64), (2, 32), (3, 16)])
+@pytest.mark.parametrize("bnd", ["open", "reflective"])
+def test_nonperiodic_boundaries(cuda, dim, n, bnd):
+    s = pr.smooth_random(dim, n, seed=5, dtype=np.float64)
+    config, params, rv = pr.make(dim, n, boundaries=bnd, dtype=np.float64, riemann_solver=oc.HLLC)
+    check(s, config, params, rv, 8, "fast")
+
+
+def test_mixed_boundaries_2d(cuda):
+    bs = oc.BoundarySettings(oc.BoundarySettings1D(oc.PERIODIC_BOUNDARY, oc.PERIODIC_BOUNDARY),
+                             oc.BoundarySettings1D(oc.REFLECTIVE_BOUNDARY, oc.OPEN_BOUNDARY))
+    s = pr.smooth_random(2, 32, seed=6, dtype=np.float64)
+    config, params, rv = pr.make(2, 32, boundaries=bs, dtype=np.float64)
+    check(s, config, params, rv, 8, "fast")
+
+
+@pytest.mark.parametrize("dim,n,mhd", [(1, 64, False), (2, 32, False), (2, 32, True), (3, 16, False), (3, 16, True)])
+def test_split_muscl(cuda, dim, n, mhd):
+    s = pr.smooth_random(dim, n, mhd=mhd, seed=8, dtype=np.float64)
+    config, params, rv = pr.make(dim, n, mhd=mhd, dtype=np.float64, split=oc.SPLIT, time_integrator=oc.MUSCL,
+                                 params=ax.SimulationParams(dt_max=1.0))
+    check(s, config, params, rv, 6, "fast")
+
+
+def test_split_first_order_fallback(cuda):
+    s = pr.smooth_random(2, 32, seed=9, dtype=np.float64)
+    config, params, rv = pr.make(2, 32, dtype=np.float64, split=oc.SPLIT, time_integrator=oc.MUSCL,
+                                 first_order_fallback=True)
+    check(s, config, params, rv, 6, "fast")
+
+
+def test_implicit_euler_magnetic_integrator(cuda):
+    s = pr.smooth_random(2, 32, mhd=True, seed=12, dtype=np.float64)
+    config, params, rv = pr.make(2, 32, mhd=True, dtype=np.float64, fv_magnetic_integrator=oc.IMPLICIT_EULER)
+    check(s, config, params, rv, 6, "fast")
+
+
+def test_periodic_roll_equals_ghost_cells_bitwise(cuda):
+    for dim, n, mhd in [(2, 32, True), (3, 16, True)]:
+        s = pr.smooth_random(dim, n, mhd=mhd, seed=3, dtype=np.float32)
+        ca, pa, rv = pr.make(dim, n, mhd=mhd, boundary_handling=oc.GHOST_CELLS)
+        cb, pb, _ = pr.make(dim, n, mhd=mhd, boundary_handling=oc.PERIODIC_ROLL)
+        a = ti.integrate_steps(s, ca, pa, rv, 5)
+        b = ti.integrate_steps(s, cb, pb, rv, 5)
+        assert np.array_equal(a, b)
+
+
+def test_runs_to_t_end_and_counts_steps(cuda):
+    """The adaptive loop itself: exact end time, step count equal to the oracle's."""
+    config, params, rv = pr.make(2, 32, dtype=np.float64, params=ax.SimulationParams(t_end=0.05))
+    s = pr.kelvin_helmholtz(32, np.float64)
+    ref, info = fo.time_integration(s, fo.Opts.from_config(config, params), return_info=True)
+    out = ax.time_integration(s, config, params, rv)
+    assert ti.last_info.steps == info["steps"]
+    assert ti.last_info.time == pytest.approx(0.05, abs=1e-15)
+    assert pr.rel_l1(out, ref, 2, False) < 1e-12
+
+
+def test_seam_functions_on_padded_state(cuda):
+    """_evolve_state_fv / _cfl_time_step on the padded arrays the reference's loop body sees."""
+    for dim, n, mhd in [(2, 24, True), (3, 12, True), (1, 50, False)]:
+        bnd = "open" if dim == 1 else "periodic"
+        s = pr.smooth_random(dim, n, mhd=mhd, seed=4, dtype=np.float64)
+        config, params, rv = pr.make(dim, n, mhd=mhd, boundaries=bnd, dtype=np.float64)
+        o = fo.Opts.from_config(config, params)
+        sp = fo.prepare_state(s, o)
+        dt_ref = fo.cfl_time_step(sp, o, np.float64(params.gamma), np.float64(params.C_cfl), np.float64(params.dt_max))
+        dt = ti._cfl_time_step(sp, config.grid_spacing, params.dt_max, params.gamma, config, rv, params.C_cfl)
+        assert abs(float(dt) - float(dt_ref)) <= 1e-15 * float(dt_ref) * 4
+        ref = fo.evolve_state_fv(sp, np.float64(dt_ref), np.float64(params.gamma), o)
+        out = ti._evolve_state_fv(sp, float(dt_ref), params.gamma, 1.0, config, params, None, rv)
+        assert out.shape == sp.shape
+        assert pr.rel_l1(out, ref, dim, mhd) < 1e-12  # ghost cells included
+
+
+def test_conservation_fp32_periodic(cuda):
+    """Mass, momentum, energy to round-off on the CUDA path (hydro, periodic, 64^3, 20 steps)."""
+    s = pr.smooth_random(3, 64, seed=2, dtype=np.float32)
+    config, params, rv = pr.make(3, 64, riemann_solver=oc.HLLC)
+    out = ti.integrate_steps(s, config, params, rv, 20)
+    m0, p0, e0 = pr.totals(s, 3, False)
+    m1, p1, e1 = pr.totals(out, 3, False)
+    assert abs(m1 - m0) / m0 < 2e-6 and abs(e1 - e0) / e0 < 2e-6
+    for a, b in zip(p0, p1):
+        assert abs(a - b) / m0 < 2e-6
+
+
+def test_divB_held_at_reference_level(cuda):
+    for dtype, tol in [(np.float64, 1e-11), (np.float32, 2e-4)]:
+        n = 64
+        s = pr.orszag_tang(n, dtype)
+        config, params, rv = pr.make(2, n, mhd=True, box=2 * np.pi, dtype=dtype)
+        dx = config.grid_spacing
+        out = ti.integrate_steps(s, config, params, rv, 20)
+        ref = fo.time_integration(s, fo.Opts.from_config(config, params), max_steps=20)
+        d_out = np.abs(fo.divergence(out[4:7].astype(np.float64), dx, 2)).max()
+        d_ref = np.abs(fo.divergence(ref[4:7].astype(np.float64), dx, 2)).max()
+        assert d_out <= max(2 * d_ref, tol), (d_out, d_ref)
+
+
+def test_fixture_orszag_tang_on_gpu(cuda):
+    """The reference's stored final state, reproduced by the CUDA path itself (fp64, SPLIT +
+    MUSCL, 200^2, 3001 steps): the one end-to-end result pinned by the reference's own file."""
+    import os
+    from oracle.pin_orszag_tang import orszag_tang_state
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "orszag_tang_fixture.npz"))["final_state"]
+    s0, dx = orszag_tang_state()
+    config, params, rv = pr.make(2, 200, mhd=True, box=2 * np.pi, dtype=np.float64, split=oc.SPLIT,
+                                 time_integrator=oc.MUSCL, params=ax.SimulationParams(t_end=3.0))
+    out = ax.time_integration(s0, config, params, rv)
+    assert ti.last_info.steps == 3001
+    assert pr.rel_l1(out, ref, 2, True) < 1e-10
