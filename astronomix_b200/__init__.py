@@ -14,7 +14,4 @@ from .registered_variables import RegisteredVariables, get_registered_variables 
 from .helpers import get_helper_data, construct_primitive_state, HelperData  # noqa: F401
 
 
-def time_integration(*args, **kwargs):
-    """astronomix.time_integration (time_stepping/time_integration.py:61); CUDA only."""
-    from .time_integration import time_integration as _ti
-    return _ti(*args, **kwargs)
+from .stepping import time_integration  # noqa: F401,E402

@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(256) hydro_stage_kernel(const StageArgs a) {
 }
 
 // ---------------------------------------------------------------- split MUSCL-Hancock sweep
-template <typename T, int ND, int RS, int LIM>
+// AX = 0-based sweep axis (compile time, so every per-axis index stays in registers)
+template <typename T, int ND, int RS, int AX>
 __global__ void __launch_bounds__(256) split_sweep_kernel(const SweepArgs a) {
   if (a.ctl_ro && a.ctl_ro->done) return;
   const Consts<T> c = make_consts<T>(a.np);
@@ -201,27 +202,26 @@ __global__ void __launch_bounds__(256) split_sweep_kernel(const SweepArgs a) {
   for (int k = 0; k < ND; ++k) wb[k] = T(0);
   if (active) {
     const T dt = *static_cast<const T*>(a.dt) * (T)a.dt_scale;
-    const int ax = a.axis - 1;
     const Gas<T, ND> sc = load_gas<T, ND>(a.in, offset_of<ND>(a.in, cell));
     Gas<T, ND> U = cons_from_prim(sc, c);
-    const Gas<T, ND> sm1 = load_neighbor<T, ND>(a.in, a.g, cell, ax, -1);
-    const Gas<T, ND> sp1 = load_neighbor<T, ND>(a.in, a.g, cell, ax, +1);
+    const Gas<T, ND> sm1 = load_neighbor<T, ND>(a.in, a.g, cell, AX, -1);
+    const Gas<T, ND> sp1 = load_neighbor<T, ND>(a.in, a.g, cell, AX, +1);
     T alpha = T(0);
-    if constexpr (RS == RS_LF) alpha = static_cast<const T*>(a.alpha_lf)[ax];
+    if constexpr (RS == RS_LF) alpha = static_cast<const T*>(a.alpha_lf)[AX];
     Gas<T, ND> Fl, Fr;
     if (a.first_order) {  // evolve_state.py:72-74
-      Fl = riemann<T, ND, RS>(sm1, sc, a.axis, alpha, c);
-      Fr = riemann<T, ND, RS>(sc, sp1, a.axis, alpha, c);
+      Fl = riemann<T, ND, RS>(sm1, sc, AX + 1, alpha, c);
+      Fr = riemann<T, ND, RS>(sc, sp1, AX + 1, alpha, c);
     } else {
-      const Gas<T, ND> sm2 = load_neighbor<T, ND>(a.in, a.g, cell, ax, -2);
-      const Gas<T, ND> sp2 = load_neighbor<T, ND>(a.in, a.g, cell, ax, +2);
+      const Gas<T, ND> sm2 = load_neighbor<T, ND>(a.in, a.g, cell, AX, -2);
+      const Gas<T, ND> sp2 = load_neighbor<T, ND>(a.in, a.g, cell, AX, +2);
       const T hdt = dt / T(2);
       Gas<T, ND> lo_m, hi_m, lo_c, hi_c, lo_p, hi_p;
-      faces_muscl(sm1, slopes<T, ND, LIM>(sm2, sm1, sc, a.np.lim, c), a.axis, hdt, c, lo_m, hi_m);
-      faces_muscl(sc, slopes<T, ND, LIM>(sm1, sc, sp1, a.np.lim, c), a.axis, hdt, c, lo_c, hi_c);
-      faces_muscl(sp1, slopes<T, ND, LIM>(sc, sp1, sp2, a.np.lim, c), a.axis, hdt, c, lo_p, hi_p);
-      Fl = riemann<T, ND, RS>(hi_m, lo_c, a.axis, alpha, c);
-      Fr = riemann<T, ND, RS>(hi_c, lo_p, a.axis, alpha, c);
+      faces_muscl(sm1, slopes<T, ND, -1>(sm2, sm1, sc, a.np.lim, c), AX + 1, hdt, c, lo_m, hi_m);
+      faces_muscl(sc, slopes<T, ND, -1>(sm1, sc, sp1, a.np.lim, c), AX + 1, hdt, c, lo_c, hi_c);
+      faces_muscl(sp1, slopes<T, ND, -1>(sc, sp1, sp2, a.np.lim, c), AX + 1, hdt, c, lo_p, hi_p);
+      Fl = riemann<T, ND, RS>(hi_m, lo_c, AX + 1, alpha, c);
+      Fr = riemann<T, ND, RS>(hi_c, lo_p, AX + 1, alpha, c);
     }
 #pragma unroll
     for (int k = 0; k < ND + 2; ++k) U.q[k] = U.q[k] + (c.inv_dx * (Fl.q[k] - Fr.q[k])) * dt;
@@ -462,10 +462,12 @@ cudaError_t launch_hydro_stage(const StageArgs& a, cudaStream_t st) {
 
 template <typename T>
 static cudaError_t launch_split_sweep_t(const SweepArgs& a, cudaStream_t st) {
+  if (a.axis < 1 || a.axis > a.g.nd) return cudaErrorInvalidValue;
   AMX_DISPATCH_ND(a.g.nd, AMX_DISPATCH_RS(a.np.rs, {
     const unsigned grid = grid_for<ND>(a.g);
-    if (a.np.lim == LIM_MINMOD) split_sweep_kernel<T, ND, RS, LIM_MINMOD><<<grid, 256, 0, st>>>(a);
-    else split_sweep_kernel<T, ND, RS, -1><<<grid, 256, 0, st>>>(a);
+    if (a.axis == 1) split_sweep_kernel<T, ND, RS, 0><<<grid, 256, 0, st>>>(a);
+    if constexpr (ND >= 2) { if (a.axis == 2) split_sweep_kernel<T, ND, RS, 1><<<grid, 256, 0, st>>>(a); }
+    if constexpr (ND >= 3) { if (a.axis == 3) split_sweep_kernel<T, ND, RS, 2><<<grid, 256, 0, st>>>(a); }
   }))
   return cudaGetLastError();
 }

@@ -11,7 +11,7 @@ import pytest
 import astronomix_b200 as ax
 from astronomix_b200 import _lib, problems as pr
 from astronomix_b200 import option_classes as oc
-from astronomix_b200 import time_integration as ti
+from astronomix_b200 import stepping as ti
 from oracle import fv_oracle as fo
 
 pytestmark = pytest.mark.gpu
