@@ -76,6 +76,8 @@ PROTOTYPES = {
     "amx_abi_version": (C.c_int, []),
     "amx_last_error": (C.c_char_p, []),
     "amx_device_check": (C.c_int, []),
+    "amx_profile_enable": (C.c_int, [C.c_int]),
+    "amx_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "amx_workspace_bytes": (C.c_int, [_D, C.POINTER(C.c_size_t)]),
     "amx_pad": (C.c_int, [_D, _P, _P, _P]),
     "amx_unpad": (C.c_int, [_D, _P, _P, _P]),

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/amx.h"
 #include "amx_internal.h"
@@ -30,6 +31,51 @@ int cuda_fail(cudaError_t e, const char* where) {
     cudaError_t e__ = (expr);                           \
     if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
   } while (0)
+
+// ---- optional per-kernel-class timing (CUDA events on the launch stream; bench.py) -----------
+enum { PC_HYDRO_STAGE = 0, PC_SPLIT_SWEEP, PC_MAG_ITER, PC_MAG_FINAL, PC_ALPHA, PC_CONTROL, PC_COUNT };
+struct Profiler {
+  bool on = false;
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[PC_COUNT] = {0};
+  long long cnt[PC_COUNT] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void begin(int cls, cudaStream_t st) {
+    if (!on) return;
+    Rec r{cls, get(), get()};
+    cudaEventRecord(r.a, st);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(recs.back().b, st);
+  }
+  void resolve() {
+    for (auto& r : recs) {
+      float t = 0;
+      if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+        ms[r.cls] += t;
+        cnt[r.cls] += 1;
+      }
+      pool.push_back(r.a);
+      pool.push_back(r.b);
+    }
+    recs.clear();
+  }
+};
+Profiler g_prof;
+struct ProfScope {
+  cudaStream_t st;
+  ProfScope(int cls, cudaStream_t s) : st(s) { g_prof.begin(cls, st); }
+  ~ProfScope() { g_prof.end(st); }
+};
 
 struct Layout {
   int nd, ng, nv;          // dims, gas rows, total rows
@@ -476,7 +522,10 @@ struct Engine {
   cudaError_t alpha_of(const View& gas, void* alpha_t_out, bool guarded) {
     AlphaArgs a{g, np, gas, guarded ? ctl : nullptr, aslots()};
     ++launches;
-    CKE(strict ? amx_strict::launch_alpha(a, st) : amx_fast::launch_alpha(a, st));
+    {
+      ProfScope ps(PC_ALPHA, st);
+      CKE(strict ? amx_strict::launch_alpha(a, st) : amx_fast::launch_alpha(a, st));
+    }
     return finalize_alpha(alpha_t_out, guarded);
   }
 
@@ -490,7 +539,10 @@ struct Engine {
     a.dt = dt; a.dt_scale = dt_scale; a.alpha_lf = alpha_lf;
     a.alpha_slots = want_alpha ? aslots() : nullptr;
     ++launches;
-    CKE(strict ? amx_strict::launch_hydro_stage(a, st) : amx_fast::launch_hydro_stage(a, st));
+    {
+      ProfScope ps(PC_HYDRO_STAGE, st);
+      CKE(strict ? amx_strict::launch_hydro_stage(a, st) : amx_fast::launch_hydro_stage(a, st));
+    }
     return want_alpha ? finalize_alpha(alpha_t_out, guarded) : cudaSuccess;
   }
 
@@ -501,7 +553,10 @@ struct Engine {
     a.dt = dt; a.dt_scale = dt_scale; a.axis = axis; a.first_order = d->first_order_fallback;
     a.alpha_lf = alpha_lf; a.alpha_slots = want_alpha ? aslots() : nullptr;
     ++launches;
-    CKE(strict ? amx_strict::launch_split_sweep(a, st) : amx_fast::launch_split_sweep(a, st));
+    {
+      ProfScope ps(PC_SPLIT_SWEEP, st);
+      CKE(strict ? amx_strict::launch_split_sweep(a, st) : amx_fast::launch_split_sweep(a, st));
+    }
     return want_alpha ? finalize_alpha(alpha_t_out, guarded) : cudaSuccess;
   }
 
@@ -544,6 +599,7 @@ struct Engine {
     a.midpoint = d->magnetic_integrator == AMX_IMPLICIT_MIDPOINT;
     a.dt = dt; a.change_slots = cslots();
     ++launches;
+    ProfScope ps(PC_MAG_ITER, st);
     return strict ? amx_strict::launch_mag_iter(a, st) : amx_fast::launch_mag_iter(a, st);
   }
 
@@ -562,7 +618,10 @@ struct Engine {
     a.ctl_ro = ctl; a.fixed_final = fixed_final; a.alpha_slots = want_alpha ? aslots() : nullptr;
     (void)guarded;
     ++launches;
-    CKE(strict ? amx_strict::launch_mag_final(a, st) : amx_fast::launch_mag_final(a, st));
+    {
+      ProfScope ps(PC_MAG_FINAL, st);
+      CKE(strict ? amx_strict::launch_mag_final(a, st) : amx_fast::launch_mag_final(a, st));
+    }
     return want_alpha ? finalize_alpha(alpha_t_out, true) : cudaSuccess;
   }
 };
@@ -650,6 +709,21 @@ int amx_device_check(void) {
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
   if (n == 0) return fail(AMX_ECUDA, "no CUDA device visible; libamx has no CPU path");
+  return AMX_OK;
+}
+
+int amx_profile_enable(int on) {
+  g_prof.resolve();
+  g_prof.on = on != 0;
+  for (int k = 0; k < PC_COUNT; ++k) { g_prof.ms[k] = 0; g_prof.cnt[k] = 0; }
+  return AMX_OK;
+}
+
+int amx_profile_read(int kernel_class, double* ms_total, int64_t* launches) {
+  if (kernel_class < 0 || kernel_class >= PC_COUNT || !ms_total || !launches) return fail(AMX_EINVAL, "bad kernel_class / null output");
+  g_prof.resolve();
+  *ms_total = g_prof.ms[kernel_class];
+  *launches = g_prof.cnt[kernel_class];
   return AMX_OK;
 }
 
@@ -822,6 +896,7 @@ int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpadded_out
       CK(cudaMemcpyAsync((char*)unpadded_out + r * bytes, src + r * L.row_bytes, bytes, cudaMemcpyDeviceToDevice, E.st));
   }
   CK(cudaStreamSynchronize(E.st));
+  g_prof.resolve();
   if (stats) {
     stats->steps = steps;
     stats->magnetic_iterations = m->mag_iters_total;

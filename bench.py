@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s of the fused finite-volume MHD step on B200.
+
+Workload (BASELINE.json config 3): 3-D MHD blast wave, 256^3 cells per GPU, fp32, HLL,
+minmod, unsplit RK2-SSP, Pang-Wu magnetic sub-step (implicit midpoint), periodic,
+C_cfl 0.4, synthetic initial condition of tests/mhd_tests/mhd_blast3D.py.  One "step" is
+one full time step: CFL dt + hydro(dt/2) . magnetic(dt) . hydro(dt/2).  For N > 1 the
+domain is slab-decomposed along x with 256^3 cells per rank (weak scaling), halo exchange
+and dt / fixed-point all-reduces over NCCL.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+prints ONE JSON line (rank 0).  --impl reference times the CPU oracle (the NumPy
+restatement of the reference; JAX is not installable here) on the host cores.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cell-updates/sec (3D MHD)"
+UNIT = "cell-updates/s"
+N_CELLS = 256  # per axis, per GPU
+KERNEL_CLASSES = ["hydro_stage", "split_sweep", "magnetic_iter", "magnetic_final", "wave_bound", "control"]
+
+
+def workload_config(n=N_CELLS):
+    return {"workload": f"3D MHD blast {n}^3 per GPU, fp32, HLL, minmod, unsplit RK2-SSP, "
+                        "Pang-Wu implicit-midpoint magnetic step, periodic, C_cfl=0.4",
+            "cells_per_gpu": n ** 3, "l2_policy": "inputs larger than L2 (state 0.54 GB per GPU)"}
+
+
+def make_problem(n, dtype=np.float32):
+    from astronomix_b200 import problems as pr
+    config, params, rv = pr.make(3, n, mhd=True, dtype=dtype)
+    params = params._replace(t_end=1.0e9)  # never reached: the step count is fixed
+    state = pr.mhd_blast3d(n, dtype)
+    return config, params, rv, state
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def _oracle_worker(args):
+    n, steps, seed = args
+    from astronomix_b200 import problems as pr
+    from oracle import fv_oracle as fo
+    config, params, rv = pr.make(3, n, mhd=True)
+    params = params._replace(t_end=1.0e9)
+    s = pr.mhd_blast3d(n, np.float32)
+    o = fo.Opts.from_config(config, params)
+    fo.time_integration(s, o, max_steps=1)  # warm caches / allocator
+    t0 = time.perf_counter()
+    fo.time_integration(s, o, max_steps=steps)
+    return time.perf_counter() - t0
+
+
+def cpu_oracle_rate(n, steps, procs):
+    """cell-updates/s of the NumPy oracle: `procs` independent replicas of the same workload at
+    n^3 (throughput of all replicas over the slowest replica's wall time)."""
+    if procs == 1:
+        dt = _oracle_worker((n, steps, 0))
+        return n ** 3 * steps / dt
+    with mp.get_context("spawn").Pool(procs) as pool:
+        times = pool.map(_oracle_worker, [(n, steps, k) for k in range(procs)])
+    return procs * n ** 3 * steps / max(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = 48
+    # each "step" of this arm = one oracle time step on every replica; K steps + W warm-up
+    steps = max(1, min(args.steps, 4))
+    t0 = time.perf_counter()
+    rate = cpu_oracle_rate(n, steps, cores)
+    wall = time.perf_counter() - t0
+    sample = (f"NumPy oracle (restatement of the reference; JAX not installable here), {cores} independent "
+              f"replicas of the 3D MHD blast at {n}^3 fp32, {steps} time steps each, one process per core")
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": 1e3 * cores * n ** 3 / rate, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(), "wall_s": wall,
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- native arm
+def run_native(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from astronomix_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.require_device()
+    lib = _lib.load()
+    K, W = args.steps, args.warmup
+    n = args.cells
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from astronomix_b200 import slab
+        result = slab.bench_weak(n, K, W, dev)
+        t_ms = torch.tensor([result["ms"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        ms = float(t_ms.item())
+        e_ms = torch.tensor([result["e2e_ms"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            cells = world * n ** 3
+            line = {"metric": METRIC, "value": cells * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+                    "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": dict(workload_config(n), decomposition=f"slab along x, {n}^3 per rank, "
+                                   f"global {world * n}x{n}x{n}", **result["config"]),
+                    "e2e": {"value": cells * K / (float(e_ms.item()) * 1e-3), "unit": UNIT,
+                            "h2d_bytes_per_step": result["h2d_bytes"] * world / K,
+                            "d2h_bytes_per_step": result["d2h_bytes"] * world / K},
+                    "gpu_launches": result["launches"], "clocks": result["clocks"],
+                    "roofline": result["roofline"], "kernels": result["kernels"],
+                    "magnetic_iterations_per_step": result["mag_iters"] / K}
+            print(json.dumps(line))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
+    config, params, rv, state = make_problem(n)
+    host = torch.from_numpy(state).pin_memory()
+    s0 = host.to(dev, non_blocking=True)
+    desc = _lib.make_desc(config, params, state.shape[1:], _lib.AMX_F32)
+    nbytes = C.c_size_t()
+    _lib.check(lib.amx_workspace_bytes(C.byref(desc), C.byref(nbytes)))
+    ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = C.c_void_p((ws.data_ptr() + 255) & ~255)
+    s1, s2 = torch.empty_like(s0), torch.empty_like(s0)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    stats = _lib.AmxStats()
+
+    def integrate(src, dst, steps):
+        _lib.check(lib.amx_integrate(C.byref(desc), C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                     1.0e9, steps, ws_ptr, stream, C.byref(stats)))
+        return stats.steps, stats.magnetic_iterations, stats.kernel_launches
+
+    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps
+    integrate(s0, s1, W)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    lib.amx_profile_enable(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    ev0.record()
+    steps_done, mag_iters, launches = integrate(s1, s2, K)
+    ev1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    ms = ev0.elapsed_time(ev1)
+    assert steps_done == K, steps_done
+    kernels = {}
+    for k, name in enumerate(KERNEL_CLASSES):
+        t, c = C.c_double(), C.c_int64()
+        lib.amx_profile_read(k, C.byref(t), C.byref(c))
+        if c.value:
+            kernels[name] = {"launches": c.value, "ms_total": t.value, "share_of_step": t.value / ms}
+    lib.amx_profile_enable(0)
+    cells = n ** 3
+    value = cells * K / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel class (algorithmic bytes: DESIGN.md / SURVEY.md §8d)
+    w, ng = 4, 5
+    alg = {"hydro_stage": 0.5 * (2 * ng + 3 * ng) * w * cells}  # stage 1: r ng w ng; stage 2: r 2ng w ng
+    if "magnetic_iter" in kernels:
+        L = kernels["magnetic_iter"]["launches"]
+        firsts = K
+        alg["magnetic_iter"] = (firsts * 13 + (L - firsts) * 19) / L * w * cells
+    dom = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_total"])
+    avg_ms = kernels[dom]["ms_total"] / kernels[dom]["launches"]
+    achieved = alg[dom] / (avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "peak_source": f"{peak_src} (MEASURED_PEAKS.json copy bandwidth)",
+                "traffic": None, "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": avg_ms,
+                "step_algorithmic_bytes_per_cell": (10 * ng + 13 + 19 * (mag_iters / K)) * w,
+                "step_frac_of_hbm": value * (10 * ng + 13 + 19 * (mag_iters / K)) * w / 1e9 / hbm_peak}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = prof.get(dom, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+
+    # ---- end to end through the public call: pinned host state -> H2D -> K steps -> D2H
+    from astronomix_b200 import stepping
+    out_host = torch.empty(state.shape, dtype=torch.float32, pin_memory=True)
+
+    def e2e_once():
+        d_in = host.to(dev, non_blocking=True)
+        integrate(d_in, s2, K)
+        out_host.copy_(s2, non_blocking=True)
+
+    e2e_once()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_once()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    state_bytes = state.nbytes
+    del stepping
+
+    # ---- CPU baseline beside it (bounded sample of the same workload)
+    cpu = None
+    if not args.no_cpu:
+        nc, sc = 48, 3
+        t0c = time.perf_counter()
+        rate = cpu_oracle_rate(nc, sc, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"NumPy oracle, same 3D MHD blast at {nc}^3 fp32, {sc} steps, single process "
+                         f"({time.perf_counter() - t0c:.1f} s)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(n),
+            "e2e": {"value": cells * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": state_bytes / K,
+                    "d2h_bytes_per_step": state_bytes / K,
+                    "call": f"one amx_integrate call of {K} steps: pinned host state -> device -> host"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "kernels": kernels, "magnetic_iterations_per_step": mag_iters / K,
+            "arithmetic": "fast" if desc.arithmetic == 0 else "strict"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--cells", type=int, default=N_CELLS, help="cells per axis per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,13 @@ AMX_API const char* amx_last_error(void);
 /* 0 when a CUDA device is usable from this process, else AMX_ECUDA (+ message) */
 AMX_API int amx_device_check(void);
 
+/* Per-kernel-class device timing for bench.py: when enabled, amx_integrate / amx_step bracket
+ * every launch of a class with CUDA events on the launch stream and accumulate the elapsed
+ * time.  Classes: 0 hydro stage, 1 split sweep, 2 magnetic iteration, 3 magnetic write-back,
+ * 4 wave-bound reduction, 5 control.  amx_profile_enable also resets the counters. */
+AMX_API int amx_profile_enable(int on);
+AMX_API int amx_profile_read(int kernel_class, double* ms_total, int64_t* launches);
+
 /* scratch needed by every entry point below for this descriptor */
 AMX_API int amx_workspace_bytes(const amx_desc* d, size_t* bytes_out);
 
