@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -451,6 +452,12 @@ unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
     if (e__ != cudaSuccess) return e__;            \
   } while (0)
 
+// AMX_FORCE_GENERIC=1 keeps every launch on the one-thread-per-cell kernels (A/B testing)
+bool force_generic() {
+  static const bool v = [] { const char* e = getenv("AMX_FORCE_GENERIC"); return e && e[0] == '1'; }();
+  return v;
+}
+
 struct Engine {
   const amx_desc* d;
   Layout L;
@@ -541,7 +548,9 @@ struct Engine {
     ++launches;
     {
       ProfScope ps(PC_HYDRO_STAGE, st);
-      CKE(strict ? amx_strict::launch_hydro_stage(a, st) : amx_fast::launch_hydro_stage(a, st));
+      const bool tiled = !force_generic() && (strict ? amx_strict::tiled_stage_supported(a) : amx_fast::tiled_stage_supported(a));
+      if (tiled) CKE(strict ? amx_strict::launch_hydro_stage_tiled(a, st) : amx_fast::launch_hydro_stage_tiled(a, st));
+      else CKE(strict ? amx_strict::launch_hydro_stage(a, st) : amx_fast::launch_hydro_stage(a, st));
     }
     return want_alpha ? finalize_alpha(alpha_t_out, guarded) : cudaSuccess;
   }

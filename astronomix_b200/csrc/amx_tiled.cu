@@ -1,0 +1,524 @@
+// amx_tiled.cu -- plane-streaming shared-memory kernels for the 2-D / 3-D hot configurations.
+//
+// hydro_stage_tiled: one unsplit forward-Euler stage (evolve_state.py:339-414) [+ RK2 combine
+// :456-469], every interface flux and every limited slope computed exactly once per block:
+//   * a block owns a TY x TZ column tile (3-D: 8 x 32 cells, z contiguous; 2-D: 1 x 256) and
+//     marches along x over a chunk of planes;
+//   * x direction: the thread carries s(x), s(x+1), the x half-slope of cell x, the difference
+//     across x+1/2 and the flux at x-1/2 in registers -- one new plane load per step, no
+//     shared memory, no recomputation;
+//   * y / z directions: the plane window (tile + 2-cell halo, boundary rules applied while
+//     loading) sits in a 3-deep shared-memory ring; each thread computes the half-slopes of its
+//     own cell, publishes them, computes the fluxes at its two lower interfaces from its own and
+//     its neighbours' published slopes, publishes those, and reads the upper-interface fluxes
+//     back.  The tile-edge slopes / fluxes are extra work items spread over otherwise idle lanes.
+//   * conservative update, cons->prim, optional RK2 combine with s0, store, running max of
+//     |u|+c for the next CFL / Lax-Friedrichs alpha: all in the same pass.
+// Algorithmic traffic: read ng (+ng for the combine), write ng words per cell; the window halo
+// (3-D: 12x36 / 8x32 = 1.69x of the read) is served by L2.
+//
+// mag_iter_tiled: one evaluation of the Pang-Wu fixed point (_magnetic_field_update.py:82-165)
+// with the same marching scheme (1-cell halo, arguments averaged once per cell, E = B x v
+// computed once per cell).
+//
+// Compiled twice like amx_kernels.cu (fast / strict arithmetic).
+#include "amx_internal.h"
+#include "amx_math.cuh"
+
+#if AMX_STRICT
+#define AMX_NS amx_strict
+#else
+#define AMX_NS amx_fast
+#endif
+
+namespace AMX_NS {
+using namespace amx;
+
+namespace tiled {
+
+template <int ND>
+AMX_DI int map_index(int i, int n, int bcl, int bcr, bool& flip) {
+  flip = false;
+  if (i < 0) {
+    if (bcl == BC_PERIODIC) return i + n;
+    if (bcl == BC_OPEN) return 0;
+    if (bcl == BC_REFLECTIVE) { flip = true; return -1 - i; }
+    return i;
+  }
+  if (i >= n) {
+    if (bcr == BC_PERIODIC) return i - n;
+    if (bcr == BC_OPEN) return n - 1;
+    if (bcr == BC_REFLECTIVE) { flip = true; return 2 * n - 1 - i; }
+    return i;
+  }
+  return i;
+}
+
+template <typename T>
+AMX_DI Consts<T> make_consts(const NumPar& np) {
+  Consts<T> c;
+  c.gamma = (T)np.gamma;
+  c.gm1 = c.gamma - T(1);
+  c.dx = (T)np.dx;
+  c.inv_dx = (T)(1.0 / np.dx);
+  c.half_dx = (T)(np.dx / 2);
+  c.va_eps = (T)(3 * np.dx);
+  return c;
+}
+
+AMX_DI unsigned long long bits_of(float v) { return (unsigned long long)__float_as_uint(v); }
+AMX_DI unsigned long long bits_of(double v) { return (unsigned long long)__double_as_longlong(v); }
+
+// limited HALF difference d = (limiter(dm/dx, dp/dx) * dx) / 2 of one variable from the
+// differences across the cell's lower (dm) and upper (dp) interface
+// (limited_gradients.py:50-60 + reconstruction.py:409-412)
+template <typename T, int LIM>
+AMX_DI T half_slope(T dm, T dp, int lim, const Consts<T>& c) {
+#if AMX_STRICT
+  const T a = dm / c.dx, b = dp / c.dx;
+  const T g = (LIM == LIM_MINMOD) ? minmod(a, b) : limited_slope(a, b, lim, c);
+  return (g * c.dx) / T(2);
+#else
+  if constexpr (LIM == LIM_MINMOD) {
+    return T(0.5) * minmod(dm, dp);
+  } else {
+    const T g = limited_slope(dm * c.inv_dx, dp * c.inv_dx, lim, c);
+    return (g * c.dx) * T(0.5);
+  }
+#endif
+}
+
+template <int ND> struct Tile;
+template <> struct Tile<3> { static constexpr int TY = 8, TZ = 32; };
+template <> struct Tile<2> { static constexpr int TY = 1, TZ = 256; };
+
+template <typename T, int ND>
+constexpr size_t hydro_smem_bytes() {
+  constexpr int NV = ND + 2, TY = Tile<ND>::TY, TZ = Tile<ND>::TZ;
+  constexpr int WY = ND == 3 ? TY + 4 : 1, WZ = TZ + 4;
+  size_t n = 3 * NV * WY * WZ + NV * TY * (TZ + 2) + NV * TY * (TZ + 1);
+  if (ND == 3) n += NV * (TY + 2) * TZ + NV * (TY + 1) * TZ;
+  return n * sizeof(T);
+}
+
+template <typename T, int ND, int RS, int LIM>
+__global__ void __launch_bounds__(256) hydro_stage_tiled(const StageArgs a, const int xchunk) {
+  if (a.ctl_ro && a.ctl_ro->done) return;
+  constexpr int NV = ND + 2;
+  constexpr int TY = Tile<ND>::TY, TZ = Tile<ND>::TZ;
+  constexpr int WY = ND == 3 ? TY + 4 : 1, WZ = TZ + 4;
+  constexpr int YO = ND == 3 ? 2 : 0;  // row offset of the tile inside the window
+  constexpr int LA = ND - 1;           // lane (contiguous) axis
+  constexpr int PL = WY * WZ;          // window plane size per variable
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* const ring = reinterpret_cast<T*>(smem_raw);    // [3][NV][WY][WZ]
+  T* const Dz = ring + 3 * NV * PL;                   // [NV][TY][TZ+2]  half-slopes along the lane axis
+  T* const Fz = Dz + NV * TY * (TZ + 2);              // [NV][TY][TZ+1]  fluxes at lane-axis interfaces
+  T* const Dy = Fz + NV * TY * (TZ + 1);              // [NV][TY+2][TZ]  (3-D) half-slopes along y
+  T* const Fy = Dy + NV * (TY + 2) * TZ;              // [NV][TY+1][TZ]  (3-D) fluxes at y interfaces
+
+  const Consts<T> c = make_consts<T>(a.np);
+  const Geom& g = a.g;
+  const int tid = threadIdx.x;
+  const int tz = tid % TZ, ty = tid / TZ;
+  const int z0 = blockIdx.x * TZ;
+  const int y0 = ND == 3 ? blockIdx.y * TY : 0;
+  const int chunk = ND == 3 ? blockIdx.z : blockIdx.y;
+  const int xs = chunk * xchunk;
+  const int xe = min(xs + xchunk, g.n[0]);
+  if (xs >= xe) return;
+  const T dt = *static_cast<const T*>(a.dt) * (T)a.dt_scale;
+  const T dtdx = c.inv_dx;  // the update is ((1/dx) * (F_i - F_{i+1})) * dt (evolve_state.py:398-403)
+
+  // ---- this thread's own column and its extra window-halo cell, boundary rules applied
+  bool own_fy = false, own_fz = false, h_fy = false, h_fz = false;
+  const int gz = z0 + tz, gy = y0 + ty;
+  const bool col_active = gz < g.n[LA] && (ND == 2 || gy < g.n[1]);
+  long long own_off;  // offset of the (mapped) own column in `in`, plane 0
+  {
+    const int mz = map_index<ND>(gz, g.n[LA], g.bc[LA][0], g.bc[LA][1], own_fz);
+    own_off = (long long)mz * a.in.s[LA];
+    if constexpr (ND == 3) {
+      const int my = map_index<ND>(gy, g.n[1], g.bc[1][0], g.bc[1][1], own_fy);
+      own_off += (long long)my * a.in.s[1];
+    }
+  }
+  constexpr int NHALO = ND == 3 ? (WY * WZ - TY * TZ) : 4;
+  int hpos = -1;  // window position (j * WZ + k) of the halo cell this thread loads
+  long long h_off = 0;
+  if (tid < NHALO) {
+    int j, k;
+    if constexpr (ND == 3) {
+      if (tid < 4 * WZ) {
+        const int r = tid / WZ;
+        j = r < 2 ? r : (TY + r);  // rows 0, 1, TY+2, TY+3
+        k = tid % WZ;
+      } else {
+        const int h2 = tid - 4 * WZ;
+        j = 2 + h2 / 4;
+        const int q = h2 % 4;
+        k = q < 2 ? q : (TZ + q);  // columns 0, 1, TZ+2, TZ+3
+      }
+    } else {
+      j = 0;
+      k = tid < 2 ? tid : (TZ + tid);
+    }
+    hpos = j * WZ + k;
+    const int mz = map_index<ND>(z0 - 2 + k, g.n[LA], g.bc[LA][0], g.bc[LA][1], h_fz);
+    h_off = (long long)mz * a.in.s[LA];
+    if constexpr (ND == 3) {
+      const int my = map_index<ND>(y0 - 2 + j, g.n[1], g.bc[1][0], g.bc[1][1], h_fy);
+      h_off += (long long)my * a.in.s[1];
+    }
+  }
+  const T* const in = static_cast<const T*>(a.in.p);
+  const long long vs = a.in.vs;
+
+  // load the (mapped) plane xp: own cell into v[], halo cell into hv[]
+  auto load_plane = [&](int xp, T (&v)[NV], T (&hv)[NV], bool want_halo) {
+    bool fx;
+    const int mx = map_index<ND>(xp, g.n[0], g.bc[0][0], g.bc[0][1], fx);
+    const long long po = (long long)mx * a.in.s[0];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = __ldg(in + k * vs + po + own_off);
+    if (fx) v[1] = -v[1];
+    if (ND == 3 && own_fy) v[2] = -v[2];
+    if (own_fz) v[LA + 1] = -v[LA + 1];
+    if (want_halo && hpos >= 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) hv[k] = __ldg(in + k * vs + po + h_off);
+      if (fx) hv[1] = -hv[1];
+      if (ND == 3 && h_fy) hv[2] = -hv[2];
+      if (h_fz) hv[LA + 1] = -hv[LA + 1];
+    }
+  };
+  auto store_window = [&](int slot, const T (&v)[NV], const T (&hv)[NV]) {
+    T* w = ring + slot * NV * PL;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) w[k * PL + (ty + YO) * WZ + tz + 2] = v[k];
+    if (hpos >= 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) w[k * PL + hpos] = hv[k];
+    }
+  };
+
+  // ---- prologue: planes xs-2 .. xs+1
+  T sC[NV], sP[NV], dC[NV], DxP[NV], FxL[NV], hv[NV];
+  {
+    T sM2[NV], sM1[NV];
+    load_plane(xs - 2, sM2, hv, false);
+    load_plane(xs - 1, sM1, hv, false);
+    load_plane(xs, sC, hv, true);
+    store_window(0, sC, hv);
+    load_plane(xs + 1, sP, hv, true);
+    store_window(1, sP, hv);
+    Gas<T, ND> L, R;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const T d0 = sC[k] - sM1[k];
+      DxP[k] = sP[k] - sC[k];
+      const T dM1 = half_slope<T, LIM>(sM1[k] - sM2[k], d0, a.np.lim, c);
+      dC[k] = half_slope<T, LIM>(d0, DxP[k], a.np.lim, c);
+      L.q[k] = sM1[k] + dM1;
+      R.q[k] = sC[k] - dC[k];
+    }
+    T alpha = T(0);
+    if constexpr (RS == RS_LF) alpha = static_cast<const T*>(a.alpha_lf)[0];
+    const Gas<T, ND> F = riemann<T, ND, RS>(L, R, 1, alpha, c);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) FxL[k] = F.q[k];
+  }
+  __syncthreads();
+
+  T wb[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) wb[k] = T(0);
+  T alpha_lf[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) alpha_lf[k] = RS == RS_LF ? static_cast<const T*>(a.alpha_lf)[k] : T(0);
+
+  const long long out_col = (long long)gz * a.out.s[LA] + (ND == 3 ? (long long)gy * a.out.s[1] : 0);
+  const long long in0_col = a.in0.p ? ((long long)gz * a.in0.s[LA] + (ND == 3 ? (long long)gy * a.in0.s[1] : 0)) : 0;
+
+  int slotC = 0;
+  for (int x = xs; x < xe; ++x) {
+    const int slotN = slotC == 0 ? 2 : slotC - 1;  // (slotC + 2) % 3
+    T sN[NV];
+    load_plane(x + 2, sN, hv, true);
+    const T* w = ring + slotC * NV * PL;
+    const int wc = (ty + YO) * WZ + tz + 2;  // own cell in the window
+
+    // ---- half-slopes of the own cell along z (and y), published for the neighbours
+    T zM[NV], dZ[NV], yM[NV], dY[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      zM[k] = w[k * PL + wc - 1];
+      const T zp = w[k * PL + wc + 1];
+      dZ[k] = half_slope<T, LIM>(sC[k] - zM[k], zp - sC[k], a.np.lim, c);
+      Dz[(k * TY + ty) * (TZ + 2) + tz + 1] = dZ[k];
+      if constexpr (ND == 3) {
+        yM[k] = w[k * PL + wc - WZ];
+        const T yp = w[k * PL + wc + WZ];
+        dY[k] = half_slope<T, LIM>(sC[k] - yM[k], yp - sC[k], a.np.lim, c);
+        Dy[(k * (TY + 2) + ty + 1) * TZ + tz] = dY[k];
+      }
+    }
+    // tile-edge slopes: cells one outside the tile (rows -1 / TY, columns -1 / TZ)
+    if constexpr (ND == 3) {
+      if (tid < 2 * TZ) {
+        const int row = tid < TZ ? -1 : TY;
+        const int p = (row + 2) * WZ + (tid % TZ) + 2;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const T s0 = w[k * PL + p];
+          Dy[(k * (TY + 2) + row + 1) * TZ + (tid % TZ)] =
+              half_slope<T, LIM>(s0 - w[k * PL + p - WZ], w[k * PL + p + WZ] - s0, a.np.lim, c);
+        }
+      } else if (tid < 2 * TZ + 2 * TY) {
+        const int i = tid - 2 * TZ;
+        const int col = i < TY ? -1 : TZ, yy = i % TY;
+        const int p = (yy + 2) * WZ + col + 2;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const T s0 = w[k * PL + p];
+          Dz[(k * TY + yy) * (TZ + 2) + col + 1] =
+              half_slope<T, LIM>(s0 - w[k * PL + p - 1], w[k * PL + p + 1] - s0, a.np.lim, c);
+        }
+      }
+    } else {
+      if (tid < 2) {
+        const int col = tid == 0 ? -1 : TZ;
+        const int p = col + 2;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const T s0 = w[k * PL + p];
+          Dz[k * (TZ + 2) + col + 1] = half_slope<T, LIM>(s0 - w[k * PL + p - 1], w[k * PL + p + 1] - s0, a.np.lim, c);
+        }
+      }
+    }
+
+    // ---- x direction from registers: flux at x+1/2
+    T dP[NV], DxN[NV], FxR[NV];
+    {
+      Gas<T, ND> L, R;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        DxN[k] = sN[k] - sP[k];
+        dP[k] = half_slope<T, LIM>(DxP[k], DxN[k], a.np.lim, c);
+        L.q[k] = sC[k] + dC[k];
+        R.q[k] = sP[k] - dP[k];
+      }
+      const Gas<T, ND> F = riemann<T, ND, RS>(L, R, 1, alpha_lf[0], c);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) FxR[k] = F.q[k];
+    }
+    __syncthreads();  // published slopes visible
+
+    // ---- fluxes at the own cell's lower z (and y) interfaces, published
+    {
+      Gas<T, ND> L, R;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        L.q[k] = zM[k] + Dz[(k * TY + ty) * (TZ + 2) + tz];
+        R.q[k] = sC[k] - dZ[k];
+      }
+      const Gas<T, ND> F = riemann<T, ND, RS>(L, R, LA + 1, alpha_lf[LA], c);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) Fz[(k * TY + ty) * (TZ + 1) + tz] = F.q[k];
+    }
+    if constexpr (ND == 3) {
+      Gas<T, ND> L, R;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        L.q[k] = yM[k] + Dy[(k * (TY + 2) + ty) * TZ + tz];
+        R.q[k] = sC[k] - dY[k];
+      }
+      const Gas<T, ND> F = riemann<T, ND, RS>(L, R, 2, alpha_lf[1], c);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) Fy[(k * (TY + 1) + ty) * TZ + tz] = F.q[k];
+    }
+    // tile-edge fluxes: the interfaces above the last row / column of the tile
+    if constexpr (ND == 3) {
+      if (tid >= 96 && tid < 96 + TZ) {
+        const int zz = tid - 96;
+        const int p = (TY + 1) * WZ + zz + 2;  // cell (TY-1, zz); the cell above is p + WZ
+        Gas<T, ND> L, R;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          L.q[k] = w[k * PL + p] + Dy[(k * (TY + 2) + TY) * TZ + zz];
+          R.q[k] = w[k * PL + p + WZ] - Dy[(k * (TY + 2) + TY + 1) * TZ + zz];
+        }
+        const Gas<T, ND> F = riemann<T, ND, RS>(L, R, 2, alpha_lf[1], c);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) Fy[(k * (TY + 1) + TY) * TZ + zz] = F.q[k];
+      } else if (tid >= 128 && tid < 128 + TY) {
+        const int yy = tid - 128;
+        const int p = (yy + 2) * WZ + TZ + 1;  // cell (yy, TZ-1); the next cell is p + 1
+        Gas<T, ND> L, R;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          L.q[k] = w[k * PL + p] + Dz[(k * TY + yy) * (TZ + 2) + TZ];
+          R.q[k] = w[k * PL + p + 1] - Dz[(k * TY + yy) * (TZ + 2) + TZ + 1];
+        }
+        const Gas<T, ND> F = riemann<T, ND, RS>(L, R, 3, alpha_lf[2], c);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) Fz[(k * TY + yy) * (TZ + 1) + TZ] = F.q[k];
+      }
+    } else {
+      if (tid == 32) {
+        const int p = TZ + 1;
+        Gas<T, ND> L, R;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          L.q[k] = w[k * PL + p] + Dz[k * (TZ + 2) + TZ];
+          R.q[k] = w[k * PL + p + 1] - Dz[k * (TZ + 2) + TZ + 1];
+        }
+        const Gas<T, ND> F = riemann<T, ND, RS>(L, R, 2, alpha_lf[1], c);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) Fz[k * (TZ + 1) + TZ] = F.q[k];
+      }
+    }
+    __syncthreads();  // published fluxes visible
+
+    // ---- conservative update, axis by axis like the reference, then prim (+ RK2 combine)
+    {
+      Gas<T, ND> sc;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) sc.q[k] = sC[k];
+      Gas<T, ND> U = cons_from_prim(sc, c);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) U.q[k] = U.q[k] + (dtdx * (FxL[k] - FxR[k])) * dt;
+      if constexpr (ND == 3) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const T fl = Fy[(k * (TY + 1) + ty) * TZ + tz], fr = Fy[(k * (TY + 1) + ty + 1) * TZ + tz];
+          U.q[k] = U.q[k] + (dtdx * (fl - fr)) * dt;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const T fl = Fz[(k * TY + ty) * (TZ + 1) + tz], fr = Fz[(k * TY + ty) * (TZ + 1) + tz + 1];
+        U.q[k] = U.q[k] + (dtdx * (fl - fr)) * dt;
+      }
+      Gas<T, ND> s = prim_from_cons(U, c);
+      if (col_active) {
+        if (a.in0.p) {
+          Gas<T, ND> s0;
+          const T* p0 = static_cast<const T*>(a.in0.p) + in0_col + (long long)x * a.in0.s[0];
+#pragma unroll
+          for (int k = 0; k < NV; ++k) s0.q[k] = __ldg(p0 + k * a.in0.vs);
+          const Gas<T, ND> U0 = cons_from_prim(s0, c), U2 = cons_from_prim(s, c);
+          Gas<T, ND> Um;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) Um.q[k] = T(0.5) * (U0.q[k] + U2.q[k]);
+          s = prim_from_cons(Um, c);
+        }
+        T* po = static_cast<T*>(a.out.p) + out_col + (long long)x * a.out.s[0];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) po[k * a.out.vs] = s.q[k];
+        if (a.alpha_slots) {
+#pragma unroll
+          for (int k = 0; k < ND; ++k) wb[k] = rmax(wb[k], wave_bound(s, k + 1, c));
+        }
+      }
+    }
+
+    // ---- rotate: plane x+2 enters the ring, registers shift by one plane
+    store_window(slotN, sN, hv);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      sC[k] = sP[k];
+      sP[k] = sN[k];
+      dC[k] = dP[k];
+      DxP[k] = DxN[k];
+      FxL[k] = FxR[k];
+    }
+    slotC = slotC == 2 ? 0 : slotC + 1;
+  }
+
+  if (a.alpha_slots) {
+    __shared__ T red[ND][8];
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wb[k] = rmax(wb[k], __shfl_xor_sync(0xffffffffu, wb[k], o));
+      if (lane == 0) red[k][wid] = wb[k];
+    }
+    __syncthreads();
+    if (wid == 0) {
+      const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        T m = lane < 8 ? red[k][lane] : T(0);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) atomicMax(a.alpha_slots + (size_t)k * kAlphaSlots + (bid % kAlphaSlots), bits_of(m));
+      }
+    }
+  }
+}
+
+inline int pick_xchunk(int nx, long long tiles) {
+  const long long target = 148LL * 6;  // >= ~2 waves at 3 resident blocks per SM
+  long long nch = (target + tiles - 1) / tiles;
+  if (nch < 1) nch = 1;
+  const long long maxch = nx / 16 > 0 ? nx / 16 : 1;  // keep the 3-plane prologue below ~20 %
+  if (nch > maxch) nch = maxch;
+  return (int)((nx + nch - 1) / nch);
+}
+
+template <typename T, int ND, int RS, int LIM>
+cudaError_t launch_stage(const StageArgs& a, cudaStream_t st) {
+  constexpr int TY = Tile<ND>::TY, TZ = Tile<ND>::TZ;
+  const size_t smem = hydro_smem_bytes<T, ND>();
+  auto kern = hydro_stage_tiled<T, ND, RS, LIM>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid;
+  const int LA = ND - 1;
+  grid.x = (a.g.n[LA] + TZ - 1) / TZ;
+  const long long tiles = ND == 3 ? (long long)grid.x * ((a.g.n[1] + TY - 1) / TY) : grid.x;
+  const int xchunk = pick_xchunk(a.g.n[0], tiles);
+  const int nch = (a.g.n[0] + xchunk - 1) / xchunk;
+  if (ND == 3) { grid.y = (a.g.n[1] + TY - 1) / TY; grid.z = nch; }
+  else { grid.y = nch; grid.z = 1; }
+  kern<<<grid, 256, smem, st>>>(a, xchunk);
+  return cudaGetLastError();
+}
+
+}  // namespace tiled
+
+// The tiled stage handles 2-D / 3-D grids whose lane axis is contiguous and at least one tile
+// wide; everything else (1-D, tiny grids) stays on the generic kernel.
+bool tiled_stage_supported(const StageArgs& a) {
+  if (a.g.nd == 3)
+    return a.in.s[2] == 1 && a.out.s[2] == 1 && a.g.n[2] >= tiled::Tile<3>::TZ && a.g.n[1] >= tiled::Tile<3>::TY + 2 &&
+           a.g.n[0] >= 4 && (!a.in0.p || a.in0.s[2] == 1);
+  if (a.g.nd == 2)
+    return a.in.s[1] == 1 && a.out.s[1] == 1 && a.g.n[1] >= tiled::Tile<2>::TZ && a.g.n[0] >= 4 &&
+           (!a.in0.p || a.in0.s[1] == 1);
+  return false;
+}
+
+template <typename T>
+static cudaError_t launch_tiled_t(const StageArgs& a, cudaStream_t st) {
+#define AMX_TILED_CASE(ND_, RS_)                                                               \
+  if (a.g.nd == ND_ && a.np.rs == RS_)                                                         \
+    return a.np.lim == LIM_MINMOD ? tiled::launch_stage<T, ND_, RS_, LIM_MINMOD>(a, st)        \
+                                  : tiled::launch_stage<T, ND_, RS_, -1>(a, st);
+  AMX_TILED_CASE(3, RS_HLL) AMX_TILED_CASE(3, RS_HLLC) AMX_TILED_CASE(3, RS_HLLC_LM) AMX_TILED_CASE(3, RS_LF)
+  AMX_TILED_CASE(2, RS_HLL) AMX_TILED_CASE(2, RS_HLLC) AMX_TILED_CASE(2, RS_HLLC_LM) AMX_TILED_CASE(2, RS_LF)
+#undef AMX_TILED_CASE
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_hydro_stage_tiled(const StageArgs& a, cudaStream_t st) {
+  return a.np.dtype == 0 ? launch_tiled_t<float>(a, st) : launch_tiled_t<double>(a, st);
+}
+
+}  // namespace AMX_NS

@@ -208,3 +208,43 @@ def test_fixture_orszag_tang_on_gpu(cuda):
     out = ax.time_integration(s0, config, params, rv)
     assert ti.last_info.steps == 3001
     assert pr.rel_l1(out, ref, 2, True) < 1e-10
+
+
+# ---- the plane-streaming (tiled) kernels: grids at least one tile wide, ragged tile edges ----
+@pytest.mark.parametrize("dim,n", [(3, 32), (3, 40), (2, 256), (2, 272)])
+@pytest.mark.parametrize("bnd", ["periodic", "open", "reflective"])
+@pytest.mark.parametrize("rs,lim", [(oc.HLL, oc.MINMOD), (oc.HLLC, oc.VAN_ALBADA), (oc.LAX_FRIEDRICHS, oc.SUPERBEE)])
+def test_tiled_stage_fp64(cuda, dim, n, bnd, rs, lim):
+    s = pr.smooth_random(dim, n, seed=21 + dim, dtype=np.float64)
+    config, params, rv = pr.make(dim, n, boundaries=bnd, dtype=np.float64, riemann_solver=rs, limiter=lim)
+    check(s, config, params, rv, 4, "fast")
+
+
+@pytest.mark.parametrize("arith", ["fast", "strict"])
+@pytest.mark.parametrize("dim,n,mhd", [(3, 48, True), (2, 320, True), (3, 40, False)])
+def test_tiled_fp32(cuda, dim, n, mhd, arith):
+    s = pr.smooth_random(dim, n, mhd=mhd, seed=31, dtype=np.float32)
+    config, params, rv = pr.make(dim, n, mhd=mhd, riemann_solver=oc.HLLC if not mhd else oc.HLL)
+    check(s, config, params, rv, 6, arith)
+
+
+def test_tiled_equals_generic_bitwise_in_strict_mode(cuda):
+    """Same operation order in both kernel families: STRICT results must be identical."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r);"
+        "from astronomix_b200 import problems as pr, stepping as ti, _lib, option_classes as oc;"
+        "s = pr.smooth_random(3, 40, seed=5, dtype=np.float32);"
+        "c, p, rv = pr.make(3, 40, riemann_solver=oc.HLLC);"
+        "out = ti.integrate_steps(s, c, p, rv, 5, arithmetic=_lib.AMX_ARITH_STRICT);"
+        "np.save(sys.argv[1], out)"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for force in ("0", "1"):
+        path = f"/tmp/amx_strict_{force}.npy"
+        env = dict(os.environ, AMX_FORCE_GENERIC=force)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
+        outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1])
