@@ -609,6 +609,8 @@ struct Engine {
     a.dt = dt; a.change_slots = cslots();
     ++launches;
     ProfScope ps(PC_MAG_ITER, st);
+    const bool tiled = !force_generic() && (strict ? amx_strict::tiled_mag_supported(a) : amx_fast::tiled_mag_supported(a));
+    if (tiled) return strict ? amx_strict::launch_mag_iter_tiled(a, st) : amx_fast::launch_mag_iter_tiled(a, st);
     return strict ? amx_strict::launch_mag_iter(a, st) : amx_fast::launch_mag_iter(a, st);
   }
 

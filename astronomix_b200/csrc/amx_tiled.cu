@@ -491,6 +491,254 @@ cudaError_t launch_stage(const StageArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+
+// ================================================================ magnetic fixed point
+// One evaluation R_{k+1} = R_0 - dt * Psi(arg(R_k, R_0)) (_magnetic_field_update.py:82-165).
+// Per loaded plane every cell's argument (B, v) is averaged once, E = B x v is formed once,
+// and (B, E) go into a 4-deep shared-memory ring (1-cell halo); the curls of plane x are then
+// central differences over the ring (x-1, x, x+1).  R_0, R_k and rho of the own cell stay in
+// registers between the load of a plane and its update one step later.
+template <typename T, int ND>
+constexpr size_t mag_smem_bytes() {
+  constexpr int TY = Tile<ND>::TY, TZ = Tile<ND>::TZ;
+  constexpr int WY = ND == 3 ? TY + 2 : 1, WZ = TZ + 2;
+  return (size_t)4 * 6 * WY * WZ * sizeof(T);
+}
+
+template <typename T, int ND>
+__global__ void __launch_bounds__(256) mag_iter_tiled(const MagIterArgs a, const int xchunk) {
+  if (a.ctl_ro && (a.ctl_ro->done || (!a.first && !a.ctl_ro->mag_active))) return;
+  constexpr int TY = Tile<ND>::TY, TZ = Tile<ND>::TZ;
+  constexpr int WY = ND == 3 ? TY + 2 : 1, WZ = TZ + 2;
+  constexpr int YO = ND == 3 ? 1 : 0;
+  constexpr int LA = ND - 1;
+  constexpr int PL = WY * WZ;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* const ring = reinterpret_cast<T*>(smem_raw);  // [4][6][WY][WZ]: B (3) then E (3)
+
+  const Consts<T> c = make_consts<T>(a.np);
+  const Geom& g = a.g;
+  const int tid = threadIdx.x;
+  const int tz = tid % TZ, ty = tid / TZ;
+  const int z0 = blockIdx.x * TZ;
+  const int y0 = ND == 3 ? blockIdx.y * TY : 0;
+  const int chunk = ND == 3 ? blockIdx.z : blockIdx.y;
+  const int xs = chunk * xchunk;
+  const int xe = min(xs + xchunk, g.n[0]);
+  if (xs >= xe) return;
+  const T dt = *static_cast<const T*>(a.dt);
+  const bool have_k = a.Bk.p != nullptr;
+  const bool midpoint = a.midpoint != 0;
+
+  // mapped own column / halo cell: offsets per array, flip flags (Q12: a reflective side of
+  // axis `ax` (1-based) flips 3-vector component index ax, i.e. y for the x axis, z for the y
+  // axis and nothing for the z axis)
+  struct Col { long long oB0, og, oBk, ovk; bool f1, f2; };
+  auto make_col = [&](int wy, int wz, Col& col) {
+    bool fz, fy = false;
+    const int mz = map_index<ND>(z0 - 1 + wz, g.n[LA], g.bc[LA][0], g.bc[LA][1], fz);
+    int my = 0;
+    if constexpr (ND == 3) my = map_index<ND>(y0 - 1 + wy, g.n[1], g.bc[1][0], g.bc[1][1], fy);
+    col.oB0 = (long long)mz * a.B0.s[LA] + (ND == 3 ? (long long)my * a.B0.s[1] : 0);
+    col.og = (long long)mz * a.gas0.s[LA] + (ND == 3 ? (long long)my * a.gas0.s[1] : 0);
+    col.oBk = have_k ? (long long)mz * a.Bk.s[LA] + (ND == 3 ? (long long)my * a.Bk.s[1] : 0) : 0;
+    col.ovk = have_k ? (long long)mz * a.vk.s[LA] + (ND == 3 ? (long long)my * a.vk.s[1] : 0) : 0;
+    // lane axis is axis LA+1 (1-based): flips component LA+1 when < 3; y axis (3-D) flips component 2
+    col.f1 = false;
+    col.f2 = false;
+    if constexpr (ND == 3) { col.f2 = fy; }          // y axis (axis 2) -> component 2; z axis -> none
+    else { col.f2 = fz; }                            // 2-D lane axis is y (axis 2) -> component 2
+  };
+  Col own, halo;
+  make_col(ty + YO, tz + 1, own);
+  constexpr int NHALO = ND == 3 ? (WY * WZ - TY * TZ) : 2;
+  int hpos = -1;
+  if (tid < NHALO) {
+    int j, k;
+    if constexpr (ND == 3) {
+      if (tid < 2 * WZ) { j = tid < WZ ? 0 : TY + 1; k = tid % WZ; }
+      else { const int h2 = tid - 2 * WZ; j = 1 + h2 / 2; k = (h2 & 1) ? TZ + 1 : 0; }
+    } else {
+      j = 0;
+      k = tid == 0 ? 0 : TZ + 1;
+    }
+    hpos = j * WZ + k;
+    make_col(j, k, halo);
+  }
+  const int gz = z0 + tz, gy = y0 + ty;
+  const bool col_active = gz < g.n[LA] && (ND == 2 || gy < g.n[1]);
+
+  struct Raw { T B0[3], v0[3], Bk[3], vk[3], rho; };
+  // loads one cell of plane (mapped) mx, forms the argument and E, writes (B, E) to the ring
+  auto load_cell = [&](const Col& col, long long pB0, long long pg, long long pBk, long long pvk, bool fx,
+                       Raw& r, T* wdst) {
+    const T* pb = static_cast<const T*>(a.B0.p) + pB0 + col.oB0;
+    const T* pgas = static_cast<const T*>(a.gas0.p) + pg + col.og;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      r.B0[k] = __ldg(pb + k * a.B0.vs);
+      r.v0[k] = (k < ND) ? __ldg(pgas + (k + 1) * a.gas0.vs) : T(0);
+    }
+    r.rho = __ldg(pgas);
+    T B[3], v[3];
+    if (have_k) {
+      const T* pbk = static_cast<const T*>(a.Bk.p) + pBk + col.oBk;
+      const T* pvk_ = static_cast<const T*>(a.vk.p) + pvk + col.ovk;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        r.Bk[k] = __ldg(pbk + k * a.Bk.vs);
+        r.vk[k] = __ldg(pvk_ + k * a.vk.vs);
+        if (midpoint) { B[k] = (r.Bk[k] + r.B0[k]) / T(2); v[k] = (r.vk[k] + r.v0[k]) / T(2); }
+        else { B[k] = r.Bk[k]; v[k] = r.vk[k]; }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { r.Bk[k] = r.B0[k]; r.vk[k] = r.v0[k]; B[k] = r.B0[k]; v[k] = r.v0[k]; }
+    }
+    if (fx) { B[1] = -B[1]; v[1] = -v[1]; }       // x axis (axis 1) -> component 1
+    if (col.f2) { B[2] = -B[2]; v[2] = -v[2]; }
+    wdst[0 * PL] = B[0];
+    wdst[1 * PL] = B[1];
+    wdst[2 * PL] = B[2];
+    wdst[3 * PL] = B[1] * v[2] - B[2] * v[1];
+    wdst[4 * PL] = B[2] * v[0] - B[0] * v[2];
+    wdst[5 * PL] = B[0] * v[1] - B[1] * v[0];
+  };
+  auto load_plane = [&](int xp, int slot, Raw& r) {
+    bool fx;
+    const int mx = map_index<ND>(xp, g.n[0], g.bc[0][0], g.bc[0][1], fx);
+    const long long pB0 = (long long)mx * a.B0.s[0], pg = (long long)mx * a.gas0.s[0];
+    const long long pBk = have_k ? (long long)mx * a.Bk.s[0] : 0, pvk = have_k ? (long long)mx * a.vk.s[0] : 0;
+    T* w = ring + slot * 6 * PL;
+    load_cell(own, pB0, pg, pBk, pvk, fx, r, w + (ty + YO) * WZ + tz + 1);
+    if (hpos >= 0) {
+      Raw rh;
+      load_cell(halo, pB0, pg, pBk, pvk, fx, rh, w + hpos);
+    }
+  };
+
+  Raw rC, rN;
+  load_plane(xs - 1, 0, rC);
+  load_plane(xs, 1, rC);
+  T ch[2] = {T(0), T(0)};
+  const long long oB1 = (long long)gz * a.Bk1.s[LA] + (ND == 3 ? (long long)gy * a.Bk1.s[1] : 0);
+  const long long ov1 = (long long)gz * a.vk1.s[LA] + (ND == 3 ? (long long)gy * a.vk1.s[1] : 0);
+#if AMX_STRICT
+  const T hdx = c.dx;
+#else
+  const T hdx = T(0.5) * c.inv_dx;
+#endif
+  // central difference 0.5*(fp - fm)/dx (_vector_maths.py:55-100)
+  auto cd = [&](T fp, T fm) -> T {
+#if AMX_STRICT
+    return (T(0.5) * (fp - fm)) / hdx;
+#else
+    return hdx * (fp - fm);
+#endif
+  };
+
+  int sM = 0, sC = 1;  // ring slots of planes x-1 and x
+  for (int x = xs; x < xe; ++x) {
+    const int sP = (sC + 1) & 3;
+    load_plane(x + 1, sP, rN);
+    __syncthreads();
+    if (col_active) {
+      const T* wm = ring + sM * 6 * PL + (ty + YO) * WZ + tz + 1;
+      const T* wc = ring + sC * 6 * PL + (ty + YO) * WZ + tz + 1;
+      const T* wp = ring + sP * 6 * PL + (ty + YO) * WZ + tz + 1;
+      // field f (0..2 = B, 3..5 = E): d/dx, d/d(lane axis), d/dy (3-D)
+      auto ddx = [&](int f) { return cd(wp[f * PL], wm[f * PL]); };
+      auto ddl = [&](int f) { return cd(wc[f * PL + 1], wc[f * PL - 1]); };
+      auto ddy = [&](int f) { return cd(wc[f * PL + WZ], wc[f * PL - WZ]); };
+      T curlE[3], curlB[3];
+      if constexpr (ND == 3) {  // curl3D: lane axis is z
+        curlB[0] = ddy(2) - ddl(1); curlB[1] = ddl(0) - ddx(2); curlB[2] = ddx(1) - ddy(0);
+        curlE[0] = ddy(5) - ddl(4); curlE[1] = ddl(3) - ddx(5); curlE[2] = ddx(4) - ddy(3);
+      } else {  // curl2D: lane axis is y
+        curlB[0] = ddl(2); curlB[1] = -ddx(2); curlB[2] = ddx(1) - ddl(0);
+        curlE[0] = ddl(5); curlE[1] = -ddx(5); curlE[2] = ddx(4) - ddl(3);
+      }
+      const T Bc[3] = {wc[0], wc[PL], wc[2 * PL]};
+      T cr[3];
+      cr[0] = Bc[1] * curlB[2] - Bc[2] * curlB[1];
+      cr[1] = Bc[2] * curlB[0] - Bc[0] * curlB[2];
+      cr[2] = Bc[0] * curlB[1] - Bc[1] * curlB[0];
+#if !AMX_STRICT
+      const T ir = rdiv(T(1), rC.rho);
+#endif
+      T dB = T(0), dv = T(0);
+      T* pB1 = static_cast<T*>(a.Bk1.p) + oB1 + (long long)x * a.Bk1.s[0];
+      T* pv1 = static_cast<T*>(a.vk1.p) + ov1 + (long long)x * a.vk1.s[0];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+#if AMX_STRICT
+        const T phiB = cr[k] / rC.rho;
+#else
+        const T phiB = cr[k] * ir;
+#endif
+        const T Bn = rC.B0[k] - dt * curlE[k];
+        const T vn = rC.v0[k] - dt * phiB;
+        dB = dB + sq(rabs(rC.Bk[k] - Bn));
+        dv = dv + sq(rabs(rC.vk[k] - vn));
+        pB1[k * a.Bk1.vs] = Bn;
+        pv1[k * a.vk1.vs] = vn;
+      }
+      ch[0] = rmax(ch[0], dB);
+      ch[1] = rmax(ch[1], dv);
+    }
+    rC = rN;
+    sM = sC;
+    sC = sP;
+  }
+  ch[0] = rsqrt_(ch[0]);  // sqrt is monotone: max of norms = norm of max of squares
+  ch[1] = rsqrt_(ch[1]);
+  {
+    __shared__ T red[2][8];
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ch[k] = rmax(ch[k], __shfl_xor_sync(0xffffffffu, ch[k], o));
+      if (lane == 0) red[k][wid] = ch[k];
+    }
+    __syncthreads();
+    if (wid == 0) {
+      const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        T m = lane < 8 ? red[k][lane] : T(0);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) atomicMax(a.change_slots + (size_t)k * kAlphaSlots + (bid % kAlphaSlots), bits_of(m));
+      }
+    }
+  }
+}
+
+template <typename T, int ND>
+cudaError_t launch_mag(const MagIterArgs& a, cudaStream_t st) {
+  constexpr int TY = Tile<ND>::TY, TZ = Tile<ND>::TZ;
+  const size_t smem = mag_smem_bytes<T, ND>();
+  auto kern = mag_iter_tiled<T, ND>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  dim3 grid;
+  const int LA = ND - 1;
+  grid.x = (a.g.n[LA] + TZ - 1) / TZ;
+  const long long tiles = ND == 3 ? (long long)grid.x * ((a.g.n[1] + TY - 1) / TY) : grid.x;
+  const int xchunk = pick_xchunk(a.g.n[0], tiles);
+  const int nch = (a.g.n[0] + xchunk - 1) / xchunk;
+  if (ND == 3) { grid.y = (a.g.n[1] + TY - 1) / TY; grid.z = nch; }
+  else { grid.y = nch; grid.z = 1; }
+  kern<<<grid, 256, smem, st>>>(a, xchunk);
+  return cudaGetLastError();
+}
+
 }  // namespace tiled
 
 // The tiled stage handles 2-D / 3-D grids whose lane axis is contiguous and at least one tile
@@ -514,6 +762,21 @@ static cudaError_t launch_tiled_t(const StageArgs& a, cudaStream_t st) {
   AMX_TILED_CASE(3, RS_HLL) AMX_TILED_CASE(3, RS_HLLC) AMX_TILED_CASE(3, RS_HLLC_LM) AMX_TILED_CASE(3, RS_LF)
   AMX_TILED_CASE(2, RS_HLL) AMX_TILED_CASE(2, RS_HLLC) AMX_TILED_CASE(2, RS_HLLC_LM) AMX_TILED_CASE(2, RS_LF)
 #undef AMX_TILED_CASE
+  return cudaErrorInvalidValue;
+}
+
+bool tiled_mag_supported(const MagIterArgs& a) {
+  const int la = a.g.nd - 1;
+  if (a.g.nd != 2 && a.g.nd != 3) return false;
+  const bool unit = a.B0.s[la] == 1 && a.gas0.s[la] == 1 && a.Bk1.s[la] == 1 && a.vk1.s[la] == 1 &&
+                    (!a.Bk.p || (a.Bk.s[la] == 1 && a.vk.s[la] == 1));
+  if (a.g.nd == 3) return unit && a.g.n[2] >= tiled::Tile<3>::TZ && a.g.n[1] >= tiled::Tile<3>::TY + 2 && a.g.n[0] >= 4;
+  return unit && a.g.n[1] >= tiled::Tile<2>::TZ && a.g.n[0] >= 4;
+}
+
+cudaError_t launch_mag_iter_tiled(const MagIterArgs& a, cudaStream_t st) {
+  if (a.g.nd == 3) return a.np.dtype == 0 ? tiled::launch_mag<float, 3>(a, st) : tiled::launch_mag<double, 3>(a, st);
+  if (a.g.nd == 2) return a.np.dtype == 0 ? tiled::launch_mag<float, 2>(a, st) : tiled::launch_mag<double, 2>(a, st);
   return cudaErrorInvalidValue;
 }
 
