@@ -498,13 +498,36 @@ cudaError_t launch_stage(const StageArgs& a, cudaStream_t st) {
 // and (B, E) go into a 4-deep shared-memory ring (1-cell halo); the curls of plane x are then
 // central differences over the ring (x-1, x, x+1).  R_0, R_k and rho of the own cell stay in
 // registers between the load of a plane and its update one step later.
+// 4-byte asynchronous global->shared copy (LDGSTS); the data never passes through registers
+AMX_DI void cp_async4(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+AMX_DI void cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+template <typename T>
+AMX_DI void cp_async_elem(T* smem_dst, const T* gmem_src) {
+  if constexpr (sizeof(T) == 4) cp_async4(smem_dst, gmem_src);
+  else cp_async8(smem_dst, gmem_src);
+}
+AMX_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+AMX_DI void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename T, int ND>
 constexpr size_t mag_smem_bytes() {
   constexpr int TY = Tile<ND>::TY, TZ = Tile<ND>::TZ;
   constexpr int WY = ND == 3 ? TY + 2 : 1, WZ = TZ + 2;
-  return (size_t)4 * 6 * WY * WZ * sizeof(T);
+  return (size_t)4 * (13 + 6) * WY * WZ * sizeof(T);
 }
 
+// Plane pipeline of mag_iter_tiled (per block, planes p of the x chunk):
+//   cp.async raw(p)  ->  [2 planes later]  publish (B, E)(p) to the ring  ->  [2 planes later]  update(p)
+// raw(p) = B0, v0, rho, Bk, vk of the own cell and of one halo cell per thread, staged in shared
+// memory by LDGSTS (thread-private entries, so only cp.async.wait_group orders them); two planes
+// of loads are always in flight per block.  One __syncthreads per plane orders the (B, E) ring.
 template <typename T, int ND>
 __global__ void __launch_bounds__(256) mag_iter_tiled(const MagIterArgs a, const int xchunk) {
   if (a.ctl_ro && (a.ctl_ro->done || (!a.first && !a.ctl_ro->mag_active))) return;
@@ -513,8 +536,10 @@ __global__ void __launch_bounds__(256) mag_iter_tiled(const MagIterArgs a, const
   constexpr int YO = ND == 3 ? 1 : 0;
   constexpr int LA = ND - 1;
   constexpr int PL = WY * WZ;
+  constexpr int NRAW = 13;  // B0[3], v0[3], rho, Bk[3], vk[3]
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* const ring = reinterpret_cast<T*>(smem_raw);  // [4][6][WY][WZ]: B (3) then E (3)
+  T* const stage = reinterpret_cast<T*>(smem_raw);  // [4][13][PL]
+  T* const ring = stage + 4 * NRAW * PL;            // [4][6][PL]: B (3) then E (3)
 
   const Consts<T> c = make_consts<T>(a.np);
   const Geom& g = a.g;
@@ -530,24 +555,20 @@ __global__ void __launch_bounds__(256) mag_iter_tiled(const MagIterArgs a, const
   const bool have_k = a.Bk.p != nullptr;
   const bool midpoint = a.midpoint != 0;
 
-  // mapped own column / halo cell: offsets per array, flip flags (Q12: a reflective side of
-  // axis `ax` (1-based) flips 3-vector component index ax, i.e. y for the x axis, z for the y
-  // axis and nothing for the z axis)
-  struct Col { long long oB0, og, oBk, ovk; bool f1, f2; };
+  // Mapped own column / halo cell: one base pointer per array, flip flag.  Q12: a reflective
+  // side of axis `ax` (1-based) flips 3-vector component index ax, i.e. component 1 (y) for the
+  // x axis, component 2 (z) for the y axis and nothing for the z axis.
+  struct Col { const T *B0, *gas, *Bk, *vk; bool f2; };
   auto make_col = [&](int wy, int wz, Col& col) {
     bool fz, fy = false;
     const int mz = map_index<ND>(z0 - 1 + wz, g.n[LA], g.bc[LA][0], g.bc[LA][1], fz);
     int my = 0;
     if constexpr (ND == 3) my = map_index<ND>(y0 - 1 + wy, g.n[1], g.bc[1][0], g.bc[1][1], fy);
-    col.oB0 = (long long)mz * a.B0.s[LA] + (ND == 3 ? (long long)my * a.B0.s[1] : 0);
-    col.og = (long long)mz * a.gas0.s[LA] + (ND == 3 ? (long long)my * a.gas0.s[1] : 0);
-    col.oBk = have_k ? (long long)mz * a.Bk.s[LA] + (ND == 3 ? (long long)my * a.Bk.s[1] : 0) : 0;
-    col.ovk = have_k ? (long long)mz * a.vk.s[LA] + (ND == 3 ? (long long)my * a.vk.s[1] : 0) : 0;
-    // lane axis is axis LA+1 (1-based): flips component LA+1 when < 3; y axis (3-D) flips component 2
-    col.f1 = false;
-    col.f2 = false;
-    if constexpr (ND == 3) { col.f2 = fy; }          // y axis (axis 2) -> component 2; z axis -> none
-    else { col.f2 = fz; }                            // 2-D lane axis is y (axis 2) -> component 2
+    col.B0 = static_cast<const T*>(a.B0.p) + (long long)mz * a.B0.s[LA] + (ND == 3 ? (long long)my * a.B0.s[1] : 0);
+    col.gas = static_cast<const T*>(a.gas0.p) + (long long)mz * a.gas0.s[LA] + (ND == 3 ? (long long)my * a.gas0.s[1] : 0);
+    col.Bk = have_k ? static_cast<const T*>(a.Bk.p) + (long long)mz * a.Bk.s[LA] + (ND == 3 ? (long long)my * a.Bk.s[1] : 0) : nullptr;
+    col.vk = have_k ? static_cast<const T*>(a.vk.p) + (long long)mz * a.vk.s[LA] + (ND == 3 ? (long long)my * a.vk.s[1] : 0) : nullptr;
+    col.f2 = ND == 3 ? fy : fz;  // the y axis is the row axis in 3-D and the lane axis in 2-D
   };
   Col own, halo;
   make_col(ty + YO, tz + 1, own);
@@ -567,36 +588,56 @@ __global__ void __launch_bounds__(256) mag_iter_tiled(const MagIterArgs a, const
   }
   const int gz = z0 + tz, gy = y0 + ty;
   const bool col_active = gz < g.n[LA] && (ND == 2 || gy < g.n[1]);
+  const int wown = (ty + YO) * WZ + tz + 1;
 
-  struct Raw { T B0[3], v0[3], Bk[3], vk[3], rho; };
-  // loads one cell of plane (mapped) mx, forms the argument and E, writes (B, E) to the ring
-  auto load_cell = [&](const Col& col, long long pB0, long long pg, long long pBk, long long pvk, bool fx,
-                       Raw& r, T* wdst) {
-    const T* pb = static_cast<const T*>(a.B0.p) + pB0 + col.oB0;
-    const T* pgas = static_cast<const T*>(a.gas0.p) + pg + col.og;
+  // stage one cell of plane p (asynchronously)
+  auto issue_cell = [&](const Col& col, int mx, T* dst) {
+    const T* pb = col.B0 + (long long)mx * a.B0.s[0];
+    const T* pg = col.gas + (long long)mx * a.gas0.s[0];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      r.B0[k] = __ldg(pb + k * a.B0.vs);
-      r.v0[k] = (k < ND) ? __ldg(pgas + (k + 1) * a.gas0.vs) : T(0);
-    }
-    r.rho = __ldg(pgas);
-    T B[3], v[3];
+    for (int k = 0; k < 3; ++k) cp_async_elem(dst + k * PL, pb + k * a.B0.vs);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) cp_async_elem(dst + (3 + k) * PL, pg + (k + 1) * a.gas0.vs);
+    cp_async_elem(dst + 6 * PL, pg);
     if (have_k) {
-      const T* pbk = static_cast<const T*>(a.Bk.p) + pBk + col.oBk;
-      const T* pvk_ = static_cast<const T*>(a.vk.p) + pvk + col.ovk;
+      const T* pbk = col.Bk + (long long)mx * a.Bk.s[0];
+      const T* pvk = col.vk + (long long)mx * a.vk.s[0];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        r.Bk[k] = __ldg(pbk + k * a.Bk.vs);
-        r.vk[k] = __ldg(pvk_ + k * a.vk.vs);
-        if (midpoint) { B[k] = (r.Bk[k] + r.B0[k]) / T(2); v[k] = (r.vk[k] + r.v0[k]) / T(2); }
-        else { B[k] = r.Bk[k]; v[k] = r.vk[k]; }
+        cp_async_elem(dst + (7 + k) * PL, pbk + k * a.Bk.vs);
+        cp_async_elem(dst + (10 + k) * PL, pvk + k * a.vk.vs);
       }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { r.Bk[k] = r.B0[k]; r.vk[k] = r.v0[k]; B[k] = r.B0[k]; v[k] = r.v0[k]; }
     }
-    if (fx) { B[1] = -B[1]; v[1] = -v[1]; }       // x axis (axis 1) -> component 1
-    if (col.f2) { B[2] = -B[2]; v[2] = -v[2]; }
+  };
+  // planes beyond xe + 1 are never published; their group is committed empty
+  auto issue_plane = [&](int p) {
+    if (p <= xe) {
+      bool fx;
+      const int mx = map_index<ND>(p, g.n[0], g.bc[0][0], g.bc[0][1], fx);
+      T* st = stage + ((p - xs + 1) & 3) * NRAW * PL;
+      issue_cell(own, mx, st + wown);
+      if (hpos >= 0) issue_cell(halo, mx, st + hpos);
+    }
+    cp_async_commit();
+  };
+  // argument (R_k + R_0)/2 or R_k and E = B x v of one staged cell -> ring
+  auto publish_cell = [&](const T* src, bool fx, bool f2, T* wdst) {
+    T B[3], v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const T b0 = src[k * PL];
+      const T v0 = (k < ND) ? src[(3 + k) * PL] : T(0);
+      if (have_k) {
+        const T bk = src[(7 + k) * PL], vk = src[(10 + k) * PL];
+        if (midpoint) { B[k] = (bk + b0) / T(2); v[k] = (vk + v0) / T(2); }
+        else { B[k] = bk; v[k] = vk; }
+      } else {
+        B[k] = b0;
+        v[k] = v0;
+      }
+    }
+    if (fx) { B[1] = -B[1]; v[1] = -v[1]; }
+    if (f2) { B[2] = -B[2]; v[2] = -v[2]; }
     wdst[0 * PL] = B[0];
     wdst[1 * PL] = B[1];
     wdst[2 * PL] = B[2];
@@ -604,25 +645,19 @@ __global__ void __launch_bounds__(256) mag_iter_tiled(const MagIterArgs a, const
     wdst[4 * PL] = B[2] * v[0] - B[0] * v[2];
     wdst[5 * PL] = B[0] * v[1] - B[1] * v[0];
   };
-  auto load_plane = [&](int xp, int slot, Raw& r) {
+  auto publish_plane = [&](int p) {
     bool fx;
-    const int mx = map_index<ND>(xp, g.n[0], g.bc[0][0], g.bc[0][1], fx);
-    const long long pB0 = (long long)mx * a.B0.s[0], pg = (long long)mx * a.gas0.s[0];
-    const long long pBk = have_k ? (long long)mx * a.Bk.s[0] : 0, pvk = have_k ? (long long)mx * a.vk.s[0] : 0;
+    (void)map_index<ND>(p, g.n[0], g.bc[0][0], g.bc[0][1], fx);
+    const int slot = (p - xs + 1) & 3;
+    const T* st = stage + slot * NRAW * PL;
     T* w = ring + slot * 6 * PL;
-    load_cell(own, pB0, pg, pBk, pvk, fx, r, w + (ty + YO) * WZ + tz + 1);
-    if (hpos >= 0) {
-      Raw rh;
-      load_cell(halo, pB0, pg, pBk, pvk, fx, rh, w + hpos);
-    }
+    publish_cell(st + wown, fx, own.f2, w + wown);
+    if (hpos >= 0) publish_cell(st + hpos, fx, halo.f2, w + hpos);
   };
 
-  Raw rC, rN;
-  load_plane(xs - 1, 0, rC);
-  load_plane(xs, 1, rC);
   T ch[2] = {T(0), T(0)};
-  const long long oB1 = (long long)gz * a.Bk1.s[LA] + (ND == 3 ? (long long)gy * a.Bk1.s[1] : 0);
-  const long long ov1 = (long long)gz * a.vk1.s[LA] + (ND == 3 ? (long long)gy * a.vk1.s[1] : 0);
+  T* const pB1 = static_cast<T*>(a.Bk1.p) + (long long)gz * a.Bk1.s[LA] + (ND == 3 ? (long long)gy * a.Bk1.s[1] : 0);
+  T* const pv1 = static_cast<T*>(a.vk1.p) + (long long)gz * a.vk1.s[LA] + (ND == 3 ? (long long)gy * a.vk1.s[1] : 0);
 #if AMX_STRICT
   const T hdx = c.dx;
 #else
@@ -636,61 +671,80 @@ __global__ void __launch_bounds__(256) mag_iter_tiled(const MagIterArgs a, const
     return hdx * (fp - fm);
 #endif
   };
-
-  int sM = 0, sC = 1;  // ring slots of planes x-1 and x
-  for (int x = xs; x < xe; ++x) {
-    const int sP = (sC + 1) & 3;
-    load_plane(x + 1, sP, rN);
-    __syncthreads();
-    if (col_active) {
-      const T* wm = ring + sM * 6 * PL + (ty + YO) * WZ + tz + 1;
-      const T* wc = ring + sC * 6 * PL + (ty + YO) * WZ + tz + 1;
-      const T* wp = ring + sP * 6 * PL + (ty + YO) * WZ + tz + 1;
-      // field f (0..2 = B, 3..5 = E): d/dx, d/d(lane axis), d/dy (3-D)
-      auto ddx = [&](int f) { return cd(wp[f * PL], wm[f * PL]); };
-      auto ddl = [&](int f) { return cd(wc[f * PL + 1], wc[f * PL - 1]); };
-      auto ddy = [&](int f) { return cd(wc[f * PL + WZ], wc[f * PL - WZ]); };
-      T curlE[3], curlB[3];
-      if constexpr (ND == 3) {  // curl3D: lane axis is z
-        curlB[0] = ddy(2) - ddl(1); curlB[1] = ddl(0) - ddx(2); curlB[2] = ddx(1) - ddy(0);
-        curlE[0] = ddy(5) - ddl(4); curlE[1] = ddl(3) - ddx(5); curlE[2] = ddx(4) - ddy(3);
-      } else {  // curl2D: lane axis is y
-        curlB[0] = ddl(2); curlB[1] = -ddx(2); curlB[2] = ddx(1) - ddl(0);
-        curlE[0] = ddl(5); curlE[1] = -ddx(5); curlE[2] = ddx(4) - ddl(3);
-      }
-      const T Bc[3] = {wc[0], wc[PL], wc[2 * PL]};
-      T cr[3];
-      cr[0] = Bc[1] * curlB[2] - Bc[2] * curlB[1];
-      cr[1] = Bc[2] * curlB[0] - Bc[0] * curlB[2];
-      cr[2] = Bc[0] * curlB[1] - Bc[1] * curlB[0];
-#if !AMX_STRICT
-      const T ir = rdiv(T(1), rC.rho);
-#endif
-      T dB = T(0), dv = T(0);
-      T* pB1 = static_cast<T*>(a.Bk1.p) + oB1 + (long long)x * a.Bk1.s[0];
-      T* pv1 = static_cast<T*>(a.vk1.p) + ov1 + (long long)x * a.vk1.s[0];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-#if AMX_STRICT
-        const T phiB = cr[k] / rC.rho;
-#else
-        const T phiB = cr[k] * ir;
-#endif
-        const T Bn = rC.B0[k] - dt * curlE[k];
-        const T vn = rC.v0[k] - dt * phiB;
-        dB = dB + sq(rabs(rC.Bk[k] - Bn));
-        dv = dv + sq(rabs(rC.vk[k] - vn));
-        pB1[k * a.Bk1.vs] = Bn;
-        pv1[k * a.vk1.vs] = vn;
-      }
-      ch[0] = rmax(ch[0], dB);
-      ch[1] = rmax(ch[1], dv);
+  // update of plane x from ring slots of planes x-1, x, x+1 and the staged raw centre values
+  auto update = [&](int x) {
+    const int sC = (x - xs + 1) & 3, sM = (sC + 3) & 3, sP = (sC + 1) & 3;
+    const T* wm = ring + sM * 6 * PL + wown;
+    const T* wc = ring + sC * 6 * PL + wown;
+    const T* wp = ring + sP * 6 * PL + wown;
+    const T* rw = stage + sC * NRAW * PL + wown;
+    auto ddx = [&](int f) { return cd(wp[f * PL], wm[f * PL]); };
+    auto ddl = [&](int f) { return cd(wc[f * PL + 1], wc[f * PL - 1]); };
+    auto ddy = [&](int f) { return cd(wc[f * PL + WZ], wc[f * PL - WZ]); };
+    T curlE[3], curlB[3];
+    if constexpr (ND == 3) {  // curl3D: lane axis is z
+      curlB[0] = ddy(2) - ddl(1); curlB[1] = ddl(0) - ddx(2); curlB[2] = ddx(1) - ddy(0);
+      curlE[0] = ddy(5) - ddl(4); curlE[1] = ddl(3) - ddx(5); curlE[2] = ddx(4) - ddy(3);
+    } else {  // curl2D: lane axis is y
+      curlB[0] = ddl(2); curlB[1] = -ddx(2); curlB[2] = ddx(1) - ddl(0);
+      curlE[0] = ddl(5); curlE[1] = -ddx(5); curlE[2] = ddx(4) - ddl(3);
     }
-    rC = rN;
-    sM = sC;
-    sC = sP;
+    const T Bc[3] = {wc[0], wc[PL], wc[2 * PL]};
+    T cr[3];
+    cr[0] = Bc[1] * curlB[2] - Bc[2] * curlB[1];
+    cr[1] = Bc[2] * curlB[0] - Bc[0] * curlB[2];
+    cr[2] = Bc[0] * curlB[1] - Bc[1] * curlB[0];
+    const T rho = rw[6 * PL];
+#if !AMX_STRICT
+    const T ir = rdiv(T(1), rho);
+#endif
+    T dB = T(0), dv = T(0);
+    T* qB = pB1 + (long long)x * a.Bk1.s[0];
+    T* qv = pv1 + (long long)x * a.vk1.s[0];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#if AMX_STRICT
+      const T phiB = cr[k] / rho;
+#else
+      const T phiB = cr[k] * ir;
+#endif
+      const T b0 = rw[k * PL];
+      const T v0 = (k < ND) ? rw[(3 + k) * PL] : T(0);
+      const T Bn = b0 - dt * curlE[k];
+      const T vn = v0 - dt * phiB;
+      const T bk = have_k ? rw[(7 + k) * PL] : b0;
+      const T vk = have_k ? rw[(10 + k) * PL] : v0;
+      dB = dB + sq(rabs(bk - Bn));
+      dv = dv + sq(rabs(vk - vn));
+      qB[k * a.Bk1.vs] = Bn;
+      qv[k * a.vk1.vs] = vn;
+    }
+    ch[0] = rmax(ch[0], dB);
+    ch[1] = rmax(ch[1], dv);
+  };
+
+  // ---- prologue: planes xs-1 .. xs+2 in flight, (B, E) of xs-1, xs, xs+1 published
+  issue_plane(xs - 1);
+  issue_plane(xs);
+  issue_plane(xs + 1);
+  issue_plane(xs + 2);
+  cp_async_wait<2>();
+  publish_plane(xs - 1);
+  publish_plane(xs);
+  // stage slot of plane xs-1 is free again (its raw values are never needed)
+  issue_plane(xs + 3);
+  cp_async_wait<2>();
+  publish_plane(xs + 1);
+  // ---- steady state: at step x the groups of planes x+2 and x+3 are outstanding
+  for (int x = xs; x < xe; ++x) {
+    cp_async_wait<1>();  // plane x+2 has landed (own entries)
+    __syncthreads();     // ring(x+1) visible to all; every thread is done with update(x-1)
+    if (x + 2 <= xe) publish_plane(x + 2);
+    if (col_active) update(x);
+    issue_plane(x + 4);  // into the stage slot of plane x, just consumed by this thread
   }
-  ch[0] = rsqrt_(ch[0]);  // sqrt is monotone: max of norms = norm of max of squares
+  cp_async_wait<0>();
+  ch[0] = rsqrt_(ch[0]);  // sqrt is monotone: max of norms = norm of the max of squares
   ch[1] = rsqrt_(ch[1]);
   {
     __shared__ T red[2][8];
