@@ -104,6 +104,7 @@ AMX_DI Consts<T> make_consts(const NumPar& np) {
   Consts<T> c;
   c.gamma = (T)np.gamma;
   c.gm1 = c.gamma - T(1);
+  c.inv_gm1 = T(1) / c.gm1;
   c.dx = (T)np.dx;
   c.inv_dx = (T)(1.0 / np.dx);
   c.half_dx = (T)(np.dx / 2);

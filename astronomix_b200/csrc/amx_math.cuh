@@ -68,6 +68,7 @@ template <typename T> AMX_DI T sgn(T a) { return a > T(0) ? T(1) : (a < T(0) ? T
 template <typename T>
 struct Consts {
   T gamma, gm1;     // gamma, gamma - 1 (in T)
+  T inv_gm1;        // 1/(gamma-1), used by the FAST flavour only
   T dx, inv_dx;     // T(dx), T(1/dx): "1 / grid_spacing * stencil" multiplies by T(1/dx)
   T half_dx;        // T(dx/2): split reconstruction distances
   T va_eps;         // T(3*dx): van Albada epsilon (Q10)
@@ -105,7 +106,11 @@ AMX_DI T absvel_sq(const Gas<T, ND>& s) {
 // _equations.py:253-266: p/(gamma-1) + 0.5*rho*u^2
 template <typename T, int ND>
 AMX_DI T total_energy(const Gas<T, ND>& s, const Consts<T>& c) {
-  return rdiv(s.q[Gas<T, ND>::P], c.gm1) + (T(0.5) * s.q[0]) * absvel_sq(s);
+#if AMX_STRICT
+  return s.q[Gas<T, ND>::P] / c.gm1 + (T(0.5) * s.q[0]) * absvel_sq(s);
+#else
+  return s.q[Gas<T, ND>::P] * c.inv_gm1 + (T(0.5) * s.q[0]) * absvel_sq(s);
+#endif
 }
 
 // _equations.py:104-156
@@ -175,7 +180,8 @@ AMX_DI Gas<T, ND> euler_flux(const Gas<T, ND>& s, int ax, const Consts<T>& c) {
 // min(a,b) for two positives, max(a,b) for two negatives and (signed) zero otherwise.
 template <typename T>
 AMX_DI T minmod(T a, T b) {
-  return (a > T(0) && b > T(0)) ? rmin(a, b) : ((a < T(0) && b < T(0)) ? rmax(a, b) : T(0));
+  // max(0, min(a,b)) + min(0, max(a,b)): exact, branch-free, 4 FMNMX + 1 FADD
+  return rmax(T(0), rmin(a, b)) + rmin(T(0), rmax(a, b));
 }
 template <typename T>
 AMX_DI T maxmod(T a, T b) {  // limiters.py:35-37
@@ -233,6 +239,7 @@ AMX_DI Gas<T, ND> slopes(const Gas<T, ND>& m, const Gas<T, ND>& s, const Gas<T, 
 template <typename T, int ND>
 AMX_DI Gas<T, ND> hll_flux(const Gas<T, ND>& L, const Gas<T, ND>& R, int ax, const Consts<T>& c) {
   constexpr int P = ND + 1;
+#if AMX_STRICT
   const T uL = L.q[ax], uR = R.q[ax];
   const T cL = sound_speed(L.q[0], L.q[P], c), cR = sound_speed(R.q[0], R.q[P], c);
   const Gas<T, ND> FL = euler_flux(L, ax, c), FR = euler_flux(R, ax, c);
@@ -242,17 +249,45 @@ AMX_DI Gas<T, ND> hll_flux(const Gas<T, ND>& L, const Gas<T, ND>& R, int ax, con
   Gas<T, ND> F;
   const T den = SR - SL;
   const T SLSR = SL * SR;
-#if AMX_STRICT
 #pragma unroll
   for (int k = 0; k < ND + 2; ++k)
     F.q[k] = (SR * FL.q[k] - SL * FR.q[k] + SLSR * (UR.q[k] - UL.q[k])) / den;
-#else
-  const T iden = rdiv(T(1), den);
-#pragma unroll
-  for (int k = 0; k < ND + 2; ++k)
-    F.q[k] = (SR * FL.q[k] - SL * FR.q[k] + SLSR * (UR.q[k] - UL.q[k])) * iden;
-#endif
   return F;
+#else
+  // Same flux, arranged for the issue slots: one reciprocal per density and per interface,
+  // momenta and energies formed once and shared by the flux and the conserved state,
+  // F = a*FL - b*FR + ab*(UR - UL) with a = SR/(SR-SL), b = SL/(SR-SL), ab = a*SL.
+  T m[2][ND], E[2], un[2], cs[2], pr[2], rho[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const Gas<T, ND>& W = s == 0 ? L : R;
+    rho[s] = W.q[0];
+    pr[s] = W.q[P];
+    un[s] = W.q[ax];
+    cs[s] = rsqrt_((c.gamma * pr[s]) * rdiv(T(1), rho[s]));
+    T ke = ND == 3 ? T(1e-20) : T(0);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      m[s][k] = rho[s] * W.q[k + 1];
+      ke = ke + W.q[k + 1] * W.q[k + 1];
+    }
+    E[s] = pr[s] * c.inv_gm1 + (T(0.5) * rho[s]) * ke;
+  }
+  const T SR = rmax(rmax(un[0] + cs[0], un[1] + cs[1]), T(0));
+  const T SL = rmin(rmin(un[0] - cs[0], un[1] - cs[1]), T(0));
+  const T iden = rdiv(T(1), SR - SL);
+  const T a = SR * iden, b = SL * iden, ab = a * SL;
+  Gas<T, ND> F;
+  F.q[0] = a * m[0][ax - 1] - b * m[1][ax - 1] + ab * (rho[1] - rho[0]);
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    T fl = un[0] * m[0][k], fr = un[1] * m[1][k];
+    if (k == ax - 1) { fl = fl + pr[0]; fr = fr + pr[1]; }
+    F.q[k + 1] = a * fl - b * fr + ab * (m[1][k] - m[0][k]);
+  }
+  F.q[P] = a * (un[0] * (E[0] + pr[0])) - b * (un[1] * (E[1] + pr[1])) + ab * (E[1] - E[0]);
+  return F;
+#endif
 }
 
 // _riemann_solver/hll.py:123-261 (HLLC; LM = HLLC-LM low-Mach rescaling of SL, SR in the

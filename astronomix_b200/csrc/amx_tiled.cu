@@ -59,6 +59,7 @@ AMX_DI Consts<T> make_consts(const NumPar& np) {
   Consts<T> c;
   c.gamma = (T)np.gamma;
   c.gm1 = c.gamma - T(1);
+  c.inv_gm1 = T(1) / c.gm1;
   c.dx = (T)np.dx;
   c.inv_dx = (T)(1.0 / np.dx);
   c.half_dx = (T)(np.dx / 2);
@@ -128,7 +129,6 @@ __global__ void __launch_bounds__(256) hydro_stage_tiled(const StageArgs a, cons
   const int xe = min(xs + xchunk, g.n[0]);
   if (xs >= xe) return;
   const T dt = *static_cast<const T*>(a.dt) * (T)a.dt_scale;
-  const T dtdx = c.inv_dx;  // the update is ((1/dx) * (F_i - F_{i+1})) * dt (evolve_state.py:398-403)
 
   // ---- this thread's own column and its extra window-halo cell, boundary rules applied
   bool own_fy = false, own_fz = false, h_fy = false, h_fz = false;
@@ -202,8 +202,16 @@ __global__ void __launch_bounds__(256) hydro_stage_tiled(const StageArgs a, cons
     }
   };
 
+  // conservative update of one variable: U + ((1/dx) * (Fl - Fr)) * dt (evolve_state.py:398-403)
+#if AMX_STRICT
+  auto upd = [&](T U, T fl, T fr) -> T { return U + (c.inv_dx * (fl - fr)) * dt; };
+#else
+  const T dtdx = c.inv_dx * dt;
+  auto upd = [&](T U, T fl, T fr) -> T { return U + dtdx * (fl - fr); };
+#endif
+
   // ---- prologue: planes xs-2 .. xs+1
-  T sC[NV], sP[NV], dC[NV], DxP[NV], FxL[NV], hv[NV];
+  T sC[NV], sP[NV], dC[NV], FxL[NV], hv[NV];
   {
     T sM2[NV], sM1[NV];
     load_plane(xs - 2, sM2, hv, false);
@@ -216,9 +224,8 @@ __global__ void __launch_bounds__(256) hydro_stage_tiled(const StageArgs a, cons
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const T d0 = sC[k] - sM1[k];
-      DxP[k] = sP[k] - sC[k];
       const T dM1 = half_slope<T, LIM>(sM1[k] - sM2[k], d0, a.np.lim, c);
-      dC[k] = half_slope<T, LIM>(d0, DxP[k], a.np.lim, c);
+      dC[k] = half_slope<T, LIM>(d0, sP[k] - sC[k], a.np.lim, c);
       L.q[k] = sM1[k] + dM1;
       R.q[k] = sC[k] - dC[k];
     }
@@ -237,31 +244,30 @@ __global__ void __launch_bounds__(256) hydro_stage_tiled(const StageArgs a, cons
 #pragma unroll
   for (int k = 0; k < ND; ++k) alpha_lf[k] = RS == RS_LF ? static_cast<const T*>(a.alpha_lf)[k] : T(0);
 
-  const long long out_col = (long long)gz * a.out.s[LA] + (ND == 3 ? (long long)gy * a.out.s[1] : 0);
-  const long long in0_col = a.in0.p ? ((long long)gz * a.in0.s[LA] + (ND == 3 ? (long long)gy * a.in0.s[1] : 0)) : 0;
+  T* const out_col = static_cast<T*>(a.out.p) + (long long)gz * a.out.s[LA] + (ND == 3 ? (long long)gy * a.out.s[1] : 0);
+  const T* const in0_col = a.in0.p ? static_cast<const T*>(a.in0.p) + (long long)gz * a.in0.s[LA] +
+                                         (ND == 3 ? (long long)gy * a.in0.s[1] : 0)
+                                   : nullptr;
+  const int wc = (ty + YO) * WZ + tz + 2;  // own cell in the window
+  const int dzo = ty * (TZ + 2) + tz + 1;  // own entry of Dz (per variable: + k*TY*(TZ+2))
+  const int fzo = ty * (TZ + 1) + tz;      // own lower-interface entry of Fz
+  const int dyo = (ty + 1) * TZ + tz;      // own entry of Dy
+  const int fyo = ty * TZ + tz;            // own lower-interface entry of Fy
 
   int slotC = 0;
   for (int x = xs; x < xe; ++x) {
     const int slotN = slotC == 0 ? 2 : slotC - 1;  // (slotC + 2) % 3
     T sN[NV];
-    load_plane(x + 2, sN, hv, true);
+    load_plane(x + 2, sN, hv, true);  // consumed at the end of the step
     const T* w = ring + slotC * NV * PL;
-    const int wc = (ty + YO) * WZ + tz + 2;  // own cell in the window
 
-    // ---- half-slopes of the own cell along z (and y), published for the neighbours
-    T zM[NV], dZ[NV], yM[NV], dY[NV];
+    // ---- phase 1: half-slopes of the own cell along z (and y), published for the neighbours
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      zM[k] = w[k * PL + wc - 1];
-      const T zp = w[k * PL + wc + 1];
-      dZ[k] = half_slope<T, LIM>(sC[k] - zM[k], zp - sC[k], a.np.lim, c);
-      Dz[(k * TY + ty) * (TZ + 2) + tz + 1] = dZ[k];
-      if constexpr (ND == 3) {
-        yM[k] = w[k * PL + wc - WZ];
-        const T yp = w[k * PL + wc + WZ];
-        dY[k] = half_slope<T, LIM>(sC[k] - yM[k], yp - sC[k], a.np.lim, c);
-        Dy[(k * (TY + 2) + ty + 1) * TZ + tz] = dY[k];
-      }
+      const T s0 = sC[k];
+      Dz[k * TY * (TZ + 2) + dzo] = half_slope<T, LIM>(s0 - w[k * PL + wc - 1], w[k * PL + wc + 1] - s0, a.np.lim, c);
+      if constexpr (ND == 3)
+        Dy[k * (TY + 2) * TZ + dyo] = half_slope<T, LIM>(s0 - w[k * PL + wc - WZ], w[k * PL + wc + WZ] - s0, a.np.lim, c);
     }
     // tile-edge slopes: cells one outside the tile (rows -1 / TY, columns -1 / TZ)
     if constexpr (ND == 3) {
@@ -296,46 +302,30 @@ __global__ void __launch_bounds__(256) hydro_stage_tiled(const StageArgs a, cons
         }
       }
     }
-
-    // ---- x direction from registers: flux at x+1/2
-    T dP[NV], DxN[NV], FxR[NV];
-    {
-      Gas<T, ND> L, R;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        DxN[k] = sN[k] - sP[k];
-        dP[k] = half_slope<T, LIM>(DxP[k], DxN[k], a.np.lim, c);
-        L.q[k] = sC[k] + dC[k];
-        R.q[k] = sP[k] - dP[k];
-      }
-      const Gas<T, ND> F = riemann<T, ND, RS>(L, R, 1, alpha_lf[0], c);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) FxR[k] = F.q[k];
-    }
     __syncthreads();  // published slopes visible
 
-    // ---- fluxes at the own cell's lower z (and y) interfaces, published
+    // ---- phase 2: fluxes at the own cell's lower z (and y) interfaces, published
     {
       Gas<T, ND> L, R;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        L.q[k] = zM[k] + Dz[(k * TY + ty) * (TZ + 2) + tz];
-        R.q[k] = sC[k] - dZ[k];
+        L.q[k] = w[k * PL + wc - 1] + Dz[k * TY * (TZ + 2) + dzo - 1];
+        R.q[k] = sC[k] - Dz[k * TY * (TZ + 2) + dzo];
       }
       const Gas<T, ND> F = riemann<T, ND, RS>(L, R, LA + 1, alpha_lf[LA], c);
 #pragma unroll
-      for (int k = 0; k < NV; ++k) Fz[(k * TY + ty) * (TZ + 1) + tz] = F.q[k];
+      for (int k = 0; k < NV; ++k) Fz[k * TY * (TZ + 1) + fzo] = F.q[k];
     }
     if constexpr (ND == 3) {
       Gas<T, ND> L, R;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        L.q[k] = yM[k] + Dy[(k * (TY + 2) + ty) * TZ + tz];
-        R.q[k] = sC[k] - dY[k];
+        L.q[k] = w[k * PL + wc - WZ] + Dy[k * (TY + 2) * TZ + dyo - TZ];
+        R.q[k] = sC[k] - Dy[k * (TY + 2) * TZ + dyo];
       }
       const Gas<T, ND> F = riemann<T, ND, RS>(L, R, 2, alpha_lf[1], c);
 #pragma unroll
-      for (int k = 0; k < NV; ++k) Fy[(k * (TY + 1) + ty) * TZ + tz] = F.q[k];
+      for (int k = 0; k < NV; ++k) Fy[k * (TY + 1) * TZ + fyo] = F.q[k];
     }
     // tile-edge fluxes: the interfaces above the last row / column of the tile
     if constexpr (ND == 3) {
@@ -378,33 +368,43 @@ __global__ void __launch_bounds__(256) hydro_stage_tiled(const StageArgs a, cons
         for (int k = 0; k < NV; ++k) Fz[k * (TZ + 1) + TZ] = F.q[k];
       }
     }
+
+    // ---- phase 3a: x direction from registers -- flux at x+1/2 (first use of plane x+2)
+    T dP[NV], FxR[NV];
+    {
+      Gas<T, ND> L, R;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        dP[k] = half_slope<T, LIM>(sP[k] - sC[k], sN[k] - sP[k], a.np.lim, c);
+        L.q[k] = sC[k] + dC[k];
+        R.q[k] = sP[k] - dP[k];
+      }
+      const Gas<T, ND> F = riemann<T, ND, RS>(L, R, 1, alpha_lf[0], c);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) FxR[k] = F.q[k];
+    }
     __syncthreads();  // published fluxes visible
 
-    // ---- conservative update, axis by axis like the reference, then prim (+ RK2 combine)
+    // ---- phase 3b: conservative update, axis by axis like the reference, prim (+ RK2 combine)
     {
       Gas<T, ND> sc;
 #pragma unroll
       for (int k = 0; k < NV; ++k) sc.q[k] = sC[k];
       Gas<T, ND> U = cons_from_prim(sc, c);
 #pragma unroll
-      for (int k = 0; k < NV; ++k) U.q[k] = U.q[k] + (dtdx * (FxL[k] - FxR[k])) * dt;
+      for (int k = 0; k < NV; ++k) U.q[k] = upd(U.q[k], FxL[k], FxR[k]);
       if constexpr (ND == 3) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          const T fl = Fy[(k * (TY + 1) + ty) * TZ + tz], fr = Fy[(k * (TY + 1) + ty + 1) * TZ + tz];
-          U.q[k] = U.q[k] + (dtdx * (fl - fr)) * dt;
-        }
+        for (int k = 0; k < NV; ++k)
+          U.q[k] = upd(U.q[k], Fy[k * (TY + 1) * TZ + fyo], Fy[k * (TY + 1) * TZ + fyo + TZ]);
       }
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const T fl = Fz[(k * TY + ty) * (TZ + 1) + tz], fr = Fz[(k * TY + ty) * (TZ + 1) + tz + 1];
-        U.q[k] = U.q[k] + (dtdx * (fl - fr)) * dt;
-      }
+      for (int k = 0; k < NV; ++k) U.q[k] = upd(U.q[k], Fz[k * TY * (TZ + 1) + fzo], Fz[k * TY * (TZ + 1) + fzo + 1]);
       Gas<T, ND> s = prim_from_cons(U, c);
       if (col_active) {
-        if (a.in0.p) {
+        if (in0_col) {
           Gas<T, ND> s0;
-          const T* p0 = static_cast<const T*>(a.in0.p) + in0_col + (long long)x * a.in0.s[0];
+          const T* p0 = in0_col + (long long)x * a.in0.s[0];
 #pragma unroll
           for (int k = 0; k < NV; ++k) s0.q[k] = __ldg(p0 + k * a.in0.vs);
           const Gas<T, ND> U0 = cons_from_prim(s0, c), U2 = cons_from_prim(s, c);
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(256) hydro_stage_tiled(const StageArgs a, cons
           for (int k = 0; k < NV; ++k) Um.q[k] = T(0.5) * (U0.q[k] + U2.q[k]);
           s = prim_from_cons(Um, c);
         }
-        T* po = static_cast<T*>(a.out.p) + out_col + (long long)x * a.out.s[0];
+        T* po = out_col + (long long)x * a.out.s[0];
 #pragma unroll
         for (int k = 0; k < NV; ++k) po[k * a.out.vs] = s.q[k];
         if (a.alpha_slots) {
@@ -430,7 +430,6 @@ __global__ void __launch_bounds__(256) hydro_stage_tiled(const StageArgs a, cons
       sC[k] = sP[k];
       sP[k] = sN[k];
       dC[k] = dP[k];
-      DxP[k] = DxN[k];
       FxL[k] = FxR[k];
     }
     slotC = slotC == 2 ? 0 : slotC + 1;
