@@ -1,0 +1,160 @@
+"""World-size-2 (gloo, CPU) test of the slab driver's host logic: decomposition, halo exchange
+pairing, all-reduces, step sequencing.  The kernels are replaced by a test-only backend built
+on the oracle; the decomposed run must equal the single-domain oracle run bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from astronomix_b200 import problems as pr
+from astronomix_b200 import option_classes as oc
+from astronomix_b200.slab import NG, SlabDriver
+from oracle import fv_oracle as fo
+
+
+class OracleBackend:
+    """Same interface as slab.AmxBackend, computed with the oracle on the local padded slab
+    treated as periodic: only the ghost planes come out wrong, and they are never used."""
+
+    def __init__(self, config, params, dtype):
+        self.o = fo.Opts.from_config(config, params)
+        self.o.boundary_handling = fo.PERIODIC_ROLL
+        self.t = np.float64 if dtype == torch.float64 else np.float32
+        self.gamma = self.t(params.gamma)
+        self.launches = 0
+
+    def _np(self, x):
+        return x.numpy()
+
+    def alpha(self, gas, out):
+        g = self._np(gas)[:, NG:-NG]
+        c = fo.speed_of_sound(g[0], g[self.o.p_i], self.gamma)
+        for k in range(self.o.dim):
+            out[k] = float(np.max(np.abs(g[k + 1]) + c))
+
+    def dt_from_alpha(self, alpha, time, t_end, dt_out):
+        a = self._np(alpha)[: self.o.dim].astype(self.t)
+        if self.o.split == fo.UNSPLIT:
+            dt = self.t(self.o.C_cfl) * 1 / np.sum(a / self.o.grid_spacing)
+        else:
+            dt = self.t(self.o.C_cfl) * self.o.grid_spacing / np.max(a)
+            if self.o.use_max_adaptive_timestep:
+                dt = min(dt, self.t(self.o.dt_max))
+        if time is not None:
+            dt = min(dt, self.t(t_end) - self.t(time.item()))
+        dt_out.fill_(float(dt))
+
+    def hydro_stage(self, gas_in, gas0, gas_out, dt, scale, alpha_lf, alpha_out):
+        h = self.t(dt.item()) * self.t(scale)
+        s = fo.evolve_gas_state_unsplit_inner(self._np(gas_in), h, self.gamma, self.o)
+        if gas0 is not None:
+            U = self.t(0.5) * (fo.conserved_state_from_primitive(self._np(gas0), self.gamma, self.o)
+                               + fo.conserved_state_from_primitive(s, self.gamma, self.o))
+            s = fo.primitive_state_from_conserved(U, self.gamma, self.o)
+        gas_out[:, NG:-NG] = torch.from_numpy(s[:, NG:-NG].copy())
+        if alpha_out is not None:
+            self.alpha(gas_out, alpha_out)
+
+    def split_sweep(self, gas_in, gas_out, axis, dt, scale, alpha_lf, alpha_out):
+        h = self.t(dt.item()) * self.t(scale)
+        s = fo.evolve_state_along_axis(self._np(gas_in), h, self.gamma, self.o, axis)
+        gas_out[:, NG:-NG] = torch.from_numpy(s[:, NG:-NG].copy())
+        if alpha_out is not None:
+            self.alpha(gas_out, alpha_out)
+
+    def magnetic_iter(self, B0, gas0, bvk, bvk1, dt, change_out):
+        o, dx, h = self.o, self.o.grid_spacing, self.t(dt.item())
+        B, g = self._np(B0), self._np(gas0)
+        v = np.zeros_like(B)
+        v[: o.dim] = g[1:1 + o.dim]
+        curl = fo.curl2D if o.dim == 2 else fo.curl3D
+        if bvk is None:
+            Bk, vk = B, v
+            aB, av = (B + B) / 2, (v + v) / 2
+        else:
+            Bk, vk = self._np(bvk)[:3], self._np(bvk)[3:]
+            aB, av = ((Bk + B) / 2, (vk + v) / 2) if o.fv_magnetic_integrator == fo.IMPLICIT_MIDPOINT else (Bk, vk)
+        B1 = B - h * curl(fo.cross(aB, av), dx)
+        v1 = v - h * (fo.cross(aB, curl(aB, dx)) / g[0])
+        inner = (slice(None), slice(NG, -NG))
+        change_out[0] = float(np.max(fo._norm0((Bk - B1)[inner])))
+        change_out[1] = float(np.max(fo._norm0((vk - v1)[inner])))
+        bvk1[:3, NG:-NG] = torch.from_numpy(B1[inner].copy())
+        bvk1[3:, NG:-NG] = torch.from_numpy(v1[inner].copy())
+
+    def magnetic_final(self, gas, bv_final, B_out, alpha_out):
+        o, t = self.o, self.t
+        g, X = self._np(gas), self._np(bv_final)
+        v = np.zeros_like(X[:3])
+        v[: o.dim] = g[1:1 + o.dim]
+        vn, rho = X[3:], g[0]
+        g53 = 5 / 3
+        E = fo.total_energy_from_primitives(rho, fo._norm0(v), g[o.p_i], g53)
+        E2 = E - t(0.5) * rho * fo._norm0(v) ** 2 + t(0.5) * rho * fo._norm0(vn) ** 2
+        p2 = fo.pressure_from_energy(E2, rho, fo._norm0(vn), g53)
+        g[1:1 + o.dim] = vn[: o.dim]
+        g[o.p_i] = p2
+        B_out.copy_(bv_final[:3])
+        if alpha_out is not None:
+            self.alpha(gas, alpha_out)
+
+
+def _worker(rank, world, port, case, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dim, n, mhd, split, steps = case
+        kw = dict(split=oc.SPLIT, time_integrator=oc.MUSCL) if split else {}
+        config, params, rv = pr.make(dim, n, mhd=mhd, dtype=np.float64, riemann_solver=oc.HLLC, **kw)
+        s = pr.smooth_random(dim, n, mhd=mhd, seed=17, dtype=np.float64)
+        drv = SlabDriver(config, params, rv, (n,) * dim, torch.float64, torch.device("cpu"),
+                         backend=OracleBackend(config, params, torch.float64))
+        drv.scatter(torch.from_numpy(s))
+        info = drv.run(max_steps=steps)
+        full = drv.gather()
+        if rank == 0:
+            np.save(out_path, full.numpy())
+            np.save(out_path + ".iters.npy", np.array([info.steps, info.magnetic_iterations, drv.collectives]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("case", [(2, 16, False, False, 3), (2, 16, True, False, 3), (3, 8, True, False, 2),
+                                  (2, 16, True, True, 2)])
+def test_two_rank_slab_equals_single_domain(case, tmp_path):
+    dim, n, mhd, split, steps = case
+    out = str(tmp_path / "slab.npy")
+    mp.spawn(_worker, args=(2, _free_port(), case, out), nprocs=2, join=True)
+    got = np.load(out)
+    nsteps, iters, colls = np.load(out + ".iters.npy")
+    kw = dict(split=oc.SPLIT, time_integrator=oc.MUSCL) if split else {}
+    config, params, rv = pr.make(dim, n, mhd=mhd, dtype=np.float64, riemann_solver=oc.HLLC, **kw)
+    s = pr.smooth_random(dim, n, mhd=mhd, seed=17, dtype=np.float64)
+    ref, info = fo.time_integration(s, fo.Opts.from_config(config, params), max_steps=steps, return_info=True)
+    assert nsteps == info["steps"] == steps
+    if mhd:
+        assert iters == sum(info["iterations"])
+    assert colls > 0
+    assert np.array_equal(got, ref), np.abs(got - ref).max()
+
+
+def test_single_rank_driver_wraps_locally():
+    """world = 1 (no process group): the driver's own periodic wrap."""
+    config, params, rv = pr.make(2, 16, mhd=True, dtype=np.float64)
+    s = pr.smooth_random(2, 16, mhd=True, seed=2, dtype=np.float64)
+    drv = SlabDriver(config, params, rv, (16, 16), torch.float64, torch.device("cpu"),
+                     backend=OracleBackend(config, params, torch.float64))
+    drv.scatter(torch.from_numpy(s))
+    drv.run(max_steps=3)
+    ref = fo.time_integration(s, fo.Opts.from_config(config, params), max_steps=3)
+    assert np.array_equal(drv.gather().numpy(), ref)
