@@ -458,6 +458,12 @@ bool force_generic() {
   return v;
 }
 
+// AMX_NO_VEC=1 skips the z-vectorised kernels (amx_vec.cu) in favour of the scalar tiled ones
+bool no_vec() {
+  static const bool v = [] { const char* e = getenv("AMX_NO_VEC"); return e && e[0] == '1'; }();
+  return v;
+}
+
 struct Engine {
   const amx_desc* d;
   Layout L;
@@ -609,6 +615,8 @@ struct Engine {
     a.dt = dt; a.change_slots = cslots();
     ++launches;
     ProfScope ps(PC_MAG_ITER, st);
+    const bool vec = !force_generic() && !no_vec() && (strict ? amx_strict::vec_mag_supported(a) : amx_fast::vec_mag_supported(a));
+    if (vec) return strict ? amx_strict::launch_mag_iter_vec(a, st) : amx_fast::launch_mag_iter_vec(a, st);
     const bool tiled = !force_generic() && (strict ? amx_strict::tiled_mag_supported(a) : amx_fast::tiled_mag_supported(a));
     if (tiled) return strict ? amx_strict::launch_mag_iter_tiled(a, st) : amx_fast::launch_mag_iter_tiled(a, st);
     return strict ? amx_strict::launch_mag_iter(a, st) : amx_fast::launch_mag_iter(a, st);

@@ -1,0 +1,598 @@
+// amx_vec.cu -- z-vectorised plane-streaming kernels (fp32): every thread owns a PAIR of cells
+// adjacent along the contiguous axis, global traffic is 64-bit, the arithmetic of the two cells
+// is issued as packed f32x2 instructions (FADD2 / FMUL2 / FFMA2 on sm_100a), the x direction of
+// the stencil lives in registers and only the (y, z) neighbours go through shared memory.
+//
+// mag_iter_vec<ND>: one evaluation R_{k+1} = R_0 - dt * Psi(arg(R_k, R_0)) of the Pang-Wu fixed
+// point (_magnetic_field_update.py:82-165; curls: _vector_maths.py:55-100).
+//   * block = 8 compute warps + 1 halo warp.  3-D: the compute threads cover a 16 (y) x 32 (z)
+//     column tile as 16 x 16 pairs; the halo warp loads the two y-halo rows (one pair per lane)
+//     and the 2 x 16 z-halo cells (one scalar per lane).  2-D: 1 x 512 tile, two halo scalars.
+//   * the block marches along x over a chunk of planes.  Per plane a thread loads the raw
+//     B_0, v_0, rho, B_k, v_k of its pair (13 x LDG.64), forms the fixed-point argument and
+//     E = B x v once, publishes (B, E) to a 3-slot shared-memory ring for its y / z neighbours and
+//     keeps its own column of (B, E) in registers for the x differences: one barrier per plane.
+//   * 41 load/store instructions per pair per plane (the scalar tiled kernel: ~100 per cell).
+// Compiled twice like the other kernel files (fast / strict arithmetic); STRICT keeps the
+// reference's operation order (no contraction), so it is bitwise equal to the generic kernel.
+#include "amx_internal.h"
+#include "amx_math.cuh"
+
+#include <cstdlib>
+#include <type_traits>
+
+#if AMX_STRICT
+#define AMX_NS amx_strict
+#else
+#define AMX_NS amx_fast
+#endif
+
+namespace AMX_NS {
+using namespace amx;
+
+namespace vec {
+
+// ---------------------------------------------------------------- packed pair of floats
+struct F2 {
+  float x, y;
+};
+AMX_DI F2 mk2(float a, float b) { F2 r; r.x = a; r.y = b; return r; }
+AMX_DI F2 bc2(float a) { return mk2(a, a); }
+#if AMX_STRICT
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, so the strict
+// flavour uses the never-fused scalar intrinsics (same IEEE results, reference operation order).
+AMX_DI F2 operator+(F2 a, F2 b) { return mk2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+AMX_DI F2 operator-(F2 a, F2 b) { return mk2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+AMX_DI F2 operator*(F2 a, F2 b) { return mk2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+#else
+#define AMX_F2_BINOP(NAME, PTX)                                                                      \
+  AMX_DI F2 NAME(F2 a, F2 b) {                                                                       \
+    F2 d;                                                                                            \
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; " PTX                   \
+        " rd, ra, rb; mov.b64 {%0, %1}, rd; }"                                                       \
+        : "=f"(d.x), "=f"(d.y)                                                                       \
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                   \
+    return d;                                                                                        \
+  }
+AMX_F2_BINOP(operator+, "add.rn.f32x2")
+AMX_F2_BINOP(operator-, "sub.rn.f32x2")
+AMX_F2_BINOP(operator*, "mul.rn.f32x2")
+#undef AMX_F2_BINOP
+#endif
+AMX_DI F2 operator-(F2 a) { return mk2(-a.x, -a.y); }
+AMX_DI F2 max2(F2 a, F2 b) { return mk2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+AMX_DI F2 abs2(F2 a) { return mk2(fabsf(a.x), fabsf(a.y)); }
+
+// streamed global loads: every input line is used once per block, so it must not take an L1
+// line (the L1 left beside ~180 KB of shared memory is smaller than the loads in flight)
+template <int LD>
+AMX_DI F2 ldg2(const float* p) {
+  F2 r;
+  if constexpr (LD == 0) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    r = mk2(v.x, v.y);
+  } else if constexpr (LD == 1) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  } else {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  }
+  return r;
+}
+template <int LD>
+AMX_DI float ldg1(const float* p) {
+  float r;
+  if constexpr (LD == 0) r = __ldg(p);
+  else asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+AMX_DI void stg2(float* p, F2 v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+AMX_DI F2 lds2(const float* p) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return mk2(v.x, v.y);
+}
+AMX_DI void sts2(float* p, F2 v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+
+AMX_DI int map_index(int i, int n, int bcl, int bcr, bool& flip) {
+  flip = false;
+  if (i < 0) {
+    if (bcl == BC_PERIODIC) return i + n;
+    if (bcl == BC_OPEN) return 0;
+    if (bcl == BC_REFLECTIVE) { flip = true; return -1 - i; }
+    return i;
+  }
+  if (i >= n) {
+    if (bcr == BC_PERIODIC) return i - n;
+    if (bcr == BC_OPEN) return n - 1;
+    if (bcr == BC_REFLECTIVE) { flip = true; return 2 * n - 1 - i; }
+    return i;
+  }
+  return i;
+}
+
+AMX_DI unsigned long long bits_of(float v) { return (unsigned long long)__float_as_uint(v); }
+
+// 7 compute warps + 1 halo warp (register allocation is per 4 warps: 8 warps x 128 registers
+// x 2 blocks fills the register file exactly)
+// CW compute warps + 1 halo warp
+template <int ND, int CW> struct VT;
+template <int CW> struct VT<3, CW> { static constexpr int TY = 2 * CW, TQ = 16; };
+template <int CW> struct VT<2, CW> { static constexpr int TY = 1, TQ = 32 * CW; };
+
+template <int ND, int CW>
+constexpr size_t mag_vec_smem_bytes() {
+  constexpr int TZ = 2 * VT<ND, CW>::TQ, WY = ND == 3 ? VT<ND, CW>::TY + 2 : 1, RS = TZ + 4;
+  return ((size_t)3 * 6 * WY * RS + (size_t)2 * 13 * 2 * 32 * CW) * sizeof(float);
+}
+
+// raw fixed-point data of one pair / one halo cell in one plane
+struct Raw {
+  F2 B0[3], v0[3], rho, Bk[3], vk[3];
+};
+// A column is the element offset of its plane-0 cell, shared by every array of the launch
+// (vec_mag_supported checks that all views have the same x / y strides).
+using Col = long long;
+template <int N> using IC = std::integral_constant<int, N>;
+
+// MODE 0: first iterate (R_k = R_0, Bk / vk absent); 1: implicit midpoint; 2: implicit Euler
+template <int ND, int MODE, int LD, int CW>
+__global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(const MagIterArgs a, const int xchunk) {
+  if (a.ctl_ro && (a.ctl_ro->done || (!a.first && !a.ctl_ro->mag_active))) return;
+  constexpr int kComputeThreads = 32 * CW, kThreads = kComputeThreads + 32;
+  constexpr int TY = VT<ND, CW>::TY, TQ = VT<ND, CW>::TQ, TZ = 2 * TQ;
+  constexpr int WY = ND == 3 ? TY + 2 : 1, RS = TZ + 4, YO = ND == 3 ? 1 : 0, LA = ND - 1;
+  constexpr int PL = WY * RS;   // floats per field per ring slot
+  constexpr int SLOT = 6 * PL;  // fields: B0 B1 B2 E0 E1 E2
+  constexpr bool have_k = MODE != 0;
+  extern __shared__ __align__(16) float smem[];  // [3][6][WY][RS]; own pairs at column 2 + 2*tq
+
+  const Geom& g = a.g;
+  const int tid = threadIdx.x;
+  const bool compute = tid < kComputeThreads;
+  const int z0 = blockIdx.x * TZ;
+  const int y0 = ND == 3 ? blockIdx.y * TY : 0;
+  const int chunk = ND == 3 ? blockIdx.z : blockIdx.y;
+  const int xs = chunk * xchunk;
+  const int xe = min(xs + xchunk, g.n[0]);
+  if (xs >= xe) return;
+  const float dt = *static_cast<const float*>(a.dt);
+#if AMX_STRICT
+  const float dxf = (float)a.np.dx;
+#else
+  const float hdx = 0.5f * (float)(1.0 / a.np.dx);
+#endif
+  // ragged tile edges: active rows / pairs of this tile
+  const int ta = ND == 3 ? min(TY, g.n[1] - y0) : 1;
+  const int tqa = min(TQ, (g.n[LA] - z0) >> 1);
+  // common element strides of a plane (x) and a row (y); uniform per-field base pointers
+  const long long sx = a.B0.s[0], sy = ND == 3 ? a.B0.s[1] : 0;
+  const float* const fB0 = static_cast<const float*>(a.B0.p);
+  const float* const fG = static_cast<const float*>(a.gas0.p);
+  const float* const fBk = static_cast<const float*>(a.Bk.p);
+  const float* const fvk = static_cast<const float*>(a.vk.p);
+  const long long vB0 = a.B0.vs, vG = a.gas0.vs, vBk = a.Bk.vs, vvk = a.vk.vs;
+
+  auto make_col = [&](int gy, int gz, Col& c) { c = gz + (ND == 3 ? (long long)gy * sy : 0); };
+  // planes -1 and n[0] are the only ones the x boundary rule can touch
+  bool flo, fhi;
+  const int mlo = map_index(-1, g.n[0], g.bc[0][0], g.bc[0][1], flo);
+  const int mhi = map_index(g.n[0], g.n[0], g.bc[0][0], g.bc[0][1], fhi);
+  auto plane_map = [&](int p, bool& fx) {
+    fx = p < 0 ? flo : (p >= g.n[0] ? fhi : false);
+    return p < 0 ? mlo : (p >= g.n[0] ? mhi : p);
+  };
+
+  // ---- loads
+  auto load_pair = [&](const Col& c, int mx, Raw& r) {
+    const long long o = c + (long long)mx * sx;
+    const float* pb = fB0 + o;
+    const float* pg = fG + o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.B0[k] = ldg2<LD>(pb + k * vB0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.v0[k] = k < ND ? ldg2<LD>(pg + (k + 1) * vG) : bc2(0.f);
+    r.rho = ldg2<LD>(pg);
+    if constexpr (have_k) {
+      const float* pbk = fBk + o;
+      const float* pvk = fvk + o;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        r.Bk[k] = ldg2<LD>(pbk + k * vBk);
+        r.vk[k] = ldg2<LD>(pvk + k * vvk);
+      }
+    }
+  };
+  auto load_scalar = [&](const Col& c, int mx, Raw& r) {
+    const long long o = c + (long long)mx * sx;
+    const float* pb = fB0 + o;
+    const float* pg = fG + o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.B0[k] = bc2(ldg1<LD>(pb + k * vB0));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.v0[k] = k < ND ? bc2(ldg1<LD>(pg + (k + 1) * vG)) : bc2(0.f);
+    r.rho = bc2(1.f);
+    if constexpr (have_k) {
+      const float* pbk = fBk + o;
+      const float* pvk = fvk + o;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        r.Bk[k] = bc2(ldg1<LD>(pbk + k * vBk));
+        r.vk[k] = bc2(ldg1<LD>(pvk + k * vvk));
+      }
+    }
+  };
+  // fixed-point argument (R_k + R_0)/2 or R_k, and E = B x v (_vector_maths.py:6-12)
+  auto argument = [&](const Raw& r, bool fx, bool f2, F2 (&B)[3], F2 (&E)[3]) {
+    F2 v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if constexpr (MODE == 1) {
+        B[k] = (r.Bk[k] + r.B0[k]) * bc2(0.5f);
+        v[k] = (r.vk[k] + r.v0[k]) * bc2(0.5f);
+      } else if constexpr (MODE == 2) {
+        B[k] = r.Bk[k];
+        v[k] = r.vk[k];
+      } else {
+        B[k] = r.B0[k];
+        v[k] = r.v0[k];
+      }
+    }
+    if (fx) { B[1] = -B[1]; v[1] = -v[1]; }
+    if (f2) { B[2] = -B[2]; v[2] = -v[2]; }
+    E[0] = B[1] * v[2] - B[2] * v[1];
+    E[1] = B[2] * v[0] - B[0] * v[2];
+    E[2] = B[0] * v[1] - B[1] * v[0];
+  };
+  auto publish_pair = [&](float* slot, int off, const F2 (&B)[3], const F2 (&E)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      sts2(slot + k * PL + off, B[k]);
+      sts2(slot + (3 + k) * PL + off, E[k]);
+    }
+  };
+  auto publish_scalar = [&](float* slot, int off, const F2 (&B)[3], const F2 (&E)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      slot[k * PL + off] = B[k].x;
+      slot[(3 + k) * PL + off] = E[k].x;
+    }
+  };
+  // central difference 0.5*(fp - fm)/dx
+  auto cd = [&](F2 fp, F2 fm) -> F2 {
+#if AMX_STRICT
+    const F2 h = bc2(0.5f) * (fp - fm);
+    return mk2(h.x / dxf, h.y / dxf);
+#else
+    return bc2(hdx) * (fp - fm);
+#endif
+  };
+
+  F2 ch0 = bc2(0.f), ch1 = bc2(0.f);
+
+  if (!compute) {
+    // ================= halo warp: one y-halo pair (3-D) and one lane-axis halo cell per lane.
+    // Q12: a reflective y side (3-D) flips 3-vector component 2; in 2-D the lane axis IS y, so
+    // its halo cells flip component 2; the z axis of a 3-D grid flips nothing.
+    const int l = tid - kComputeThreads;
+    Col colA, colB;
+    bool haveA = false, haveB = false, flipA = false, flipB = false;
+    int smA = 0, smB = 0;
+    if constexpr (ND == 3) {
+      const int j = l < TQ ? 0 : ta + 1;  // window row of the halo pair
+      const int my = map_index(y0 - 1 + j, g.n[1], g.bc[1][0], g.bc[1][1], flipA);
+      make_col(my, z0 + 2 * (l % TQ), colA);
+      haveA = (l % TQ) < tqa;
+      smA = j * RS + 2 + 2 * (l % TQ);
+      const int r = l % 16, side = l / 16;  // up to 2 x 16 z-halo cells
+      bool fz;
+      const int mz = map_index(side == 0 ? z0 - 1 : z0 + 2 * tqa, g.n[2], g.bc[2][0], g.bc[2][1], fz);
+      make_col(y0 + r, mz, colB);
+      haveB = r < ta;
+      smB = (r + YO) * RS + (side == 0 ? 1 : 2 + 2 * tqa);
+    } else {
+      const int mz = map_index(l == 0 ? z0 - 1 : z0 + 2 * tqa, g.n[1], g.bc[1][0], g.bc[1][1], flipB);
+      make_col(0, mz, colB);
+      haveB = l < 2;
+      smB = l == 0 ? 1 : 2 + 2 * tqa;
+    }
+    Raw rawL, rawS;
+    auto issue = [&](int p) {
+      bool fx;
+      const int mx = plane_map(p, fx);
+      if (haveA) load_pair(colA, mx, rawL);
+      if (haveB) load_scalar(colB, mx, rawS);
+    };
+    auto process = [&](int p, int s) {
+      bool fx;
+      (void)plane_map(p, fx);
+      float* slot = smem + s * SLOT;
+      F2 B[3], E[3];
+      if (haveA) {
+        argument(rawL, fx, flipA, B, E);
+        publish_pair(slot, smA, B, E);
+      }
+      if (haveB) {
+        argument(rawS, fx, flipB, B, E);
+        publish_scalar(slot, smB, B, E);
+      }
+    };
+    issue(xs);
+    process(xs, 1);
+    issue(xs + 1);
+    process(xs + 1, 2);
+    if (xs + 2 <= xe) issue(xs + 2);
+    __syncthreads();
+    int sF = 0;  // ring slot of plane x+2
+    for (int x = xs; x < xe; ++x) {
+      if (x + 2 <= xe) {
+        process(x + 2, sF);
+        if (x + 3 <= xe) issue(x + 3);
+      }
+      __syncthreads();
+      sF = sF == 2 ? 0 : sF + 1;
+    }
+  } else {
+    // ================= compute threads: pair (ty, tq)
+    const int tq = tid % TQ, ty = tid / TQ;
+    const bool active = tq < tqa && ty < ta;
+    Col colA;
+    make_col(y0 + ty, z0 + 2 * tq, colA);
+    const int smA = (ty + YO) * RS + 2 + 2 * tq;
+    // components 1 and 2 of (B, E) of the own pair in planes p with p mod 3 == slot: registers
+    // mirror the ring slots (component 0 is only needed of the centre plane: re-read from the ring)
+    F2 RB[3][2], RE[3][2];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) RB[s][k] = RE[s][k] = bc2(0.f);
+    Raw rawL;  // loads in flight
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rawL.B0[k] = rawL.v0[k] = rawL.Bk[k] = rawL.vk[k] = bc2(0.f);
+    rawL.rho = bc2(1.f);
+    float* const fB1 = static_cast<float*>(a.Bk1.p);
+    float* const fv1 = static_cast<float*>(a.vk1.p);
+    const long long vB1 = a.Bk1.vs, vv1 = a.vk1.vs;
+    // thread-private stash of the raw data between process(p) and update(p): [2][13][pairs]
+    float* const stash = smem + 3 * SLOT + 2 * tid;
+    constexpr int SP = 2 * kComputeThreads;  // floats per stashed field
+    constexpr int SS = 13 * SP;              // floats per stash slot
+
+    auto issue = [&](int p) {
+      bool fx;
+      const int mx = plane_map(p, fx);
+      if (active) load_pair(colA, mx, rawL);
+    };
+    // consume the loads in flight as plane p: argument + E into registers (slot S), publish to
+    // ring slot S, park the raw values in stash slot q until update(p)
+    auto process = [&](int p, auto Sc, bool publish, int q) {
+      constexpr int S = decltype(Sc)::value;
+      bool fx;
+      (void)plane_map(p, fx);
+      F2 B[3], E[3];
+      argument(rawL, fx, false, B, E);
+      RB[S][0] = B[1]; RB[S][1] = B[2];
+      RE[S][0] = E[1]; RE[S][1] = E[2];
+      if (publish && active) {  // rows / pairs beyond the grid must not touch the halo entries
+        publish_pair(smem + S * SLOT, smA, B, E);
+        float* st = stash + q * SS;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          sts2(st + k * SP, rawL.B0[k]);
+          if (k < ND) sts2(st + (3 + k) * SP, rawL.v0[k]);
+          if constexpr (have_k) {
+            sts2(st + (7 + k) * SP, rawL.Bk[k]);
+            sts2(st + (10 + k) * SP, rawL.vk[k]);
+          }
+        }
+        sts2(st + 6 * SP, rawL.rho);
+      }
+    };
+    // update of plane x (ring / register slot SC) from: ring slot SC (y / z neighbours), register
+    // slots SN = plane x+1 and SF = plane x-1 (x neighbours), stash slot q (R_0, R_k, rho)
+    auto update = [&](int x, auto SCc, auto SNc, auto SFc, int q) {
+      constexpr int SC = decltype(SCc)::value, SN = decltype(SNc)::value, SF = decltype(SFc)::value;
+      const float* w = smem + SC * SLOT + smA;
+      const float* st = stash + q * SS;
+      const F2 BC[3] = {lds2(w), RB[SC][0], RB[SC][1]};
+      const F2 EC[3] = {lds2(w + 3 * PL), RE[SC][0], RE[SC][1]};
+      // lane-axis neighbours of the pair (a, b): left cell l, right cell r
+      auto ddl = [&](int f, F2 own) -> F2 {
+        const float l = w[f * PL - 1], r = w[f * PL + 2];
+        return cd(mk2(own.y, r), mk2(l, own.x));
+      };
+      auto ddx = [&](const F2(&R)[3][2], int k) -> F2 { return cd(R[SN][k - 1], R[SF][k - 1]); };
+      F2 curlB[3], curlE[3];
+      if constexpr (ND == 3) {  // curl3D: lane axis is z, row axis is y
+        auto ddy = [&](int f) -> F2 { return cd(lds2(w + f * PL + RS), lds2(w + f * PL - RS)); };
+        curlB[0] = ddy(2) - ddl(1, BC[1]);
+        curlB[1] = ddl(0, BC[0]) - ddx(RB, 2);
+        curlB[2] = ddx(RB, 1) - ddy(0);
+        curlE[0] = ddy(5) - ddl(4, EC[1]);
+        curlE[1] = ddl(3, EC[0]) - ddx(RE, 2);
+        curlE[2] = ddx(RE, 1) - ddy(3);
+      } else {  // curl2D: lane axis is y
+        curlB[0] = ddl(2, BC[2]);
+        curlB[1] = -ddx(RB, 2);
+        curlB[2] = ddx(RB, 1) - ddl(0, BC[0]);
+        curlE[0] = ddl(5, EC[2]);
+        curlE[1] = -ddx(RE, 2);
+        curlE[2] = ddx(RE, 1) - ddl(3, EC[0]);
+      }
+      F2 cr[3];
+      cr[0] = BC[1] * curlB[2] - BC[2] * curlB[1];
+      cr[1] = BC[2] * curlB[0] - BC[0] * curlB[2];
+      cr[2] = BC[0] * curlB[1] - BC[1] * curlB[0];
+      const F2 rho = lds2(st + 6 * SP);
+#if !AMX_STRICT
+      const F2 ir = mk2(rdiv(1.f, rho.x), rdiv(1.f, rho.y));
+#endif
+      F2 dB = bc2(0.f), dv = bc2(0.f);
+      const long long o = colA + (long long)x * sx;
+      float* qB = fB1 + o;
+      float* qv = fv1 + o;
+      const F2 dt2 = bc2(dt);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+#if AMX_STRICT
+        const F2 phiB = mk2(cr[k].x / rho.x, cr[k].y / rho.y);
+#else
+        const F2 phiB = cr[k] * ir;
+#endif
+        const F2 b0 = lds2(st + k * SP);
+        const F2 v0 = k < ND ? lds2(st + (3 + k) * SP) : bc2(0.f);
+        const F2 Bn = b0 - dt2 * curlE[k];
+        const F2 vn = v0 - dt2 * phiB;
+        const F2 bk = have_k ? lds2(st + (7 + k) * SP) : b0;
+        const F2 vk = have_k ? lds2(st + (10 + k) * SP) : v0;
+        const F2 eB = abs2(bk - Bn), ev = abs2(vk - vn);
+        dB = dB + eB * eB;
+        dv = dv + ev * ev;
+        stg2(qB + k * vB1, Bn);
+        stg2(qv + k * vv1, vn);
+      }
+      ch0 = max2(ch0, dB);
+      ch1 = max2(ch1, dv);
+    };
+
+    // ---- prologue: planes xs-1 (registers only), xs, xs+1 (published); loads of xs+2 in flight
+    issue(xs - 1);
+    process(xs - 1, IC<0>{}, false, 0);
+    issue(xs);
+    process(xs, IC<1>{}, true, 0);
+    issue(xs + 1);
+    process(xs + 1, IC<2>{}, true, 1);
+    if (xs + 2 <= xe) issue(xs + 2);
+    __syncthreads();
+
+    // one plane: update x, then turn the loads in flight into plane x+2 (which takes over the
+    // registers / ring slot of plane x-1 and the stash slot of plane x) and start the next loads
+    int q = 0;
+    auto step = [&](int x, auto SCc, auto SNc, auto SFc) {
+      if (active) update(x, SCc, SNc, SFc, q);
+      if (x + 2 <= xe) {
+        process(x + 2, SFc, true, q);
+        if (x + 3 <= xe) issue(x + 3);
+      }
+      __syncthreads();
+      q ^= 1;
+    };
+    for (int x = xs;;) {
+      step(x, IC<1>{}, IC<2>{}, IC<0>{});
+      if (++x >= xe) break;
+      step(x, IC<2>{}, IC<0>{}, IC<1>{});
+      if (++x >= xe) break;
+      step(x, IC<0>{}, IC<1>{}, IC<2>{});
+      if (++x >= xe) break;
+    }
+  }
+
+  // ---- change norms: max over cells of the squared 3-norms, sqrt (monotone), block max, slots
+  float chs[2] = {rsqrt_(fmaxf(ch0.x, ch0.y)), rsqrt_(fmaxf(ch1.x, ch1.y))};
+  __shared__ float red[2][kThreads / 32];
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) chs[k] = fmaxf(chs[k], __shfl_xor_sync(0xffffffffu, chs[k], o));
+    if (lane == 0) red[k][wid] = chs[k];
+  }
+  __syncthreads();
+  if (tid < 2) {
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) m = fmaxf(m, red[tid][i]);
+    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    atomicMax(a.change_slots + (size_t)tid * kAlphaSlots + (bid % kAlphaSlots), bits_of(m));
+  }
+}
+
+// number of x chunks minimising (waves of blocks) x (planes per chunk + prologue planes)
+inline int pick_chunks(int nx, long long tiles, int blocks_per_sm, int prologue) {
+  const long long slots = 148LL * blocks_per_sm;
+  int best = 1;
+  long long best_cost = -1;
+  const int maxch = nx / 8 > 0 ? nx / 8 : 1;
+  for (int nch = 1; nch <= maxch; ++nch) {
+    const long long blocks = tiles * nch;
+    const long long waves = (blocks + slots - 1) / slots;
+    const long long cost = waves * ((nx + nch - 1) / nch + prologue);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nch; }
+  }
+  return best;
+}
+
+template <int ND, int MODE, int LD, int CW>
+cudaError_t launch_mag(const MagIterArgs& a, cudaStream_t st) {
+  constexpr int TY = VT<ND, CW>::TY, TZ = 2 * VT<ND, CW>::TQ, kThreads = 32 * CW + 32;
+  const size_t smem = mag_vec_smem_bytes<ND, CW>();
+  auto kern = mag_iter_vec<ND, MODE, LD, CW>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // Leave the carveout to the driver (just enough shared memory for two blocks): the remaining L1
+    // tracks the loads in flight, and starving it costs ~45 % (measured: 0.47 ms with
+    // cudaSharedmemCarveoutMaxShared, 0.32 ms without).
+    static const int carve = [] { const char* e = getenv("AMX_VEC_CARVE"); return e ? atoi(e) : -1; }();
+    if (carve >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    configured = true;
+  }
+  dim3 grid;
+  const int LA = ND - 1;
+  grid.x = (a.g.n[LA] + TZ - 1) / TZ;
+  const int ytiles = ND == 3 ? (a.g.n[1] + TY - 1) / TY : 1;
+  const long long tiles = (long long)grid.x * ytiles;
+  const int nch = pick_chunks(a.g.n[0], tiles, CW == 7 ? 2 : 1, 3);
+  const int xchunk = (a.g.n[0] + nch - 1) / nch;
+  const int nchunks = (a.g.n[0] + xchunk - 1) / xchunk;
+  if (ND == 3) { grid.y = ytiles; grid.z = nchunks; }
+  else { grid.y = nchunks; grid.z = 1; }
+  kern<<<grid, kThreads, smem, st>>>(a, xchunk);
+  return cudaGetLastError();
+}
+
+inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+inline bool view_ok(const View& v, int nd) {
+  const int la = nd - 1;
+  if (v.s[la] != 1 || (v.vs & 1) || !aligned8(v.p)) return false;
+  for (int ax = 0; ax < la; ++ax)
+    if (v.s[ax] & 1) return false;
+  return true;
+}
+
+}  // namespace vec
+
+// fp32, 2-D / 3-D, contiguous 8-byte-aligned rows, even extent along the contiguous axis
+bool vec_mag_supported(const MagIterArgs& a) {
+  if (a.np.dtype != 0) return false;
+  const int nd = a.g.nd;
+  if (nd != 2 && nd != 3) return false;
+  if (!vec::view_ok(a.B0, nd) || !vec::view_ok(a.gas0, nd) || !vec::view_ok(a.Bk1, nd) || !vec::view_ok(a.vk1, nd)) return false;
+  if (a.Bk.p && (!vec::view_ok(a.Bk, nd) || !vec::view_ok(a.vk, nd))) return false;
+  for (int ax = 0; ax < nd - 1; ++ax) {
+    const long long s0 = a.B0.s[ax];
+    if (a.gas0.s[ax] != s0 || a.Bk1.s[ax] != s0 || a.vk1.s[ax] != s0) return false;
+    if (a.Bk.p && (a.Bk.s[ax] != s0 || a.vk.s[ax] != s0)) return false;
+  }
+  if (a.g.n[0] < 4 || (a.g.n[nd - 1] & 1) || a.g.n[nd - 1] < 8) return false;
+  return nd == 2 || a.g.n[1] >= 4;
+}
+
+template <int ND, int LD, int CW>
+static cudaError_t launch_mag_ld(const MagIterArgs& a, cudaStream_t st) {
+  if (!a.Bk.p) return vec::launch_mag<ND, 0, LD, CW>(a, st);
+  return a.midpoint ? vec::launch_mag<ND, 1, LD, CW>(a, st) : vec::launch_mag<ND, 2, LD, CW>(a, st);
+}
+template <int ND>
+static cudaError_t launch_mag_mode(const MagIterArgs& a, cudaStream_t st) {
+  static const int cw = [] { const char* e = getenv("AMX_VEC_CW"); return e ? atoi(e) : 7; }();
+  if (cw == 8) return launch_mag_ld<ND, 0, 8>(a, st);
+  return launch_mag_ld<ND, 0, 7>(a, st);
+}
+
+cudaError_t launch_mag_iter_vec(const MagIterArgs& a, cudaStream_t st) {
+  if (a.g.nd == 3) return launch_mag_mode<3>(a, st);
+  if (a.g.nd == 2) return launch_mag_mode<2>(a, st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace AMX_NS

@@ -280,3 +280,48 @@ def test_slab_driver_lax_friedrichs(cuda):
     drv.scatter(torch.from_numpy(s))
     drv.run(max_steps=3)
     assert pr.rel_l1(drv.gather().cpu().numpy(), ref, 3, True) < 1e-12
+
+
+# ---- z-vectorised kernels (amx_vec.cu): fp32, grids a whole number of 16 x 32 (2-D: 512) tiles ----
+@pytest.mark.parametrize("arith", ["fast", "strict"])
+@pytest.mark.parametrize("dim,n", [(3, 32), (3, 64), (2, 512)])
+def test_vec_kernels_fp32_vs_oracle(cuda, dim, n, arith):
+    s = pr.smooth_random(dim, n, mhd=True, seed=51 + dim, dtype=np.float32)
+    config, params, rv = pr.make(dim, n, mhd=True)
+    check(s, config, params, rv, 5, arith)
+
+
+def _run_subprocess_variants(code, variants):
+    import os
+    import subprocess
+    import sys
+    outs = []
+    for k, env_extra in enumerate(variants):
+        path = f"/tmp/amx_variant_{os.getpid()}_{k}.npy"
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, **env_extra))
+        outs.append(np.load(path))
+        os.remove(path)
+    return outs
+
+
+@pytest.mark.parametrize("dim,n", [(3, 32), (2, 512)])
+@pytest.mark.parametrize("bnd", ["periodic", "open", "reflective"])
+@pytest.mark.parametrize("integrator", ["midpoint", "euler"])
+def test_vec_equals_generic_bitwise_in_strict_mode(cuda, dim, n, bnd, integrator):
+    """Vectorised, tiled and generic kernel families follow the same operation order in STRICT
+    arithmetic: identical bits, including the boundary rules (Q12 flips) of every side."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r);"
+        "from astronomix_b200 import problems as pr, stepping as ti, _lib, option_classes as oc;"
+        "s = pr.smooth_random(%d, %d, mhd=True, seed=7, dtype=np.float32);"
+        "c, p, rv = pr.make(%d, %d, mhd=True, boundaries=%r, fv_magnetic_integrator=%s);"
+        "out = ti.integrate_steps(s, c, p, rv, 3, arithmetic=_lib.AMX_ARITH_STRICT);"
+        "np.save(sys.argv[1], out)"
+    ) % (root, dim, n, dim, n, bnd, "oc.IMPLICIT_MIDPOINT" if integrator == "midpoint" else "oc.IMPLICIT_EULER")
+    vec, tiled, generic = _run_subprocess_variants(
+        code, [{}, {"AMX_NO_VEC": "1"}, {"AMX_FORCE_GENERIC": "1"}])
+    assert np.isfinite(vec).all()
+    assert np.array_equal(vec, generic)
+    assert np.array_equal(tiled, generic)
