@@ -555,7 +555,9 @@ struct Engine {
     {
       ProfScope ps(PC_HYDRO_STAGE, st);
       const bool tiled = !force_generic() && (strict ? amx_strict::tiled_stage_supported(a) : amx_fast::tiled_stage_supported(a));
-      if (tiled) CKE(strict ? amx_strict::launch_hydro_stage_tiled(a, st) : amx_fast::launch_hydro_stage_tiled(a, st));
+      const bool vec = !force_generic() && !no_vec() && (strict ? amx_strict::vec_stage_supported(a) : amx_fast::vec_stage_supported(a));
+      if (vec) CKE(strict ? amx_strict::launch_hydro_stage_vec(a, st) : amx_fast::launch_hydro_stage_vec(a, st));
+      else if (tiled) CKE(strict ? amx_strict::launch_hydro_stage_tiled(a, st) : amx_fast::launch_hydro_stage_tiled(a, st));
       else CKE(strict ? amx_strict::launch_hydro_stage(a, st) : amx_fast::launch_hydro_stage(a, st));
     }
     return want_alpha ? finalize_alpha(alpha_t_out, guarded) : cudaSuccess;

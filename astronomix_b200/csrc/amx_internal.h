@@ -139,7 +139,9 @@ struct CopyArgs {  // strided row copy (pad / unpad / concatenate)
   bool tiled_mag_supported(const amx::MagIterArgs&);                                      \
   cudaError_t launch_mag_iter_tiled(const amx::MagIterArgs&, cudaStream_t);               \
   bool vec_mag_supported(const amx::MagIterArgs&);                                        \
-  cudaError_t launch_mag_iter_vec(const amx::MagIterArgs&, cudaStream_t);
+  cudaError_t launch_mag_iter_vec(const amx::MagIterArgs&, cudaStream_t);                 \
+  bool vec_stage_supported(const amx::StageArgs&);                                        \
+  cudaError_t launch_hydro_stage_vec(const amx::StageArgs&, cudaStream_t);
 
 }  // namespace amx
 

@@ -61,6 +61,56 @@ AMX_DI double rmax(double a, double b) { return fmax(a, b); }
 template <typename T> AMX_DI T sq(T a) { return a * a; }
 template <typename T> AMX_DI T sgn(T a) { return a > T(0) ? T(1) : (a < T(0) ? T(-1) : T(0)); }
 
+// ---------------------------------------------------------------- packed pair of floats
+// Two cells adjacent along the contiguous axis handled by one thread (amx_vec.cu).  In the FAST
+// flavour +, -, * are the packed sm_100a instructions FADD2 / FMUL2 (ptxas contracts them into
+// FFMA2 and folds negations / scalar broadcasts into operand modifiers).  ptxas contracts
+// mul.rn.f32x2 + add.rn.f32x2 even under -fmad=false, so the STRICT flavour uses the never-fused
+// scalar intrinsics (same IEEE results, reference operation order).
+struct F2 {
+  float x, y;
+  F2() = default;
+  AMX_DI explicit F2(float a) : x(a), y(a) {}
+  AMX_DI explicit F2(double a) : x((float)a), y((float)a) {}
+  AMX_DI explicit F2(int a) : x((float)a), y((float)a) {}
+  AMX_DI F2(float a, float b) : x(a), y(b) {}
+};
+AMX_DI F2 mk2(float a, float b) { return F2(a, b); }
+AMX_DI F2 bc2(float a) { return F2(a, a); }
+#if AMX_STRICT
+AMX_DI F2 operator+(F2 a, F2 b) { return mk2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+AMX_DI F2 operator-(F2 a, F2 b) { return mk2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+AMX_DI F2 operator*(F2 a, F2 b) { return mk2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+#else
+#define AMX_F2_BINOP(NAME, PTX)                                                                      \
+  AMX_DI F2 NAME(F2 a, F2 b) {                                                                       \
+    F2 d;                                                                                            \
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; " PTX                   \
+        " rd, ra, rb; mov.b64 {%0, %1}, rd; }"                                                       \
+        : "=f"(d.x), "=f"(d.y)                                                                       \
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                   \
+    return d;                                                                                        \
+  }
+AMX_F2_BINOP(operator+, "add.rn.f32x2")
+AMX_F2_BINOP(operator-, "sub.rn.f32x2")
+AMX_F2_BINOP(operator*, "mul.rn.f32x2")
+#undef AMX_F2_BINOP
+#endif
+AMX_DI F2 operator-(F2 a) { return mk2(-a.x, -a.y); }
+AMX_DI F2 operator/(F2 a, F2 b) { return mk2(a.x / b.x, a.y / b.y); }  // IEEE division per half
+AMX_DI F2 rdiv(F2 a, F2 b) { return mk2(rdiv(a.x, b.x), rdiv(a.y, b.y)); }
+AMX_DI F2 rsqrt_(F2 a) { return mk2(rsqrt_(a.x), rsqrt_(a.y)); }
+AMX_DI F2 rsin(F2 a) { return mk2(rsin(a.x), rsin(a.y)); }
+AMX_DI F2 rabs(F2 a) { return mk2(fabsf(a.x), fabsf(a.y)); }
+AMX_DI F2 rmin(F2 a, F2 b) { return mk2(fminf(a.x, b.x), fminf(a.y, b.y)); }
+AMX_DI F2 rmax(F2 a, F2 b) { return mk2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+
+// s >= 0 ? a : b and s <= 0 ? a : b (upwind selection of the HLLC family), per half for pairs
+template <typename T> AMX_DI T sel_ge0(T s, T a, T b) { return (s >= T(0)) ? a : b; }
+template <typename T> AMX_DI T sel_le0(T s, T a, T b) { return (s <= T(0)) ? a : b; }
+AMX_DI F2 sel_ge0(F2 s, F2 a, F2 b) { return mk2(s.x >= 0.f ? a.x : b.x, s.y >= 0.f ? a.y : b.y); }
+AMX_DI F2 sel_le0(F2 s, F2 a, F2 b) { return mk2(s.x <= 0.f ? a.x : b.x, s.y <= 0.f ? a.y : b.y); }
+
 // Per-launch constants, rounded to the working type the way the reference's scalars are
 // under jit: gamma is a traced scalar of the working dtype, so gamma-1 is
 // evaluated in T; grid_spacing is a Python double folded at trace time and rounded on
@@ -215,6 +265,15 @@ AMX_DI T limited_slope(T a, T b, int lim, const Consts<T>& c) {
   }
 }
 
+// pairs: the non-minmod limiters branch per cell, so they run per half on the scalar code
+AMX_DI F2 limited_slope(F2 a, F2 b, int lim, const Consts<F2>& c) {
+  if (lim == LIM_MINMOD) return minmod(a, b);
+  Consts<float> cf;
+  cf.gamma = c.gamma.x; cf.gm1 = c.gm1.x; cf.inv_gm1 = c.inv_gm1.x; cf.dx = c.dx.x; cf.inv_dx = c.inv_dx.x;
+  cf.half_dx = c.half_dx.x; cf.va_eps = c.va_eps.x;
+  return mk2(limited_slope(a.x, b.x, lim, cf), limited_slope(a.y, b.y, lim, cf));
+}
+
 // limited slope (per unit length) of every gas variable from the three cells m, c, p
 template <typename T, int ND, int LIM>
 AMX_DI Gas<T, ND> slopes(const Gas<T, ND>& m, const Gas<T, ND>& s, const Gas<T, ND>& p, int lim,
@@ -333,8 +392,8 @@ AMX_DI Gas<T, ND> hllc_flux(const Gas<T, ND>& L, const Gas<T, ND>& R, int ax, co
     const T bulk = T(0.5) * (FL.q[k] + FR.q[k]);
     const T diss = T(0.5) * (SLs * (UsL.q[k] - UL.q[k]) + aS * (UsL.q[k] - UsR.q[k]) + SRs * (UsR.q[k] - UR.q[k]));
     T f = bulk + diss;
-    f = (SL >= T(0)) ? FL.q[k] : f;
-    f = (SR <= T(0)) ? FR.q[k] : f;
+    f = sel_ge0(SL, FL.q[k], f);
+    f = sel_le0(SR, FR.q[k], f);
     F.q[k] = f;
   }
   return F;

@@ -32,34 +32,6 @@ using namespace amx;
 
 namespace vec {
 
-// ---------------------------------------------------------------- packed pair of floats
-struct F2 {
-  float x, y;
-};
-AMX_DI F2 mk2(float a, float b) { F2 r; r.x = a; r.y = b; return r; }
-AMX_DI F2 bc2(float a) { return mk2(a, a); }
-#if AMX_STRICT
-// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, so the strict
-// flavour uses the never-fused scalar intrinsics (same IEEE results, reference operation order).
-AMX_DI F2 operator+(F2 a, F2 b) { return mk2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
-AMX_DI F2 operator-(F2 a, F2 b) { return mk2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
-AMX_DI F2 operator*(F2 a, F2 b) { return mk2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
-#else
-#define AMX_F2_BINOP(NAME, PTX)                                                                      \
-  AMX_DI F2 NAME(F2 a, F2 b) {                                                                       \
-    F2 d;                                                                                            \
-    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; " PTX                   \
-        " rd, ra, rb; mov.b64 {%0, %1}, rd; }"                                                       \
-        : "=f"(d.x), "=f"(d.y)                                                                       \
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                   \
-    return d;                                                                                        \
-  }
-AMX_F2_BINOP(operator+, "add.rn.f32x2")
-AMX_F2_BINOP(operator-, "sub.rn.f32x2")
-AMX_F2_BINOP(operator*, "mul.rn.f32x2")
-#undef AMX_F2_BINOP
-#endif
-AMX_DI F2 operator-(F2 a) { return mk2(-a.x, -a.y); }
 AMX_DI F2 max2(F2 a, F2 b) { return mk2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
 AMX_DI F2 abs2(F2 a) { return mk2(fabsf(a.x), fabsf(a.y)); }
 
@@ -550,6 +522,507 @@ cudaError_t launch_mag(const MagIterArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// ================================================================ unsplit hydro stage
+// hydro_stage_vec<ND, RS, LIM, COMBINE>: one forward-Euler stage of the unsplit scheme
+// (evolve_state.py:339-414) [+ RK2 combine :456-469] with the same thread layout as mag_iter_vec.
+//   * planes are staged by cp.async (LDGSTS) straight into a 3-slot shared-memory window ring
+//     (tile + 2-cell halo; halo rows / columns by the halo warp, boundary rules by index mapping),
+//     so no registers are tied up by loads in flight;
+//   * x direction: s(x), s(x+1), the x half-slope and the flux at x-1/2 are carried in registers;
+//   * y direction: a thread reads rows y-2, y-1, y+1 of its pair from the window, computes the
+//     half-slopes of rows y-1 and y and the flux at y-1/2, publishes it, and after the plane's
+//     one barrier reads the flux at y+1/2 published by the row above;
+//   * z direction (inside the pair and across it): the half-slopes of cells z-1, z, z+1 and the
+//     fluxes at z-1/2 and z+1/2 are evaluated as packed pairs; the flux at z+3/2 is the first
+//     half of the right neighbour's pair, read back after the barrier;
+//   * the fluxes on the upper tile edges (top row, right column) are extra work of the halo warp.
+// Every flux is computed exactly once; slopes of rows y-1 / cells z-1 are recomputed (cheap).
+template <int LIM>
+AMX_DI F2 half_slope(F2 dm, F2 dp, int lim, const Consts<F2>& c) {
+#if AMX_STRICT
+  const F2 a = dm / c.dx, b = dp / c.dx;
+  const F2 g = (LIM == LIM_MINMOD) ? minmod(a, b) : limited_slope(a, b, lim, c);
+  return (g * c.dx) / F2(2);
+#else
+  if constexpr (LIM == LIM_MINMOD) {
+    return F2(0.5f) * minmod(dm, dp);
+  } else {
+    const F2 g = limited_slope(dm * c.inv_dx, dp * c.inv_dx, lim, c);
+    return (g * c.dx) * F2(0.5f);
+  }
+#endif
+}
+
+AMX_DI Consts<F2> make_consts2(const NumPar& np) {
+  Consts<F2> c;
+  const float gamma = (float)np.gamma;
+  const float gm1 = gamma - 1.0f;
+  c.gamma = F2(gamma);
+  c.gm1 = F2(gm1);
+  c.inv_gm1 = F2(1.0f / gm1);
+  c.dx = F2((float)np.dx);
+  c.inv_dx = F2((float)(1.0 / np.dx));
+  c.half_dx = F2((float)(np.dx / 2));
+  c.va_eps = F2((float)(3 * np.dx));
+  return c;
+}
+
+AMX_DI void cp_async8(float* smem_dst, const float* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+AMX_DI void cp_async4(float* smem_dst, const float* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+AMX_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+AMX_DI void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kHydroCW = 7;  // compute warps (+ 1 halo warp = 256 threads, 2 blocks per SM)
+
+template <int ND>
+struct HG {
+  static constexpr int NV = ND + 2;
+  static constexpr int TY = ND == 3 ? 2 * kHydroCW : 1, TQ = ND == 3 ? 16 : 32 * kHydroCW, TZ = 2 * TQ;
+  static constexpr int WY = ND == 3 ? TY + 4 : 1, YO = ND == 3 ? 2 : 0;
+  static constexpr int RSW = TZ + 8;       // window row: cells z0-2, z0-1 at columns 2, 3; own pairs from column 4
+  static constexpr int PLW = WY * RSW;     // floats per variable per window slot
+  static constexpr int WSLOT = NV * PLW;
+  static constexpr int PLFY = ND == 3 ? (TY + 1) * TZ : 0;  // y fluxes: lower interfaces of rows 0 .. TY
+  static constexpr int PLFZ = TY * (TQ + 1);                // first halves of the lane-axis flux pairs + edge
+  static constexpr int FSLOT = NV * (PLFY + PLFZ);
+  static constexpr size_t smem_bytes = (size_t)(3 * WSLOT + 2 * FSLOT) * sizeof(float);
+};
+
+template <int ND, int RS, int LIM, bool COMBINE>
+__global__ void __launch_bounds__(32 * kHydroCW + 32, 2) hydro_stage_vec(const StageArgs a, const int xchunk) {
+  if (a.ctl_ro && a.ctl_ro->done) return;
+  using G = HG<ND>;
+  constexpr int NV = G::NV, TY = G::TY, TQ = G::TQ, TZ = G::TZ, YO = G::YO, RSW = G::RSW, PLW = G::PLW;
+  constexpr int WSLOT = G::WSLOT, PLFY = G::PLFY, PLFZ = G::PLFZ, FSLOT = G::FSLOT;
+  constexpr int LA = ND - 1;  // lane (contiguous) axis
+  constexpr int kCompute = 32 * kHydroCW;
+  extern __shared__ __align__(16) float smem[];
+  float* const win = smem;                 // [3][NV][WY][RSW]
+  float* const flx = smem + 3 * WSLOT;     // [2][NV][PLFY + PLFZ]
+
+  const Consts<F2> c = make_consts2(a.np);
+  const Geom& g = a.g;
+  const int lim = a.np.lim;
+  const int tid = threadIdx.x;
+  const bool compute = tid < kCompute;
+  const int z0 = blockIdx.x * TZ;
+  const int y0 = ND == 3 ? blockIdx.y * TY : 0;
+  const int chunk = ND == 3 ? blockIdx.z : blockIdx.y;
+  const int xs = chunk * xchunk;
+  const int xe = min(xs + xchunk, g.n[0]);
+  if (xs >= xe) return;
+  const float dts = *static_cast<const float*>(a.dt) * (float)a.dt_scale;
+  const int ta = ND == 3 ? min(TY, g.n[1] - y0) : 1;   // active rows / pairs of a ragged tile
+  const int tqa = min(TQ, (g.n[LA] - z0) >> 1);
+  const long long sx = a.in.s[0], sy = ND == 3 ? a.in.s[1] : 0;  // common strides (vec_stage_supported)
+  const float* const fin = static_cast<const float*>(a.in.p);
+  const long long vin = a.in.vs;
+  F2 alpha_lf[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) alpha_lf[k] = RS == RS_LF ? F2(static_cast<const float*>(a.alpha_lf)[k]) : F2(0.f);
+
+  auto plane_map = [&](int p, bool& fx) { return map_index(p, g.n[0], g.bc[0][0], g.bc[0][1], fx); };
+  // conservative update of one variable: U + ((1/dx) * (Fl - Fr)) * dt (evolve_state.py:398-403)
+#if AMX_STRICT
+  const F2 dt2 = F2(dts);
+  auto upd = [&](F2 U, F2 fl, F2 fr) -> F2 { return U + (c.inv_dx * (fl - fr)) * dt2; };
+#else
+  const F2 dtdx = c.inv_dx * F2(dts);
+  auto upd = [&](F2 U, F2 fl, F2 fr) -> F2 { return U + dtdx * (fl - fr); };
+#endif
+  // flux at the interface between cells m1 | s0 from the four cells m2, m1, s0, p1 along `ax`
+  auto edge_flux = [&](const F2 (&m2)[NV], const F2 (&m1)[NV], const F2 (&s0)[NV], const F2 (&p1)[NV], int ax,
+                       F2 alpha) -> Gas<F2, ND> {
+    Gas<F2, ND> L, R;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const F2 d0 = s0[k] - m1[k];
+      L.q[k] = m1[k] + half_slope<LIM>(m1[k] - m2[k], d0, lim, c);
+      R.q[k] = s0[k] - half_slope<LIM>(d0, p1[k] - s0[k], lim, c);
+    }
+    return riemann<F2, ND, RS>(L, R, ax, alpha, c);
+  };
+
+  float wbx = 0.f, wby = 0.f, wbz = 0.f;  // running max of |u_axis| + c (axes x, y, z; 2-D: x, y in wbx, wby)
+
+  if (!compute) {
+    // ================= halo warp
+    const int l = tid - kCompute;
+    // items: A0 / A1 = y-halo pairs (3-D), B = lane-axis halo pair of one row (two mapped cells)
+    long long colA0 = 0, colA1 = 0, colB0 = 0, colB1 = 0;
+    bool haveA = false, haveB = false, fA0 = false, fA1 = false, fB0 = false, fB1 = false;
+    int smA0 = 0, smA1 = 0, smB = 0;
+    if constexpr (ND == 3) {
+      const int q = l % TQ, jr = l / TQ;  // jr = 0, 1
+      haveA = q < tqa;
+      const int my0 = map_index(y0 - 2 + jr, g.n[1], g.bc[1][0], g.bc[1][1], fA0);
+      const int my1 = map_index(y0 + ta + jr, g.n[1], g.bc[1][0], g.bc[1][1], fA1);
+      colA0 = z0 + 2 * q + (long long)my0 * sy;
+      colA1 = z0 + 2 * q + (long long)my1 * sy;
+      smA0 = jr * RSW + 4 + 2 * q;
+      smA1 = (ta + 2 + jr) * RSW + 4 + 2 * q;
+      const int r = l % 16, side = l / 16;
+      haveB = r < ta;
+      const int zc = side == 0 ? z0 - 2 : z0 + 2 * tqa;
+      const int mz0 = map_index(zc, g.n[2], g.bc[2][0], g.bc[2][1], fB0);
+      const int mz1 = map_index(zc + 1, g.n[2], g.bc[2][0], g.bc[2][1], fB1);
+      colB0 = mz0 + (long long)(y0 + r) * sy;
+      colB1 = mz1 + (long long)(y0 + r) * sy;
+      smB = (r + YO) * RSW + (side == 0 ? 2 : 4 + 2 * tqa);
+    } else {
+      haveB = l < 2;
+      const int zc = l == 0 ? z0 - 2 : z0 + 2 * tqa;
+      const int mz0 = map_index(zc, g.n[1], g.bc[1][0], g.bc[1][1], fB0);
+      const int mz1 = map_index(zc + 1, g.n[1], g.bc[1][0], g.bc[1][1], fB1);
+      colB0 = mz0;
+      colB1 = mz1;
+      smB = l == 0 ? 2 : 4 + 2 * tqa;
+    }
+    auto issue = [&](int p, int slot) {
+      bool fx;
+      const long long o = (long long)plane_map(p, fx) * sx;
+      float* w = win + slot * WSLOT;
+      if (haveA) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          cp_async8(w + k * PLW + smA0, fin + k * vin + o + colA0);
+          cp_async8(w + k * PLW + smA1, fin + k * vin + o + colA1);
+        }
+      }
+      if (haveB) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          cp_async4(w + k * PLW + smB, fin + k * vin + o + colB0);
+          cp_async4(w + k * PLW + smB + 1, fin + k * vin + o + colB1);
+        }
+      }
+      cp_async_commit();
+    };
+    // sign flips of reflective sides on the landed halo entries (own entries only)
+    auto fixup = [&](int p, int slot) {
+      bool fx;
+      (void)plane_map(p, fx);
+      float* w = win + slot * WSLOT;
+      if (haveA) {
+        if (fx) { w[PLW + smA0] = -w[PLW + smA0]; w[PLW + smA0 + 1] = -w[PLW + smA0 + 1];
+                  w[PLW + smA1] = -w[PLW + smA1]; w[PLW + smA1 + 1] = -w[PLW + smA1 + 1]; }
+        if (fA0) { w[2 * PLW + smA0] = -w[2 * PLW + smA0]; w[2 * PLW + smA0 + 1] = -w[2 * PLW + smA0 + 1]; }
+        if (fA1) { w[2 * PLW + smA1] = -w[2 * PLW + smA1]; w[2 * PLW + smA1 + 1] = -w[2 * PLW + smA1 + 1]; }
+      }
+      if (haveB) {
+        if (fx) { w[PLW + smB] = -w[PLW + smB]; w[PLW + smB + 1] = -w[PLW + smB + 1]; }
+        if (fB0) w[(LA + 1) * PLW + smB] = -w[(LA + 1) * PLW + smB];
+        if (fB1) w[(LA + 1) * PLW + smB + 1] = -w[(LA + 1) * PLW + smB + 1];
+      }
+    };
+    // fluxes on the upper tile edges of plane x (window slot s complete and visible)
+    auto edge_fluxes = [&](int s, int fs) {
+      const float* w = win + s * WSLOT;
+      float* f = flx + fs * FSLOT;
+      if constexpr (ND == 3) {
+        if (l < TQ) {
+          if (l < tqa) {  // interface below row ta (pair l)
+            const float* wp = w + (ta + 2) * RSW + 4 + 2 * l;
+            F2 m2[NV], m1[NV], s0[NV], p1[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              m2[k] = lds2(wp + k * PLW - 2 * RSW);
+              m1[k] = lds2(wp + k * PLW - RSW);
+              s0[k] = lds2(wp + k * PLW);
+              p1[k] = lds2(wp + k * PLW + RSW);
+            }
+            const Gas<F2, ND> F = edge_flux(m2, m1, s0, p1, 2, alpha_lf[1]);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) sts2(f + k * (PLFY + PLFZ) + ta * TZ + 2 * l, F.q[k]);
+          }
+          return;
+        }
+      }
+      const int r = ND == 3 ? l - TQ : l;
+      if (r < ta && (ND == 3 || l == 0)) {  // interface left of the first right-halo cell of row r
+        const float* wp = w + (r + YO) * RSW + 4 + 2 * tqa;
+        F2 m2[NV], m1[NV], s0[NV], p1[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          m2[k] = F2(wp[k * PLW - 2]);
+          m1[k] = F2(wp[k * PLW - 1]);
+          s0[k] = F2(wp[k * PLW]);
+          p1[k] = F2(wp[k * PLW + 1]);
+        }
+        const Gas<F2, ND> F = edge_flux(m2, m1, s0, p1, LA + 1, alpha_lf[LA]);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) f[k * (PLFY + PLFZ) + PLFY + r * (TQ + 1) + tqa] = F.q[k].x;
+      }
+    };
+    issue(xs, 1);
+    issue(xs + 1, 2);
+    issue(xs + 2, 0);
+    cp_async_wait<1>();
+    fixup(xs, 1);
+    fixup(xs + 1, 2);
+    __syncthreads();
+    int sC = 1, sN = 2, sF = 0, fs = 0;
+    for (int x = xs; x < xe; ++x) {
+      edge_fluxes(sC, fs);
+      cp_async_wait<0>();
+      fixup(x + 2, sF);
+      __syncthreads();
+      issue(x + 3, sC);
+      const int t = sC; sC = sN; sN = sF; sF = t;
+      fs ^= 1;
+    }
+    cp_async_wait<0>();
+  } else {
+    // ================= compute threads: pair (ty, tq)
+    const int tq = tid % TQ, ty = tid / TQ;
+    const bool active = tq < tqa && ty < ta;
+    const long long col = z0 + 2 * tq + (ND == 3 ? (long long)(y0 + ty) * sy : 0);
+    const int smW = (ty + YO) * RSW + 4 + 2 * tq;  // own pair inside a window plane
+    float* const fout = static_cast<float*>(a.out.p);
+    const float* const fin0 = static_cast<const float*>(a.in0.p);
+    const long long vout = a.out.vs, vin0 = a.in0.vs;
+
+    auto issue = [&](int p, int slot) {
+      if (active) {
+        bool fx;
+        const float* src = fin + (long long)plane_map(p, fx) * sx + col;
+        float* w = win + slot * WSLOT + smW;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) cp_async8(w + k * PLW, src + k * vin);
+      }
+      cp_async_commit();
+    };
+    auto fixup = [&](int p, int slot) {  // reflective x side: v_x of the mirrored plane changes sign
+      bool fx;
+      (void)plane_map(p, fx);
+      if (fx && active) {
+        float* w = win + slot * WSLOT + smW + PLW;
+        w[0] = -w[0];
+        w[1] = -w[1];
+      }
+    };
+    auto load_direct = [&](int p, F2 (&v)[NV]) {
+      bool fx;
+      const float* src = fin + (long long)plane_map(p, fx) * sx + col;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) v[k] = active ? ldg2<0>(src + k * vin) : F2(1.f);
+      if (fx) v[1] = -v[1];
+    };
+    auto read_own = [&](int slot, F2 (&v)[NV]) {
+      const float* w = win + slot * WSLOT + smW;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) v[k] = active ? lds2(w + k * PLW) : F2(1.f);
+    };
+
+    // ---- prologue: planes xs-2, xs-1 in registers; xs, xs+1 in the ring; xs+2 in flight
+    F2 sC[NV], sP[NV], dC[NV], FxL[NV];
+    issue(xs, 1);
+    issue(xs + 1, 2);
+    issue(xs + 2, 0);
+    {
+      F2 sM2[NV], sM1[NV];
+      load_direct(xs - 2, sM2);
+      load_direct(xs - 1, sM1);
+      cp_async_wait<1>();
+      fixup(xs, 1);
+      fixup(xs + 1, 2);
+      read_own(1, sC);
+      read_own(2, sP);
+      Gas<F2, ND> L, R;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const F2 d0 = sC[k] - sM1[k];
+        const F2 dM1 = half_slope<LIM>(sM1[k] - sM2[k], d0, lim, c);
+        dC[k] = half_slope<LIM>(d0, sP[k] - sC[k], lim, c);
+        L.q[k] = sM1[k] + dM1;
+        R.q[k] = sC[k] - dC[k];
+      }
+      const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, 1, alpha_lf[0], c);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) FxL[k] = F.q[k];
+    }
+    __syncthreads();
+
+    int sCs = 1, sNs = 2, sFs = 0, fs = 0;
+    for (int x = xs; x < xe; ++x) {
+      const float* w = win + sCs * WSLOT + smW;
+      float* f = flx + fs * FSLOT;
+      // ---- phase 1a: flux at the lower y interface (rows y-2, y-1, y, y+1 of the window)
+      if constexpr (ND == 3) {
+        Gas<F2, ND> L, R;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const F2 m2 = lds2(w + k * PLW - 2 * RSW), m1 = lds2(w + k * PLW - RSW), p1 = lds2(w + k * PLW + RSW);
+          const F2 d0 = sC[k] - m1;
+          L.q[k] = m1 + half_slope<LIM>(m1 - m2, d0, lim, c);
+          R.q[k] = sC[k] - half_slope<LIM>(d0, p1 - sC[k], lim, c);
+        }
+        const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, 2, alpha_lf[1], c);
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) sts2(f + k * (PLFY + PLFZ) + ty * TZ + 2 * tq, F.q[k]);
+        }
+      }
+      // ---- phase 1b: fluxes at the two lower lane-axis interfaces of the pair (a, b):
+      // cells l2 l1 | a b | r1;  L = (l1, a) + (d_l1, d_a),  R = (a, b) - (d_a, d_b)
+      F2 Fz[NV];
+      {
+        Gas<F2, ND> L, R;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const F2 lp = lds2(w + k * PLW - 2);
+          const float r1 = w[k * PLW + 2];
+          const F2 la = mk2(lp.y, sC[k].x);
+          const F2 D1 = la - lp, D2 = sC[k] - la, D3 = mk2(sC[k].y, r1) - sC[k];
+          L.q[k] = la + half_slope<LIM>(D1, D2, lim, c);
+          R.q[k] = sC[k] - half_slope<LIM>(D2, D3, lim, c);
+        }
+        const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, LA + 1, alpha_lf[LA], c);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) Fz[k] = F.q[k];
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) f[k * (PLFY + PLFZ) + PLFY + ty * (TQ + 1) + tq] = F.q[k].x;
+        }
+      }
+      // ---- phase 1c: x direction from registers; plane x+2 has landed in ring slot sFs
+      F2 dP[NV], FxR[NV], sN[NV];
+      cp_async_wait<0>();
+      fixup(x + 2, sFs);
+      read_own(sFs, sN);
+      {
+        Gas<F2, ND> L, R;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          dP[k] = half_slope<LIM>(sP[k] - sC[k], sN[k] - sP[k], lim, c);
+          L.q[k] = sC[k] + dC[k];
+          R.q[k] = sP[k] - dP[k];
+        }
+        const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, 1, alpha_lf[0], c);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) FxR[k] = F.q[k];
+      }
+      // RK2 combine input (centre pair of s0), consumed after the barrier
+      F2 s0v[NV];
+      if constexpr (COMBINE) {
+        const float* p0 = fin0 + (long long)x * sx + col;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s0v[k] = active ? ldg2<0>(p0 + k * vin0) : F2(1.f);
+      }
+      __syncthreads();  // fluxes of plane x published; window of plane x+2 complete
+      issue(x + 3, sCs);  // ring slot of plane x is free (its last readers were phase 1)
+
+      // ---- phase 2: conservative update axis by axis like the reference, prim (+ RK2 combine)
+      {
+        Gas<F2, ND> sc;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sc.q[k] = sC[k];
+        Gas<F2, ND> U = cons_from_prim(sc, c);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) U.q[k] = upd(U.q[k], FxL[k], FxR[k]);
+        if constexpr (ND == 3) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const float* fy = f + k * (PLFY + PLFZ) + ty * TZ + 2 * tq;
+            U.q[k] = upd(U.q[k], lds2(fy), lds2(fy + TZ));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const float fr = f[k * (PLFY + PLFZ) + PLFY + ty * (TQ + 1) + tq + 1];
+          U.q[k] = upd(U.q[k], Fz[k], mk2(Fz[k].y, fr));
+        }
+        Gas<F2, ND> s = prim_from_cons(U, c);
+        if (active) {
+          if constexpr (COMBINE) {
+            Gas<F2, ND> s0;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) s0.q[k] = s0v[k];
+            const Gas<F2, ND> U0 = cons_from_prim(s0, c), U2 = cons_from_prim(s, c);
+            Gas<F2, ND> Um;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) Um.q[k] = F2(0.5f) * (U0.q[k] + U2.q[k]);
+            s = prim_from_cons(Um, c);
+          }
+          float* po = fout + (long long)x * sx + col;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) stg2(po + k * vout, s.q[k]);
+          if (a.alpha_slots) {
+            const F2 bx = wave_bound(s, 1, c), by = wave_bound(s, 2, c);
+            wbx = fmaxf(wbx, fmaxf(bx.x, bx.y));
+            wby = fmaxf(wby, fmaxf(by.x, by.y));
+            if constexpr (ND == 3) {
+              const F2 bz = wave_bound(s, 3, c);
+              wbz = fmaxf(wbz, fmaxf(bz.x, bz.y));
+            }
+          }
+        }
+      }
+      // ---- rotate: registers shift by one plane
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        sC[k] = sP[k];
+        sP[k] = sN[k];
+        dC[k] = dP[k];
+        FxL[k] = FxR[k];
+      }
+      const int t = sCs; sCs = sNs; sNs = sFs; sFs = t;
+      fs ^= 1;
+    }
+    cp_async_wait<0>();
+  }
+
+  if (a.alpha_slots) {
+    float wb[3] = {wbx, wby, wbz};
+    __shared__ float red[3][8];
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wb[k] = fmaxf(wb[k], __shfl_xor_sync(0xffffffffu, wb[k], o));
+      if (lane == 0) red[k][wid] = wb[k];
+    }
+    __syncthreads();
+    if (tid < ND) {
+      float m = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m = fmaxf(m, red[tid][i]);
+      const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+      atomicMax(a.alpha_slots + (size_t)tid * kAlphaSlots + (bid % kAlphaSlots), bits_of(m));
+    }
+  }
+}
+
+template <int ND, int RS, int LIM, bool COMBINE>
+cudaError_t launch_stage_vec(const StageArgs& a, cudaStream_t st) {
+  using G = HG<ND>;
+  auto kern = hydro_stage_vec<ND, RS, LIM, COMBINE>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid;
+  const int LA = ND - 1;
+  grid.x = (a.g.n[LA] + G::TZ - 1) / G::TZ;
+  const int ytiles = ND == 3 ? (a.g.n[1] + G::TY - 1) / G::TY : 1;
+  const int nch = pick_chunks(a.g.n[0], (long long)grid.x * ytiles, 2, 4);
+  const int xchunk = (a.g.n[0] + nch - 1) / nch;
+  const int nchunks = (a.g.n[0] + xchunk - 1) / xchunk;
+  if (ND == 3) { grid.y = ytiles; grid.z = nchunks; }
+  else { grid.y = nchunks; grid.z = 1; }
+  kern<<<grid, 32 * kHydroCW + 32, G::smem_bytes, st>>>(a, xchunk);
+  return cudaGetLastError();
+}
+
 inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 inline bool view_ok(const View& v, int nd) {
   const int la = nd - 1;
@@ -592,6 +1065,38 @@ static cudaError_t launch_mag_mode(const MagIterArgs& a, cudaStream_t st) {
 cudaError_t launch_mag_iter_vec(const MagIterArgs& a, cudaStream_t st) {
   if (a.g.nd == 3) return launch_mag_mode<3>(a, st);
   if (a.g.nd == 2) return launch_mag_mode<2>(a, st);
+  return cudaErrorInvalidValue;
+}
+
+// fp32, 2-D / 3-D, in / out / in0 with the same 8-byte-aligned contiguous layout, even lane extent
+bool vec_stage_supported(const StageArgs& a) {
+  if (a.np.dtype != 0) return false;
+  const int nd = a.g.nd;
+  if (nd != 2 && nd != 3) return false;
+  if (!vec::view_ok(a.in, nd) || !vec::view_ok(a.out, nd)) return false;
+  if (a.in0.p && !vec::view_ok(a.in0, nd)) return false;
+  for (int ax = 0; ax < nd - 1; ++ax) {
+    if (a.out.s[ax] != a.in.s[ax]) return false;
+    if (a.in0.p && a.in0.s[ax] != a.in.s[ax]) return false;
+  }
+  if (a.g.n[0] < 4 || (a.g.n[nd - 1] & 1) || a.g.n[nd - 1] < 8) return false;
+  if (nd == 3 && a.g.n[1] < 4) return false;
+  if (a.np.rs != RS_HLL && a.np.rs != RS_HLLC) return false;
+  return true;
+}
+
+template <int ND, int RS, int LIM>
+static cudaError_t launch_stage_vec_c(const StageArgs& a, cudaStream_t st) {
+  return a.in0.p ? vec::launch_stage_vec<ND, RS, LIM, true>(a, st) : vec::launch_stage_vec<ND, RS, LIM, false>(a, st);
+}
+template <int ND, int RS>
+static cudaError_t launch_stage_vec_l(const StageArgs& a, cudaStream_t st) {
+  return a.np.lim == LIM_MINMOD ? launch_stage_vec_c<ND, RS, LIM_MINMOD>(a, st) : launch_stage_vec_c<ND, RS, -1>(a, st);
+}
+
+cudaError_t launch_hydro_stage_vec(const StageArgs& a, cudaStream_t st) {
+  if (a.g.nd == 3) return a.np.rs == RS_HLL ? launch_stage_vec_l<3, RS_HLL>(a, st) : launch_stage_vec_l<3, RS_HLLC>(a, st);
+  if (a.g.nd == 2) return a.np.rs == RS_HLL ? launch_stage_vec_l<2, RS_HLL>(a, st) : launch_stage_vec_l<2, RS_HLLC>(a, st);
   return cudaErrorInvalidValue;
 }
 
