@@ -821,13 +821,16 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, 2) hydro_stage_vec(const S
       for (int k = 0; k < NV; ++k) v[k] = active ? lds2(w + k * PLW) : F2(1.f);
     };
 
-    // ---- prologue: planes xs-2, xs-1 in registers; xs, xs+1 in the ring; xs+2 in flight
-    F2 sC[NV], sP[NV], dC[NV], FxL[NV];
+    // ---- prologue: planes xs-2, xs-1 in registers; xs, xs+1 in the ring; xs+2 in flight.
+    // Across steps a thread carries only the x half-slope of the centre plane and the flux at
+    // x-1/2 (ping-pong register sets, the loop is unrolled by two); the centre / next planes of
+    // its own pair are re-read from the window ring.
+    F2 d0[NV], F0[NV], d1[NV], F1[NV];
     issue(xs, 1);
     issue(xs + 1, 2);
     issue(xs + 2, 0);
     {
-      F2 sM2[NV], sM1[NV];
+      F2 sM2[NV], sM1[NV], sC[NV], sP[NV];
       load_direct(xs - 2, sM2);
       load_direct(xs - 1, sM1);
       cp_async_wait<1>();
@@ -838,31 +841,34 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, 2) hydro_stage_vec(const S
       Gas<F2, ND> L, R;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        const F2 d0 = sC[k] - sM1[k];
-        const F2 dM1 = half_slope<LIM>(sM1[k] - sM2[k], d0, lim, c);
-        dC[k] = half_slope<LIM>(d0, sP[k] - sC[k], lim, c);
+        const F2 dd = sC[k] - sM1[k];
+        const F2 dM1 = half_slope<LIM>(sM1[k] - sM2[k], dd, lim, c);
+        d0[k] = half_slope<LIM>(dd, sP[k] - sC[k], lim, c);
         L.q[k] = sM1[k] + dM1;
-        R.q[k] = sC[k] - dC[k];
+        R.q[k] = sC[k] - d0[k];
       }
       const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, 1, alpha_lf[0], c);
 #pragma unroll
-      for (int k = 0; k < NV; ++k) FxL[k] = F.q[k];
+      for (int k = 0; k < NV; ++k) F0[k] = F.q[k];
     }
     __syncthreads();
 
     int sCs = 1, sNs = 2, sFs = 0, fs = 0;
-    for (int x = xs; x < xe; ++x) {
+    // one plane: (dC, FxL) in, (dP, FxR) out
+    auto step = [&](int x, const F2 (&dC)[NV], const F2 (&FxL)[NV], F2 (&dP)[NV], F2 (&FxR)[NV]) {
       const float* w = win + sCs * WSLOT + smW;
       float* f = flx + fs * FSLOT;
+      F2 sC[NV];
+      read_own(sCs, sC);
       // ---- phase 1a: flux at the lower y interface (rows y-2, y-1, y, y+1 of the window)
       if constexpr (ND == 3) {
         Gas<F2, ND> L, R;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           const F2 m2 = lds2(w + k * PLW - 2 * RSW), m1 = lds2(w + k * PLW - RSW), p1 = lds2(w + k * PLW + RSW);
-          const F2 d0 = sC[k] - m1;
-          L.q[k] = m1 + half_slope<LIM>(m1 - m2, d0, lim, c);
-          R.q[k] = sC[k] - half_slope<LIM>(d0, p1 - sC[k], lim, c);
+          const F2 dd = sC[k] - m1;
+          L.q[k] = m1 + half_slope<LIM>(m1 - m2, dd, lim, c);
+          R.q[k] = sC[k] - half_slope<LIM>(dd, p1 - sC[k], lim, c);
         }
         const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, 2, alpha_lf[1], c);
         if (active) {
@@ -892,12 +898,13 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, 2) hydro_stage_vec(const S
           for (int k = 0; k < NV; ++k) f[k * (PLFY + PLFZ) + PLFY + ty * (TQ + 1) + tq] = F.q[k].x;
         }
       }
-      // ---- phase 1c: x direction from registers; plane x+2 has landed in ring slot sFs
-      F2 dP[NV], FxR[NV], sN[NV];
+      // ---- phase 1c: x direction; plane x+2 has landed in ring slot sFs
       cp_async_wait<0>();
       fixup(x + 2, sFs);
-      read_own(sFs, sN);
       {
+        F2 sP[NV], sN[NV];
+        read_own(sNs, sP);
+        read_own(sFs, sN);
         Gas<F2, ND> L, R;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
@@ -965,16 +972,14 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, 2) hydro_stage_vec(const S
           }
         }
       }
-      // ---- rotate: registers shift by one plane
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        sC[k] = sP[k];
-        sP[k] = sN[k];
-        dC[k] = dP[k];
-        FxL[k] = FxR[k];
-      }
       const int t = sCs; sCs = sNs; sNs = sFs; sFs = t;
       fs ^= 1;
+    };
+    for (int x = xs;;) {
+      step(x, d0, F0, d1, F1);
+      if (++x >= xe) break;
+      step(x, d1, F1, d0, F0);
+      if (++x >= xe) break;
     }
     cp_async_wait<0>();
   }
