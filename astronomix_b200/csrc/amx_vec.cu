@@ -93,7 +93,7 @@ template <int CW> struct VT<2, CW> { static constexpr int TY = 1, TQ = 32 * CW; 
 template <int ND, int CW>
 constexpr size_t mag_vec_smem_bytes() {
   constexpr int TZ = 2 * VT<ND, CW>::TQ, WY = ND == 3 ? VT<ND, CW>::TY + 2 : 1, RS = TZ + 4;
-  return ((size_t)3 * 6 * WY * RS + (size_t)2 * 13 * 2 * 32 * CW) * sizeof(float);
+  return ((size_t)2 * 6 * WY * RS + (size_t)2 * 13 * 2 * 32 * CW) * sizeof(float);
 }
 
 // raw fixed-point data of one pair / one halo cell in one plane
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(co
   constexpr int PL = WY * RS;   // floats per field per ring slot
   constexpr int SLOT = 6 * PL;  // fields: B0 B1 B2 E0 E1 E2
   constexpr bool have_k = MODE != 0;
-  extern __shared__ __align__(16) float smem[];  // [3][6][WY][RS]; own pairs at column 2 + 2*tq
+  extern __shared__ __align__(16) float smem[];  // ring [2][6][WY][RS] (own pairs at column 2 + 2*tq), stash
 
   const Geom& g = a.g;
   const int tid = threadIdx.x;
@@ -287,20 +287,15 @@ __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(co
         publish_scalar(slot, smB, B, E);
       }
     };
+    // plane p lives in ring slot (p - xs) & 1; step x turns the loads in flight into plane x+1
     issue(xs);
-    process(xs, 1);
+    process(xs, 0);
     issue(xs + 1);
-    process(xs + 1, 2);
-    if (xs + 2 <= xe) issue(xs + 2);
     __syncthreads();
-    int sF = 0;  // ring slot of plane x+2
     for (int x = xs; x < xe; ++x) {
-      if (x + 2 <= xe) {
-        process(x + 2, sF);
-        if (x + 3 <= xe) issue(x + 3);
-      }
+      process(x + 1, (x + 1 - xs) & 1);
+      if (x + 2 <= xe) issue(x + 2);
       __syncthreads();
-      sF = sF == 2 ? 0 : sF + 1;
     }
   } else {
     // ================= compute threads: pair (ty, tq)
@@ -324,7 +319,7 @@ __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(co
     float* const fv1 = static_cast<float*>(a.vk1.p);
     const long long vB1 = a.Bk1.vs, vv1 = a.vk1.vs;
     // thread-private stash of the raw data between process(p) and update(p): [2][13][pairs]
-    float* const stash = smem + 3 * SLOT + 2 * tid;
+    float* const stash = smem + 2 * SLOT + 2 * tid;
     constexpr int SP = 2 * kComputeThreads;  // floats per stashed field
     constexpr int SS = 13 * SP;              // floats per stash slot
 
@@ -333,10 +328,11 @@ __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(co
       const int mx = plane_map(p, fx);
       if (active) load_pair(colA, mx, rawL);
     };
-    // consume the loads in flight as plane p: argument + E into registers (slot S), publish to
-    // ring slot S, park the raw values in stash slot q until update(p)
-    auto process = [&](int p, auto Sc, bool publish, int q) {
+    // consume the loads in flight as plane p: argument + E into register set S, publish to ring
+    // slot q, park the raw values in stash slot q until update(p)   (q < 0: registers only)
+    auto process = [&](int p, auto Sc, int q) {
       constexpr int S = decltype(Sc)::value;
+      const bool publish = q >= 0;
       bool fx;
       (void)plane_map(p, fx);
       F2 B[3], E[3];
@@ -344,7 +340,7 @@ __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(co
       RB[S][0] = B[1]; RB[S][1] = B[2];
       RE[S][0] = E[1]; RE[S][1] = E[2];
       if (publish && active) {  // rows / pairs beyond the grid must not touch the halo entries
-        publish_pair(smem + S * SLOT, smA, B, E);
+        publish_pair(smem + q * SLOT, smA, B, E);
         float* st = stash + q * SS;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -358,11 +354,11 @@ __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(co
         sts2(st + 6 * SP, rawL.rho);
       }
     };
-    // update of plane x (ring / register slot SC) from: ring slot SC (y / z neighbours), register
-    // slots SN = plane x+1 and SF = plane x-1 (x neighbours), stash slot q (R_0, R_k, rho)
+    // update of plane x (register set SC) from: ring slot q (y / z neighbours), register sets
+    // SN = plane x+1 and SF = plane x-1 (x neighbours), stash slot q (R_0, R_k, rho)
     auto update = [&](int x, auto SCc, auto SNc, auto SFc, int q) {
       constexpr int SC = decltype(SCc)::value, SN = decltype(SNc)::value, SF = decltype(SFc)::value;
-      const float* w = smem + SC * SLOT + smA;
+      const float* w = smem + q * SLOT + smA;
       const float* st = stash + q * SS;
       const F2 BC[3] = {lds2(w), RB[SC][0], RB[SC][1]};
       const F2 EC[3] = {lds2(w + 3 * PL), RE[SC][0], RE[SC][1]};
@@ -425,25 +421,22 @@ __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(co
       ch1 = max2(ch1, dv);
     };
 
-    // ---- prologue: planes xs-1 (registers only), xs, xs+1 (published); loads of xs+2 in flight
+    // ---- prologue: plane xs-1 in registers only, plane xs published; loads of xs+1 in flight
     issue(xs - 1);
-    process(xs - 1, IC<0>{}, false, 0);
+    process(xs - 1, IC<0>{}, -1);
     issue(xs);
-    process(xs, IC<1>{}, true, 0);
+    process(xs, IC<1>{}, 0);
     issue(xs + 1);
-    process(xs + 1, IC<2>{}, true, 1);
-    if (xs + 2 <= xe) issue(xs + 2);
     __syncthreads();
 
-    // one plane: update x, then turn the loads in flight into plane x+2 (which takes over the
-    // registers / ring slot of plane x-1 and the stash slot of plane x) and start the next loads
+    // one plane: the loads in flight become plane x+1 (register set SN, ring / stash slot q^1),
+    // the loads of plane x+2 start, then plane x (set SC, slot q) is updated with set SF = plane
+    // x-1.  Ring slot q^1 was last read by update(x-1), before the previous barrier.
     int q = 0;
     auto step = [&](int x, auto SCc, auto SNc, auto SFc) {
+      process(x + 1, SNc, q ^ 1);
+      if (x + 2 <= xe) issue(x + 2);
       if (active) update(x, SCc, SNc, SFc, q);
-      if (x + 2 <= xe) {
-        process(x + 2, SFc, true, q);
-        if (x + 3 <= xe) issue(x + 3);
-      }
       __syncthreads();
       q ^= 1;
     };
