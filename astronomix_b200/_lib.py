@@ -13,7 +13,7 @@ from . import option_classes as oc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libamx.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 AMX_F32, AMX_F64 = 0, 1
 AMX_ARITH_FAST, AMX_ARITH_STRICT = 0, 1
@@ -60,6 +60,8 @@ class AmxStats(C.Structure):
         ("time", C.c_double),
         ("last_dt", C.c_double),
         ("kernel_launches", C.c_int64),
+        ("pair_launches", C.c_int64),
+        ("single_launches", C.c_int64),
     ]
 
 

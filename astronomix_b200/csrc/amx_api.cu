@@ -34,7 +34,7 @@ int cuda_fail(cudaError_t e, const char* where) {
   } while (0)
 
 // ---- optional per-kernel-class timing (CUDA events on the launch stream; bench.py) -----------
-enum { PC_HYDRO_STAGE = 0, PC_SPLIT_SWEEP, PC_MAG_ITER, PC_MAG_FINAL, PC_ALPHA, PC_CONTROL, PC_COUNT };
+enum { PC_HYDRO_STAGE = 0, PC_SPLIT_SWEEP, PC_MAG_ITER, PC_MAG_FINAL, PC_ALPHA, PC_CONTROL, PC_MAG_PAIR, PC_COUNT };
 struct Profiler {
   bool on = false;
   struct Rec { int cls; cudaEvent_t a, b; };
@@ -103,8 +103,8 @@ int validate(const amx_desc* d) {
   if (d->riemann > AMX_LAX_FRIEDRICHS)
     return fail(AMX_EUNSUPPORTED, "HYBRID_HLLC / AM_HLLC fluxes are not built yet (SURVEY.md f2)");
   if (d->limiter < 0 || d->limiter > 5) return fail(AMX_EINVAL, "Unknown limiter.");
-  if (d->limiter == 5)
-    return fail(AMX_EUNSUPPORTED, "VAN_ALBADA_PP reconstruction is not built yet (SURVEY.md a14)");
+  if (d->limiter == 5 && d->split == AMX_UNSPLIT && d->ndim == 1)
+    return fail(AMX_EUNSUPPORTED, "VAN_ALBADA_PP in 1-D is not built (the reference's 1-D branch sums over the grid)");
   if (d->split == AMX_UNSPLIT) {
     if (d->time_integrator != AMX_RK2_SSP)
       return fail(AMX_EINVAL, "Only the RK2 SSP time integrator is currently supported for the unsplit scheme.");
@@ -174,6 +174,11 @@ NumPar numpar_of(const amx_desc* d) {
   p.dx = d->dx;
   // params.gamma enters the jitted loop as a scalar of the working dtype (Q20)
   p.gamma = d->dtype == AMX_F32 ? (double)(float)d->gamma : d->gamma;
+  // split sweeps call _calculate_limited_gradients only: VAN_ALBADA_PP is plain van Albada there
+  if (d->limiter == 5 && d->split != AMX_UNSPLIT) p.lim = 4;
+  // reconstruction.py:190-197: q = 2 / C_cfl (MHD: the hydro part runs half steps) or 1 / C_cfl
+  const double two = d->mhd ? 2.0 : 1.0;
+  p.pp_q = d->dtype == AMX_F32 ? (double)((float)two / (float)d->C_cfl) : two / d->C_cfl;
   return p;
 }
 
@@ -286,6 +291,7 @@ __global__ void step_begin_kernel(Ctl* ctl, DtPar p, long long max_steps) {
   ctl->dt_f = (float)dt;
   ctl->mag_active = 1;
   ctl->mag_iter = 0;
+  ctl->mag_fix = 0;
 }
 
 template <typename T>
@@ -308,17 +314,56 @@ __global__ void dt_only_kernel(const T* alpha_t, const T* time_t, DtPar p, T* dt
   *dt_out = dt_from_alpha<T>(a, q, time);
 }
 
-// _magnetic_field_update.py:127-141 while_condition, evaluated after launch j of the fixed point
+// _magnetic_field_update.py:127-141 while_condition.
+// Slot finalisation and while-condition in one launch, after a fixed-point launch that made
+// `nevals` evaluations (1: mag_iter_*, 2: mag_pair_vec) into iterate buffer `nb`, `c0` evaluations
+// having been completed before it.  The condition is evaluated after EACH evaluation, as the
+// reference does.  A pair whose first evaluation already ends the loop leaves R_{k+2} in the
+// buffer: mag_fix asks for that one evaluation to be re-run alone into the same buffer.
 template <typename T>
-__global__ void mag_check_kernel(Ctl* ctl, double tol, int j) {
-  if (ctl->done || !ctl->mag_active) return;
-  const T m = (T)ctl->change[0] > (T)ctl->change[1] ? (T)ctl->change[0] : (T)ctl->change[1];
-  if (m > (T)tol && ctl->mag_iter < 1000) {
-    ctl->mag_iter += 1;
-  } else {
+__global__ void mag_check_fused_kernel(Ctl* ctl, double tol, int c0, int nevals, int nb) {
+  if (ctl->done || !ctl->mag_active) return;  // the launch before this one exited without touching the slots
+  __shared__ T red[4][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = 0; k < 2 * nevals; ++k) {
+    unsigned long long* slots = k < 2 ? &ctl->change_slots[k][0] : &ctl->change2_slots[k - 2][0];
+    T m = T(0);
+    for (int i = threadIdx.x; i < kAlphaSlots; i += blockDim.x) {
+      const T v = from_bits<T>(slots[i]);
+      m = v > m ? v : m;
+      slots[i] = 0ull;
+    }
+    for (int o = 16; o > 0; o >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, m, o); m = w > m ? w : m; }
+    if (lane == 0) red[k][wid] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  T n[4] = {T(0), T(0), T(0), T(0)};
+  for (int k = 0; k < 2 * nevals; ++k)
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) n[k] = red[k][i] > n[k] ? red[k][i] : n[k];
+  ctl->change[0] = (double)n[0];
+  ctl->change[1] = (double)n[1];
+  if (nevals == 2) ctl->pair_runs += 1; else ctl->single_runs += 1;
+  const T m1 = n[0] > n[1] ? n[0] : n[1];
+  if (!(m1 > (T)tol && ctl->mag_iter < 1000)) {
     ctl->mag_active = 0;
-    ctl->mag_final = j & 1;
-    if (m > (T)tol) ctl->not_converged = 1;
+    ctl->mag_final = nb;
+    if (m1 > (T)tol) ctl->not_converged = 1;
+    if (nevals == 2) { ctl->mag_fix = 1; ctl->mag_fix_base = c0; ctl->single_runs += 1; }
+    return;
+  }
+  ctl->mag_iter += 1;
+  if (nevals == 2) {
+    const T m2 = n[2] > n[3] ? n[2] : n[3];
+    ctl->change[0] = (double)n[2];
+    ctl->change[1] = (double)n[3];
+    if (m2 > (T)tol && ctl->mag_iter < 1000) {
+      ctl->mag_iter += 1;
+    } else {
+      ctl->mag_active = 0;
+      ctl->mag_final = nb;
+      if (m2 > (T)tol) ctl->not_converged = 1;
+    }
   }
 }
 
@@ -329,6 +374,7 @@ __global__ void set_dt_kernel(Ctl* ctl, const T* dt_dev) {
   ctl->done = 0;
   ctl->mag_active = 1;
   ctl->mag_iter = 0;
+  ctl->mag_fix = 0;
 }
 
 // ---------------------------------------------------------------- layout kernels
@@ -458,6 +504,19 @@ bool force_generic() {
   return v;
 }
 
+// AMX_NO_PAIR=1 keeps the fixed point on one evaluation per launch (amx_pair.cu off)
+bool no_pair() {
+  static const bool v = [] { const char* e = getenv("AMX_NO_PAIR"); return e && e[0] == '1'; }();
+  return v;
+}
+
+// AMX_PAIR_GREEDY=1 enqueues pair launches regardless of the expected evaluation count, so an odd
+// count ends on the first evaluation of a pair and exercises the Ctl::mag_fix re-run (tests)
+bool pair_greedy() {
+  static const bool v = [] { const char* e = getenv("AMX_PAIR_GREEDY"); return e && e[0] == '1'; }();
+  return v;
+}
+
 // AMX_NO_VEC=1 skips the z-vectorised kernels (amx_vec.cu) in favour of the scalar tiled ones
 bool no_vec() {
   static const bool v = [] { const char* e = getenv("AMX_NO_VEC"); return e && e[0] == '1'; }();
@@ -473,13 +532,13 @@ struct Engine {
   Ctl* ctl;
   cudaStream_t st;
   long long launches = 0;
-  bool strict, is32, lf;
+  bool strict, is32, lf;  // lf: every stage needs the wave bounds of its input (Lax-Friedrichs alpha, PP limiter C)
 
   Engine(const amx_desc* d_, void* ws_, void* stream)
       : d(d_), L(make_layout(d_)), g(geom_of(d_)), np(numpar_of(d_)), ws(static_cast<char*>(ws_)),
         ctl(reinterpret_cast<Ctl*>(static_cast<char*>(ws_) + L.off_ctl)), st(static_cast<cudaStream_t>(stream)),
         strict(d_->arithmetic == AMX_ARITH_STRICT), is32(d_->dtype == AMX_F32),
-        lf(d_->riemann == AMX_LAX_FRIEDRICHS) {}
+        lf(d_->riemann == AMX_LAX_FRIEDRICHS || (d_->limiter == 5 && d_->split == AMX_UNSPLIT)) {}
 
   // view over an internal workspace buffer (x ghost planes resident in slab mode)
   View internal(size_t off, int first_row = 0) const {
@@ -604,8 +663,8 @@ struct Engine {
     return cudaSuccess;
   }
 
-  cudaError_t mag_iter(const View& B0, const View& gas0, const View* Xk, const View& Xk1, const void* dt,
-                       int j, bool guarded) {
+  MagIterArgs mag_args(const View& B0, const View& gas0, const View* Xk, const View& Xk1, const void* dt,
+                       int j, bool guarded) const {
     MagIterArgs a;
     a.g = g; a.np = np; a.B0 = B0; a.gas0 = gas0;
     if (Xk) { a.Bk = *Xk; a.vk = rows_of(*Xk, 3, L.esz); }
@@ -614,7 +673,41 @@ struct Engine {
     a.ctl_ro = guarded ? ctl : nullptr;
     a.first = (j == 0);
     a.midpoint = d->magnetic_integrator == AMX_IMPLICIT_MIDPOINT;
-    a.dt = dt; a.change_slots = cslots();
+    a.dt = dt; a.change_slots = cslots(); a.change_slots2 = &ctl->change2_slots[0][0];
+    a.fix_base = -1;
+    return a;
+  }
+  bool pair_supported(const MagIterArgs& a) const {
+    if (force_generic() || no_vec() || no_pair()) return false;
+    return strict ? amx_strict::pair_mag_supported(a) : amx_fast::pair_mag_supported(a);
+  }
+  // two evaluations in one launch (amx_pair.cu); c0 = evaluations completed before it
+  cudaError_t mag_pair(const View& B0, const View& gas0, const View* Xk, const View& Xk2, const void* dt, int c0) {
+    const MagIterArgs a = mag_args(B0, gas0, Xk, Xk2, dt, c0, true);
+    ++launches;
+    ProfScope ps(PC_MAG_PAIR, st);
+    return strict ? amx_strict::launch_mag_pair_vec(a, st) : amx_fast::launch_mag_pair_vec(a, st);
+  }
+  // the single evaluation c0 + 1 re-run into the pair's buffer when the loop ended on it (Ctl::mag_fix)
+  cudaError_t mag_fix(const View& B0, const View& gas0, const View* Xk, const View& Xk1, const void* dt, int c0) {
+    MagIterArgs a = mag_args(B0, gas0, Xk, Xk1, dt, c0, true);
+    a.fix_base = c0;
+    a.change_slots = nullptr;
+    ++launches;
+    ProfScope ps(PC_MAG_ITER, st);
+    return strict ? amx_strict::launch_mag_iter_vec(a, st) : amx_fast::launch_mag_iter_vec(a, st);
+  }
+  cudaError_t mag_check_fused(int c0, int nevals, int nb) {
+    ++launches;
+    const double tol = d->fp_tol;
+    if (is32) mag_check_fused_kernel<float><<<1, 256, 0, st>>>(ctl, tol, c0, nevals, nb);
+    else mag_check_fused_kernel<double><<<1, 256, 0, st>>>(ctl, tol, c0, nevals, nb);
+    return cudaGetLastError();
+  }
+
+  cudaError_t mag_iter(const View& B0, const View& gas0, const View* Xk, const View& Xk1, const void* dt,
+                       int j, bool guarded) {
+    const MagIterArgs a = mag_args(B0, gas0, Xk, Xk1, dt, j, guarded);
     ++launches;
     ProfScope ps(PC_MAG_ITER, st);
     const bool vec = !force_generic() && !no_vec() && (strict ? amx_strict::vec_mag_supported(a) : amx_fast::vec_mag_supported(a));
@@ -622,14 +715,6 @@ struct Engine {
     const bool tiled = !force_generic() && (strict ? amx_strict::tiled_mag_supported(a) : amx_fast::tiled_mag_supported(a));
     if (tiled) return strict ? amx_strict::launch_mag_iter_tiled(a, st) : amx_fast::launch_mag_iter_tiled(a, st);
     return strict ? amx_strict::launch_mag_iter(a, st) : amx_fast::launch_mag_iter(a, st);
-  }
-
-  cudaError_t mag_check(int j) {
-    ++launches;
-    const double tol = d->fp_tol;
-    if (is32) mag_check_kernel<float><<<1, 1, 0, st>>>(ctl, tol, j);
-    else mag_check_kernel<double><<<1, 1, 0, st>>>(ctl, tol, j);
-    return cudaGetLastError();
   }
 
   cudaError_t mag_final(const View& gas, const View& B_out, const View X[2], int fixed_final, bool want_alpha,
@@ -677,28 +762,43 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
   const View Bin = rows_of(sin, L.ng, L.esz), Bout = rows_of(sout, L.ng, L.esz);
   // second half-step needs two scratch buffers besides G: A and the gas rows of ... X is free by then
   CK(E.hydro(sin, G, A, X[0], 0.5, false));
-  int j = 0;
-  CK(E.mag_iter(Bin, G, nullptr, X[0], E.dt_ptr(), 0, true));
-  CK(E.finalize_change(nullptr, true));
-  CK(E.mag_check(0));
-  for (j = 1; j < *kspec; ++j) {
-    CK(E.mag_iter(Bin, G, &X[(j - 1) & 1], X[j & 1], E.dt_ptr(), j, true));
-    CK(E.finalize_change(nullptr, true));
-    CK(E.mag_check(j));
-  }
+  // Fixed point (_magnetic_field_update.py:82-205).  *kspec = evaluations the previous step needed:
+  // that many are enqueued (as pair launches where the kernel supports the problem, amx_pair.cu)
+  // plus one launch of slack, every launch followed by the device-side while-condition; launches
+  // past convergence exit at once.  Launch number L writes iterate buffer X[L & 1].
+  const bool pairs = E.pair_supported(E.mag_args(Bin, G, nullptr, X[0], E.dt_ptr(), 0, true));
+  int c = 0, nl = 0;  // evaluations / launches enqueued
+  auto enqueue = [&](bool pair) -> int {
+    const View* src = nl == 0 ? nullptr : &X[(nl - 1) & 1];
+    const View& dst = X[nl & 1];
+    if (pair) {
+      CK(E.mag_pair(Bin, G, src, dst, E.dt_ptr(), c));
+      CK(E.mag_check_fused(c, 2, nl & 1));
+      CK(E.mag_fix(Bin, G, src, dst, E.dt_ptr(), c));
+      c += 2;
+    } else {
+      CK(E.mag_iter(Bin, G, src, dst, E.dt_ptr(), nl, true));
+      CK(E.mag_check_fused(c, 1, nl & 1));
+      c += 1;
+    }
+    ++nl;
+    return AMX_OK;
+  };
+  const int expect = std::max(1, *kspec);
+  int rc;
+  while (c < expect)
+    if ((rc = enqueue(pairs && (expect - c >= 2 || pair_greedy())))) return rc;
+  if ((rc = enqueue(pairs))) return rc;  // slack
   Ctl* m;
-  int rc = read_ctl(E, &m);
+  rc = read_ctl(E, &m);
   if (rc) return rc;
   while (m->mag_active && !m->done) {
-    for (int e = 0; e < 2; ++e, ++j) {
-      CK(E.mag_iter(Bin, G, &X[(j - 1) & 1], X[j & 1], E.dt_ptr(), j, true));
-      CK(E.finalize_change(nullptr, true));
-      CK(E.mag_check(j));
-    }
+    if ((rc = enqueue(pairs))) return rc;
+    if (!pairs && (rc = enqueue(false))) return rc;
     rc = read_ctl(E, &m);
     if (rc) return rc;
   }
-  if (!m->done) *kspec = std::max(2, m->mag_iter + 2);  // launches needed = while-iterations + 1, plus slack
+  if (!m->done) *kspec = m->mag_iter + 1;
   CK(E.mag_final(G, Bout, X, -1, E.lf, nullptr, true));
   // X buffers are free again: reuse X[0] rows as sweep scratch
   CK(E.hydro(G, sout, A, X[0], 0.5, true));
@@ -839,7 +939,7 @@ int amx_step(const amx_desc* d, const void* seam_in, void* seam_out, const void*
   CK(cudaGetLastError());
   const View sin = E.user_seam(seam_in), sout = E.user_seam(seam_out);
   if (E.lf) CK(E.alpha_of(sin, nullptr, false));
-  int kspec = d->dtype == AMX_F32 ? 4 : 8;
+  int kspec = d->dtype == AMX_F32 ? 4 : 8;  // first guess of the evaluations per step
   if ((rc = run_step(E, sin, sout, &kspec))) return rc;
   if (d->boundary_handling == AMX_GHOST_CELLS) {
     // ghosts of the result: what the reference's trailing _boundary_handler calls leave behind
@@ -863,6 +963,8 @@ int amx_step(const amx_desc* d, const void* seam_in, void* seam_out, const void*
     stats->time = 0;
     stats->last_dt = m->dt_d;
     stats->kernel_launches = E.launches;
+    stats->pair_launches = m->pair_runs;
+    stats->single_launches = m->single_runs;
     if (m->not_converged) return fail(AMX_ENOTCONVERGED, "magnetic fixed point hit the 1000-iteration cap");
   }
   return AMX_OK;
@@ -884,7 +986,7 @@ int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpadded_out
   // wave bounds of the initial state (time_integration.py:643-653 on the first pass)
   CK(E.alpha_of(vin, nullptr, false));
   const DtPar p = E.dtpar(t_end);
-  int kspec = d->dtype == AMX_F32 ? 4 : 8;
+  int kspec = d->dtype == AMX_F32 ? 4 : 8;  // first guess of the evaluations per step
   long long issued = 0;
   const int lookahead = d->mhd ? 1 : 8;  // hydro steps enqueued between host looks at the loop state
   Ctl* m = nullptr;
@@ -924,6 +1026,8 @@ int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpadded_out
     stats->time = m->time_d;
     stats->last_dt = m->dt_d;
     stats->kernel_launches = E.launches;
+    stats->pair_launches = m->pair_runs;
+    stats->single_launches = m->single_runs;
   }
   if (m->not_converged) return fail(AMX_ENOTCONVERGED, "magnetic fixed point hit the 1000-iteration cap");
   return AMX_OK;

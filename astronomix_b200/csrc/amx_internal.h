@@ -29,6 +29,7 @@ struct NumPar {
   int dtype;  // 0 f32, 1 f64
   int rs, lim;
   double dx, gamma;
+  double pp_q;  // VAN_ALBADA_PP: 2 / C_cfl (MHD half steps) or 1 / C_cfl, evaluated in the working type
 };
 
 // Device-resident loop control.  Scalars are stored as double AND in the working type where
@@ -45,11 +46,15 @@ struct Ctl {
   int mag_iter;              // while-body iterations executed this step
   int mag_final;             // buffer index holding the converged iterate
   int not_converged;         // sticky: 1000-iteration cap was hit
+  int mag_fix;               // the loop ended on the FIRST evaluation of pair launch `mag_fix_base`:
+  int mag_fix_base;          //   that evaluation is re-run alone (evaluations completed before the pair)
   int pad0;
   long long steps;
   long long mag_iters_total;
+  long long pair_runs, single_runs;  // fixed-point launches that did work (bench.py byte accounting)
   unsigned long long alpha_slots[3][kAlphaSlots];  // bit patterns of non-negative T values
   unsigned long long change_slots[2][kAlphaSlots];
+  unsigned long long change2_slots[2][kAlphaSlots];  // second evaluation of a pair launch (amx_pair.cu)
 };
 
 struct StageArgs {
@@ -89,7 +94,9 @@ struct MagIterArgs {
   int first;          // launch 0 of the fixed point never skips on mag_active
   int midpoint;       // IMPLICIT_MIDPOINT (1) or IMPLICIT_EULER (0)
   const void* dt;
-  unsigned long long* change_slots;  // [2][kAlphaSlots]
+  unsigned long long* change_slots;   // [2][kAlphaSlots]; nullable (no norms wanted)
+  unsigned long long* change_slots2;  // pair launch: norms of the second evaluation
+  int fix_base;  // >= 0: run only if ctl->mag_fix && ctl->mag_fix_base == fix_base (see Ctl)
 };
 
 struct MagFinalArgs {
@@ -141,7 +148,9 @@ struct CopyArgs {  // strided row copy (pad / unpad / concatenate)
   bool vec_mag_supported(const amx::MagIterArgs&);                                        \
   cudaError_t launch_mag_iter_vec(const amx::MagIterArgs&, cudaStream_t);                 \
   bool vec_stage_supported(const amx::StageArgs&);                                        \
-  cudaError_t launch_hydro_stage_vec(const amx::StageArgs&, cudaStream_t);
+  cudaError_t launch_hydro_stage_vec(const amx::StageArgs&, cudaStream_t);                \
+  bool pair_mag_supported(const amx::MagIterArgs&);                                       \
+  cudaError_t launch_mag_pair_vec(const amx::MagIterArgs&, cudaStream_t);
 
 }  // namespace amx
 

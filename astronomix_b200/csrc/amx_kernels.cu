@@ -190,6 +190,157 @@ __global__ void __launch_bounds__(256) hydro_stage_kernel(const StageArgs a) {
   if (a.alpha_slots) block_max_to_slots<T, ND>(wb, a.alpha_slots);
 }
 
+// ---------------------------------------------------------------- unsplit stage, VAN_ALBADA_PP
+// reconstruction.py:134-394: the van-Albada half-differences of ALL axes of a cell are scaled
+// together so that every interface state keeps rho > 0, p > 0 (alpha_density, kappa_pressure per
+// axis) and positive internal energy (beta, one per cell; needs the global wave bounds C_a =
+// alpha_a / sum(alpha)).  The flux at an interface needs the scaled difference of the cells on
+// both sides, and a cell's factors need its differences along every axis: a thread evaluates the
+// factors of its own cell and of its 2*ND face neighbours (ghost positions included: their
+// differences are those of the ghost-filled array, like the reference's).  Functional path of
+// one thread per cell, (1 + 2 ND)^2 state loads, all of them L1 / L2 hits.
+template <typename T, int ND>
+AMX_DI Gas<T, ND> load_at(const View& v, const Geom& g, const Idx3& pos) {
+  Idx3 q = pos;
+  bool flip[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) q.i[k] = map_index<ND>(pos.i[k], g.n[k], g.bc[k][0], g.bc[k][1], flip[k]);
+  Gas<T, ND> s = load_gas<T, ND>(v, offset_of<ND>(v, q));
+#pragma unroll
+  for (int k = 0; k < ND; ++k)
+    if (flip[k]) s.q[k + 1] = -s.q[k + 1];
+  return s;
+}
+
+// scaled half-differences of the cell at `pos` along axis `want` (0-based); s0 = its state
+template <typename T, int ND>
+AMX_DI Gas<T, ND> pp_half_difference(const View& v, const Geom& g, const Idx3& pos, const Gas<T, ND>& s0,
+                                     int want, const T (&Cax)[ND], T q, const Consts<T>& c) {
+  constexpr int P = ND + 1;
+  const T eps = (T)1e-14, one_eps = (T)(1.0 + 1e-14);
+  Gas<T, ND> d[ND];
+#pragma unroll
+  for (int a = 0; a < ND; ++a) {
+    Idx3 m = pos, p = pos;
+    m.i[a] -= 1;
+    p.i[a] += 1;
+    const Gas<T, ND> gsl = slopes<T, ND, LIM_VAN_ALBADA>(load_at<T, ND>(v, g, m), s0, load_at<T, ND>(v, g, p),
+                                                        LIM_VAN_ALBADA, c);
+#pragma unroll
+    for (int k = 0; k < ND + 2; ++k) d[a].q[k] = (gsl.q[k] * c.dx) / T(2);
+  }
+  const T rho = s0.q[0], pr = s0.q[P];
+  T alpha_d[ND], kappa[ND];
+#pragma unroll
+  for (int a = 0; a < ND; ++a) {
+    const T dr = d[a].q[0], dp = d[a].q[P];
+    alpha_d[a] = rabs(dr) > eps ? rmin(rho / (rabs(dr) * one_eps), T(1)) : T(1);
+    kappa[a] = rabs(dp) > eps ? rmin(pr / (rabs(dp) * one_eps), T(1)) : T(1);
+  }
+  // A1 = sum_j (sum_i C_j alpha_j drho_j d_i v_j)^2, A2 = sum_i C_i sum_j (d_i v_j)^2 (index pairing
+  // of the reference's broadcast), vsum = sum_i sum_j (d_i v_j)^2
+  T A1 = T(0), A2 = T(0), vsum = T(0);
+#pragma unroll
+  for (int j = 0; j < ND; ++j) {
+    const T f = (Cax[j] * alpha_d[j]) * d[j].q[0];
+    T acc = T(0);
+#pragma unroll
+    for (int i = 0; i < ND; ++i) acc = i == 0 ? f * d[i].q[1 + j] : acc + f * d[i].q[1 + j];
+    A1 = j == 0 ? acc * acc : A1 + acc * acc;
+  }
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    T acc = T(0);
+#pragma unroll
+    for (int j = 0; j < ND; ++j) acc = j == 0 ? sq(d[i].q[1 + j]) : acc + sq(d[i].q[1 + j]);
+    A2 = i == 0 ? Cax[i] * acc : A2 + Cax[i] * acc;
+    vsum = i == 0 ? acc : vsum + acc;
+  }
+  T beta = T(1);
+  if (vsum > eps) {
+    const T qm2 = q - T(2);
+    const T num = ((qm2 * qm2) * rho) * pr;
+    const T den = c.gm1 * (T(2) * A1 + (qm2 * sq(rho)) * A2);
+    beta = rmin(rsqrt_(num / den), T(1));
+  }
+  Gas<T, ND> r = d[0];
+#pragma unroll
+  for (int a = 1; a < ND; ++a)
+    if (a == want) r = d[a];
+  T al = alpha_d[0], ka = kappa[0];
+#pragma unroll
+  for (int a = 1; a < ND; ++a)
+    if (a == want) { al = alpha_d[a]; ka = kappa[a]; }
+  r.q[0] = r.q[0] * al;
+  r.q[P] = r.q[P] * ka;
+#pragma unroll
+  for (int k = 1; k <= ND; ++k) r.q[k] = r.q[k] * beta;
+  return r;
+}
+
+template <typename T, int ND, int RS>
+__global__ void __launch_bounds__(128) hydro_stage_pp_kernel(const StageArgs a) {
+  if (a.ctl_ro && a.ctl_ro->done) return;
+  const Consts<T> c = make_consts<T>(a.np);
+  Idx3 cell;
+  const bool active = decode_cell<ND>(a.g, cell);
+  T wb[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) wb[k] = T(0);
+  if (active) {
+    const T dt = *static_cast<const T*>(a.dt) * (T)a.dt_scale;
+    const T q = (T)a.np.pp_q;
+    T alpha[ND], Cax[ND], asum = T(0);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      alpha[k] = static_cast<const T*>(a.alpha_lf)[k];
+      asum = k == 0 ? alpha[k] : asum + alpha[k];
+    }
+#pragma unroll
+    for (int k = 0; k < ND; ++k) Cax[k] = alpha[k] / asum;
+    const Gas<T, ND> sc = load_gas<T, ND>(a.in, offset_of<ND>(a.in, cell));
+    Gas<T, ND> U = cons_from_prim(sc, c);
+#pragma unroll
+    for (int ax = 0; ax < ND; ++ax) {
+      Idx3 pm = cell, pp = cell;
+      pm.i[ax] -= 1;
+      pp.i[ax] += 1;
+      const Gas<T, ND> sm1 = load_at<T, ND>(a.in, a.g, pm), sp1 = load_at<T, ND>(a.in, a.g, pp);
+      const Gas<T, ND> dm = pp_half_difference<T, ND>(a.in, a.g, pm, sm1, ax, Cax, q, c);
+      const Gas<T, ND> dc = pp_half_difference<T, ND>(a.in, a.g, cell, sc, ax, Cax, q, c);
+      const Gas<T, ND> dp = pp_half_difference<T, ND>(a.in, a.g, pp, sp1, ax, Cax, q, c);
+      Gas<T, ND> hi_m, lo_c, hi_c, lo_p;
+#pragma unroll
+      for (int k = 0; k < ND + 2; ++k) {
+        hi_m.q[k] = sm1.q[k] + dm.q[k];
+        lo_c.q[k] = sc.q[k] - dc.q[k];
+        hi_c.q[k] = sc.q[k] + dc.q[k];
+        lo_p.q[k] = sp1.q[k] - dp.q[k];
+      }
+      const T al = RS == RS_LF ? alpha[ax] : T(0);
+      const Gas<T, ND> Fl = riemann<T, ND, RS>(hi_m, lo_c, ax + 1, al, c);
+      const Gas<T, ND> Fr = riemann<T, ND, RS>(hi_c, lo_p, ax + 1, al, c);
+#pragma unroll
+      for (int k = 0; k < ND + 2; ++k) U.q[k] = U.q[k] + (c.inv_dx * (Fl.q[k] - Fr.q[k])) * dt;
+    }
+    Gas<T, ND> s = prim_from_cons(U, c);
+    if (a.in0.p) {
+      const Gas<T, ND> s0 = load_gas<T, ND>(a.in0, offset_of<ND>(a.in0, cell));
+      const Gas<T, ND> U0 = cons_from_prim(s0, c), U2 = cons_from_prim(s, c);
+      Gas<T, ND> Um;
+#pragma unroll
+      for (int k = 0; k < ND + 2; ++k) Um.q[k] = T(0.5) * (U0.q[k] + U2.q[k]);
+      s = prim_from_cons(Um, c);
+    }
+    store_gas<T, ND>(a.out, offset_of<ND>(a.out, cell), s);
+    if (a.alpha_slots) {
+#pragma unroll
+      for (int k = 0; k < ND; ++k) wb[k] = wave_bound(s, k + 1, c);
+    }
+  }
+  if (a.alpha_slots) block_max_to_slots<T, ND>(wb, a.alpha_slots);
+}
+
 // ---------------------------------------------------------------- split MUSCL-Hancock sweep
 // AX = 0-based sweep axis (compile time, so every per-axis index stays in registers)
 template <typename T, int ND, int RS, int AX>
@@ -449,6 +600,18 @@ static inline unsigned grid_for(const Geom& g) {
   }
 
 template <typename T>
+static cudaError_t launch_hydro_stage_pp_t(const StageArgs& a, cudaStream_t st) {
+  if (a.g.nd < 2 || !a.alpha_lf) return cudaErrorInvalidValue;
+  long long total = (long long)a.g.n[0] * a.g.n[1] * (a.g.nd == 3 ? a.g.n[2] : 1);
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  AMX_DISPATCH_RS(a.np.rs, {
+    if (a.g.nd == 2) hydro_stage_pp_kernel<T, 2, RS><<<grid, 128, 0, st>>>(a);
+    else hydro_stage_pp_kernel<T, 3, RS><<<grid, 128, 0, st>>>(a);
+  })
+  return cudaGetLastError();
+}
+
+template <typename T>
 static cudaError_t launch_hydro_stage_t(const StageArgs& a, cudaStream_t st) {
   AMX_DISPATCH_ND(a.g.nd, AMX_DISPATCH_RS(a.np.rs, {
     const unsigned grid = grid_for<ND>(a.g);
@@ -458,6 +621,8 @@ static cudaError_t launch_hydro_stage_t(const StageArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_hydro_stage(const StageArgs& a, cudaStream_t st) {
+  if (a.np.lim == LIM_VAN_ALBADA_PP)
+    return a.np.dtype == 0 ? launch_hydro_stage_pp_t<float>(a, st) : launch_hydro_stage_pp_t<double>(a, st);
   return a.np.dtype == 0 ? launch_hydro_stage_t<float>(a, st) : launch_hydro_stage_t<double>(a, st);
 }
 

@@ -17,7 +17,8 @@
 
 namespace amx {
 
-enum : int { LIM_MINMOD = 0, LIM_OSHER = 1, LIM_DOUBLE_MINMOD = 2, LIM_SUPERBEE = 3, LIM_VAN_ALBADA = 4 };
+enum : int { LIM_MINMOD = 0, LIM_OSHER = 1, LIM_DOUBLE_MINMOD = 2, LIM_SUPERBEE = 3, LIM_VAN_ALBADA = 4,
+             LIM_VAN_ALBADA_PP = 5 };
 enum : int { RS_HLL = 0, RS_HLLC = 1, RS_HLLC_LM = 2, RS_LF = 3 };
 
 #define AMX_DI __device__ __forceinline__

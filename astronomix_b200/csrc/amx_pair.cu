@@ -1,0 +1,378 @@
+// amx_pair.cu -- TWO consecutive evaluations of the Pang-Wu fixed point in one launch (fp32, 3-D).
+//
+//   R_{k+1} = R_0 - dt * Psi(arg(R_k,     R_0))        (_magnetic_field_update.py:82-165)
+//   R_{k+2} = R_0 - dt * Psi(arg(R_{k+1}, R_0))
+//
+// The fixed point is memory-bound: one evaluation streams R_0, rho, R_k (13 words per cell) and
+// writes R_{k+1} (6 words).  Fusing two evaluations keeps R_{k+1} on chip: 19 words per TWO
+// evaluations instead of 38 (temporal blocking).  The intermediate iterate is never
+// written; both change norms max|R_k - R_{k+1}| and max|R_{k+1} - R_{k+2}| are produced, so the
+// reference's while-condition (:127-141) is evaluated after every evaluation exactly as before.
+// If the loop turns out to end on the FIRST evaluation of a pair, amx_api.cu re-runs that single
+// evaluation from R_k (still intact in the other iterate buffer) with mag_iter_vec.
+//
+// Layout: a block owns a TY (y) x 64 (z) tile of columns and marches along x.  One warp per
+// window row (32 pairs of z-adjacent cells per row), the window being the tile plus a 2-cell
+// frame: rows y0-2 .. y0+TY+1, cells z0-2 .. z0+65.
+//   warps 0 .. TY-1    tile rows            load, argument 1, evaluation 1, evaluation 2
+//   warps TY, TY+1     rows y0-1, y0+TY     load, argument 1, evaluation 1 (frame of evaluation 2)
+//   warps TY+2, TY+3   rows y0-2, y0+TY+1   load, argument 1
+//   warp  TY+4         the two side pairs (z0-2, z0-1) and (z0+64, z0+65) of every window row
+// Per plane step i (one __syncthreads each):
+//   P1(i+2)  the loads in flight become plane i+2: argument (B, v), E = B x v -> ring A
+//   E1(i+1)  Psi from ring A (planes i, i+1, i+2), R_{k+1}(i+1), norm 1, argument 2 -> ring B;
+//            R_0, rho, R_{k+1} of the own pair -> thread-private stash; loads of plane i+3 start
+//   E2(i)    Psi from ring B (planes i-1, i, i+1), R_{k+2}(i) -> global memory, norm 2
+// Rings hold 3 planes of (B, E) (6 fields); x neighbours are the own column in the other two
+// slots, y / z neighbours come from the centre slot.  y and z must be periodic (a ghost cell of an
+// open / reflective side is a COPY of an interior R_{k+1}, not a cell with its own stencil);
+// x is periodic or resident halo planes (slab ranks).  Anything else runs as two single launches.
+#include "amx_vec_common.cuh"
+
+#include <cstdlib>
+
+namespace AMX_NS {
+using namespace amx;
+
+namespace vec {
+
+template <int TY>
+struct PG {
+  static constexpr int WYA = TY + 4, WYB = TY + 2;
+  static constexpr int RS = 72;  // window row: cell column c (0 .. 67) at float c + 2
+  static constexpr int PLA = WYA * RS, PLB = WYB * RS;
+  static constexpr int SLOTA = 6 * PLA, SLOTB = 6 * PLB;
+  static constexpr int NT = 32 * TY;   // tile threads
+  static constexpr int SP = 2 * NT;    // floats per stashed field
+  static constexpr int SS = 13 * SP;   // floats per stash slot
+  static constexpr int kWarps = TY + 5, kThreads = 32 * kWarps;
+  static constexpr size_t smem_bytes = (size_t)(3 * SLOTA + 3 * SLOTB + 2 * SS) * sizeof(float);
+};
+
+struct RawP {
+  F2 B0[3], v0[3], rho, Bk[3], vk[3];
+};
+
+// Psi of the argument whose (B, E) sit in a 3-slot ring: curl E and B x curl B of the own pair.
+// w / wm / wp point at field 0 of the own pair in the centre / x-1 / x+1 slots (_vector_maths.py:55-78).
+template <int PL, int RS>
+AMX_DI void psi_ring(const float* w, const float* wm, const float* wp, float dpar, F2 (&curlE)[3], F2 (&cr)[3]) {
+  auto cd = [&](F2 fp, F2 fm) -> F2 {
+#if AMX_STRICT
+    const F2 h = bc2(0.5f) * (fp - fm);
+    return mk2(h.x / dpar, h.y / dpar);
+#else
+    return bc2(dpar) * (fp - fm);
+#endif
+  };
+  F2 BC[3], EC[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    BC[k] = lds2(w + k * PL);
+    EC[k] = lds2(w + (3 + k) * PL);
+  }
+  auto ddl = [&](int f, F2 own) -> F2 {
+    const float l = w[f * PL - 1], r = w[f * PL + 2];
+    return cd(mk2(own.y, r), mk2(l, own.x));
+  };
+  auto ddy = [&](int f) -> F2 { return cd(lds2(w + f * PL + RS), lds2(w + f * PL - RS)); };
+  auto ddx = [&](int f) -> F2 { return cd(lds2(wp + f * PL), lds2(wm + f * PL)); };
+  F2 curlB[3];
+  curlB[0] = ddy(2) - ddl(1, BC[1]);
+  curlB[1] = ddl(0, BC[0]) - ddx(2);
+  curlB[2] = ddx(1) - ddy(0);
+  curlE[0] = ddy(5) - ddl(4, EC[1]);
+  curlE[1] = ddl(3, EC[0]) - ddx(5);
+  curlE[2] = ddx(4) - ddy(3);
+  cr[0] = BC[1] * curlB[2] - BC[2] * curlB[1];
+  cr[1] = BC[2] * curlB[0] - BC[0] * curlB[2];
+  cr[2] = BC[0] * curlB[1] - BC[1] * curlB[0];
+}
+
+// FIRST: evaluation 1 starts from R_k = R_0 (launch 0 of the fixed point).  MID: implicit midpoint
+// (argument (R + R_0)/2) or implicit Euler (argument R).
+template <bool FIRST, bool MID, int TY, int LD>
+__global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIterArgs a, const int xchunk) {
+  if (a.ctl_ro && (a.ctl_ro->done || (!a.first && !a.ctl_ro->mag_active))) return;
+  using G = PG<TY>;
+  constexpr int RS = G::RS, PLA = G::PLA, PLB = G::PLB, SLOTA = G::SLOTA, SLOTB = G::SLOTB;
+  constexpr int SP = G::SP, SS = G::SS;
+  extern __shared__ __align__(16) float smem[];
+  float* const ringA = smem;                    // [3][6][TY+4][RS]
+  float* const ringB = smem + 3 * SLOTA;        // [3][6][TY+2][RS]
+  float* const stash0 = ringB + 3 * SLOTB;      // [2][13][NT] pairs
+
+  const Geom& g = a.g;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int z0 = blockIdx.x * 64;
+  const int y0 = blockIdx.y * TY;
+  const int xs = blockIdx.z * xchunk;
+  const int xe = min(xs + xchunk, g.n[0]);
+  if (xs >= xe) return;
+  const float dt = *static_cast<const float*>(a.dt);
+#if AMX_STRICT
+  const float dpar = (float)a.np.dx;
+#else
+  const float dpar = 0.5f * (float)(1.0 / a.np.dx);
+#endif
+  const int ta = min(TY, g.n[1] - y0);
+  const int tqa = min(32, (g.n[2] - z0) >> 1);
+  const long long sx = a.B0.s[0], sy = a.B0.s[1];
+  const float* const fB0 = static_cast<const float*>(a.B0.p);
+  const float* const fG = static_cast<const float*>(a.gas0.p);
+  const float* const fBk = static_cast<const float*>(a.Bk.p);
+  const float* const fvk = static_cast<const float*>(a.vk.p);
+  const long long vB0 = a.B0.vs, vG = a.gas0.vs, vBk = a.Bk.vs, vvk = a.vk.vs;
+  float* const fB1 = static_cast<float*>(a.Bk1.p);
+  float* const fv1 = static_cast<float*>(a.vk1.p);
+  const long long vB1 = a.Bk1.vs, vv1 = a.vk1.vs;
+  const bool xwrap = g.bc[0][0] == BC_PERIODIC;
+
+  // ---- role of this thread: window row j, window cell column c, what it computes
+  int j, c;
+  bool exists, e1, e2 = false, need_rho = true;
+  if (wid < TY) {
+    j = 2 + wid; c = 2 + 2 * lane;
+    exists = wid < ta && lane < tqa;
+    e1 = e2 = exists;
+  } else if (wid < TY + 2) {
+    j = wid == TY ? 1 : ta + 2; c = 2 + 2 * lane;
+    exists = lane < tqa;
+    e1 = exists;
+  } else if (wid < TY + 4) {
+    j = wid == TY + 2 ? 0 : ta + 3; c = 2 + 2 * lane;
+    exists = lane < tqa;
+    e1 = false;
+    need_rho = false;
+  } else {
+    j = lane >> 1; c = (lane & 1) ? 2 + 2 * tqa : 0;
+    exists = j < ta + 4;
+    e1 = exists && j >= 1 && j <= ta + 2;
+  }
+  int gy = y0 - 2 + j, gz = z0 - 2 + c;
+  gy += gy < 0 ? g.n[1] : (gy >= g.n[1] ? -g.n[1] : 0);
+  gz += gz < 0 ? g.n[2] : (gz >= g.n[2] ? -g.n[2] : 0);
+  const Col col = gz + (long long)gy * sy;
+  const int smA = j * RS + c + 2;
+  const int smB = (j - 1) * RS + c + 2;
+  float* const stash = stash0 + 2 * (wid * 32 + lane);  // tile threads only
+
+  auto plane_off = [&](int p) -> long long {
+    if (xwrap) p += p < 0 ? g.n[0] : (p >= g.n[0] ? -g.n[0] : 0);
+    return col + (long long)p * sx;
+  };
+  auto issue = [&](int p, RawP& r) {
+    if (!exists) return;
+    const long long o = plane_off(p);
+    const float* pb = fB0 + o;
+    const float* pg = fG + o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      r.B0[k] = ldg2<LD>(pb + k * vB0);
+      r.v0[k] = ldg2<LD>(pg + (k + 1) * vG);
+    }
+    if (need_rho) r.rho = ldg2<LD>(pg);
+    if constexpr (!FIRST) {
+      const float* pbk = fBk + o;
+      const float* pvk = fvk + o;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        r.Bk[k] = ldg2<LD>(pbk + k * vBk);
+        r.vk[k] = ldg2<LD>(pvk + k * vvk);
+      }
+    }
+  };
+  // argument of an evaluation from the iterate (Bi, vi) and R_0; E = B x v (_vector_maths.py:6-12)
+  auto publish_arg = [&](float* dst, int PL, const F2 (&Bi)[3], const F2 (&vi)[3], const F2 (&B0)[3],
+                         const F2 (&v0)[3], bool from_r0) {
+    F2 B[3], v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (from_r0) { B[k] = B0[k]; v[k] = v0[k]; }
+      else if constexpr (MID) { B[k] = (Bi[k] + B0[k]) * bc2(0.5f); v[k] = (vi[k] + v0[k]) * bc2(0.5f); }
+      else { B[k] = Bi[k]; v[k] = vi[k]; }
+    }
+    F2 E[3];
+    E[0] = B[1] * v[2] - B[2] * v[1];
+    E[1] = B[2] * v[0] - B[0] * v[2];
+    E[2] = B[0] * v[1] - B[1] * v[0];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      sts2(dst + k * PL, B[k]);
+      sts2(dst + (3 + k) * PL, E[k]);
+    }
+  };
+  // R_new = R_0 - dt * Psi and the squared change norms against (Bp, vp)
+  auto advance = [&](const F2 (&curlE)[3], const F2 (&cr)[3], const F2 (&B0)[3], const F2 (&v0)[3], F2 rho,
+                     F2 (&Bn)[3], F2 (&vn)[3]) {
+#if !AMX_STRICT
+    const F2 ir = mk2(rdiv(1.f, rho.x), rdiv(1.f, rho.y));
+#endif
+    const F2 dt2 = bc2(dt);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#if AMX_STRICT
+      const F2 phiB = mk2(cr[k].x / rho.x, cr[k].y / rho.y);
+#else
+      const F2 phiB = cr[k] * ir;
+#endif
+      Bn[k] = B0[k] - dt2 * curlE[k];
+      vn[k] = v0[k] - dt2 * phiB;
+    }
+  };
+  auto change = [&](const F2 (&Bp)[3], const F2 (&vp)[3], const F2 (&Bn)[3], const F2 (&vn)[3], F2& mB, F2& mv) {
+    F2 dB = bc2(0.f), dv = bc2(0.f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const F2 eB = abs2(Bp[k] - Bn[k]), ev = abs2(vp[k] - vn[k]);
+      dB = dB + eB * eB;
+      dv = dv + ev * ev;
+    }
+    mB = max2(mB, dB);
+    mv = max2(mv, dv);
+  };
+
+  F2 n1B = bc2(0.f), n1v = bc2(0.f), n2B = bc2(0.f), n2v = bc2(0.f);
+  RawP rawX, rawY;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    rawX.B0[k] = rawX.v0[k] = rawX.Bk[k] = rawX.vk[k] = rawY.B0[k] = rawY.v0[k] = rawY.Bk[k] = rawY.vk[k] = bc2(0.f);
+  rawX.rho = rawY.rho = bc2(1.f);
+
+  // ring slots of planes i-1, i, i+1, i+2 rotate with i: slot(p) = (p - xs + 6) % 3
+  // sM / sC / sP: slots of planes i-1, i, i+1; plane i+2 shares the slot of plane i-1.
+  // At i = xs - 4 these are the slots of planes xs-5, xs-4, xs-3.
+  int sM = 1, sC = 2, sP = 0;
+
+  // rawN: plane i+2 (landing); rawC: plane i+1 (argument already published)
+  auto step = [&](int i, RawP& rawN, RawP& rawC) {
+    // ---- P1(i+2)
+    if (exists) publish_arg(ringA + sM * SLOTA + smA, PLA, rawN.Bk, rawN.vk, rawN.B0, rawN.v0, FIRST);
+    // ---- E1(i+1): ring A planes i (sC), i+1 (sP), i+2 (sM)
+    if (i >= xs - 2) {
+      if (e1) {
+        F2 curlE[3], cr[3], Bn[3], vn[3];
+        psi_ring<PLA, RS>(ringA + sP * SLOTA + smA, ringA + sC * SLOTA + smA, ringA + sM * SLOTA + smA, dpar, curlE, cr);
+        advance(curlE, cr, rawC.B0, rawC.v0, rawC.rho, Bn, vn);
+        publish_arg(ringB + sP * SLOTB + smB, PLB, Bn, vn, rawC.B0, rawC.v0, false);
+        if (e2) {
+          if constexpr (FIRST) change(rawC.B0, rawC.v0, Bn, vn, n1B, n1v);
+          else change(rawC.Bk, rawC.vk, Bn, vn, n1B, n1v);
+          float* st = stash + ((i + 1) & 1) * SS;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            sts2(st + k * SP, rawC.B0[k]);
+            sts2(st + (3 + k) * SP, rawC.v0[k]);
+            sts2(st + (7 + k) * SP, Bn[k]);
+            sts2(st + (10 + k) * SP, vn[k]);
+          }
+          sts2(st + 6 * SP, rawC.rho);
+        }
+      }
+    }
+    if (i + 3 <= xe + 1) issue(i + 3, rawC);
+    // ---- E2(i): ring B planes i-1 (sM), i (sC), i+1 (sP)
+    if (i >= xs && e2) {
+      const float* st = stash + (i & 1) * SS;
+      F2 B0[3], v0[3], B1[3], v1[3], curlE[3], cr[3], Bn[3], vn[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        B0[k] = lds2(st + k * SP);
+        v0[k] = lds2(st + (3 + k) * SP);
+        B1[k] = lds2(st + (7 + k) * SP);
+        v1[k] = lds2(st + (10 + k) * SP);
+      }
+      const F2 rho = lds2(st + 6 * SP);
+      psi_ring<PLB, RS>(ringB + sC * SLOTB + smB, ringB + sM * SLOTB + smB, ringB + sP * SLOTB + smB, dpar, curlE, cr);
+      advance(curlE, cr, B0, v0, rho, Bn, vn);
+      change(B1, v1, Bn, vn, n2B, n2v);
+      const long long o = col + (long long)i * sx;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        stg2(fB1 + o + k * vB1, Bn[k]);
+        stg2(fv1 + o + k * vv1, vn[k]);
+      }
+    }
+    __syncthreads();
+    const int t = sM; sM = sC; sC = sP; sP = t;
+  };
+
+  issue(xs - 2, rawX);
+  for (int i = xs - 4;;) {
+    step(i, rawX, rawY);
+    if (++i >= xe) break;
+    step(i, rawY, rawX);
+    if (++i >= xe) break;
+  }
+
+  // ---- change norms: sqrt of the block maxima of the squared 3-norms -> spread slots
+  float chs[4] = {rsqrt_(fmaxf(n1B.x, n1B.y)), rsqrt_(fmaxf(n1v.x, n1v.y)), rsqrt_(fmaxf(n2B.x, n2B.y)),
+                  rsqrt_(fmaxf(n2v.x, n2v.y))};
+  __shared__ float red[4][G::kWarps];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) chs[k] = fmaxf(chs[k], __shfl_xor_sync(0xffffffffu, chs[k], o));
+    if (lane == 0) red[k][wid] = chs[k];
+  }
+  __syncthreads();
+  if (tid < 4) {
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < G::kWarps; ++i) m = fmaxf(m, red[tid][i]);
+    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    unsigned long long* slots = tid < 2 ? a.change_slots : a.change_slots2;
+    atomicMax(slots + (size_t)(tid & 1) * kAlphaSlots + (bid % kAlphaSlots), bits_of(m));
+  }
+}
+
+template <bool FIRST, bool MID, int TY, int LD>
+cudaError_t launch_pair_ld(const MagIterArgs& a, cudaStream_t st) {
+  using G = PG<TY>;
+  auto kern = mag_pair_vec<FIRST, MID, TY, LD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid;
+  grid.x = (a.g.n[2] + 63) / 64;
+  grid.y = (a.g.n[1] + TY - 1) / TY;
+  const int nch = pick_chunks(a.g.n[0], (long long)grid.x * grid.y, 1, 3);
+  const int xchunk = (a.g.n[0] + nch - 1) / nch;
+  grid.z = (a.g.n[0] + xchunk - 1) / xchunk;
+  kern<<<grid, G::kThreads, G::smem_bytes, st>>>(a, xchunk);
+  return cudaGetLastError();
+}
+
+// AMX_PAIR_LD=1: stream the inputs past L1 (ld.global.nc.L1::no_allocate); default: plain __ldg
+template <bool FIRST, bool MID, int TY>
+cudaError_t launch_pair(const MagIterArgs& a, cudaStream_t st) {
+  static const int ld = [] { const char* e = getenv("AMX_PAIR_LD"); return e ? atoi(e) : 0; }();
+  return ld == 1 ? launch_pair_ld<FIRST, MID, TY, 1>(a, st) : launch_pair_ld<FIRST, MID, TY, 0>(a, st);
+}
+
+constexpr int kPairTY = 11;
+
+}  // namespace vec
+
+// fp32, 3-D, y and z periodic, x periodic or resident halo planes, same layout rules as mag_iter_vec
+bool pair_mag_supported(const MagIterArgs& a) {
+  if (!vec_mag_supported(a)) return false;
+  if (a.g.nd != 3 || !a.change_slots2) return false;
+  if (a.g.bc[1][0] != BC_PERIODIC || a.g.bc[1][1] != BC_PERIODIC) return false;
+  if (a.g.bc[2][0] != BC_PERIODIC || a.g.bc[2][1] != BC_PERIODIC) return false;
+  const bool xper = a.g.bc[0][0] == BC_PERIODIC && a.g.bc[0][1] == BC_PERIODIC;
+  const bool xhalo = a.g.bc[0][0] == BC_HALO && a.g.bc[0][1] == BC_HALO;
+  if (!xper && !xhalo) return false;
+  return a.g.n[0] >= 4 && a.g.n[1] >= 4 && a.g.n[2] >= 8;
+}
+
+cudaError_t launch_mag_pair_vec(const MagIterArgs& a, cudaStream_t st) {
+  constexpr int TY = vec::kPairTY;
+  if (!a.Bk.p) return a.midpoint ? vec::launch_pair<true, true, TY>(a, st) : vec::launch_pair<true, false, TY>(a, st);
+  return a.midpoint ? vec::launch_pair<false, true, TY>(a, st) : vec::launch_pair<false, false, TY>(a, st);
+}
+
+}  // namespace AMX_NS

@@ -15,73 +15,14 @@
 //   * 41 load/store instructions per pair per plane (the scalar tiled kernel: ~100 per cell).
 // Compiled twice like the other kernel files (fast / strict arithmetic); STRICT keeps the
 // reference's operation order (no contraction), so it is bitwise equal to the generic kernel.
-#include "amx_internal.h"
-#include "amx_math.cuh"
+#include "amx_vec_common.cuh"
 
 #include <cstdlib>
-#include <type_traits>
-
-#if AMX_STRICT
-#define AMX_NS amx_strict
-#else
-#define AMX_NS amx_fast
-#endif
 
 namespace AMX_NS {
 using namespace amx;
 
 namespace vec {
-
-AMX_DI F2 max2(F2 a, F2 b) { return mk2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
-AMX_DI F2 abs2(F2 a) { return mk2(fabsf(a.x), fabsf(a.y)); }
-
-// streamed global loads: every input line is used once per block, so it must not take an L1
-// line (the L1 left beside ~180 KB of shared memory is smaller than the loads in flight)
-template <int LD>
-AMX_DI F2 ldg2(const float* p) {
-  F2 r;
-  if constexpr (LD == 0) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
-    r = mk2(v.x, v.y);
-  } else if constexpr (LD == 1) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  } else {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  }
-  return r;
-}
-template <int LD>
-AMX_DI float ldg1(const float* p) {
-  float r;
-  if constexpr (LD == 0) r = __ldg(p);
-  else asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
-  return r;
-}
-AMX_DI void stg2(float* p, F2 v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
-AMX_DI F2 lds2(const float* p) {
-  const float2 v = *reinterpret_cast<const float2*>(p);
-  return mk2(v.x, v.y);
-}
-AMX_DI void sts2(float* p, F2 v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
-
-AMX_DI int map_index(int i, int n, int bcl, int bcr, bool& flip) {
-  flip = false;
-  if (i < 0) {
-    if (bcl == BC_PERIODIC) return i + n;
-    if (bcl == BC_OPEN) return 0;
-    if (bcl == BC_REFLECTIVE) { flip = true; return -1 - i; }
-    return i;
-  }
-  if (i >= n) {
-    if (bcr == BC_PERIODIC) return i - n;
-    if (bcr == BC_OPEN) return n - 1;
-    if (bcr == BC_REFLECTIVE) { flip = true; return 2 * n - 1 - i; }
-    return i;
-  }
-  return i;
-}
-
-AMX_DI unsigned long long bits_of(float v) { return (unsigned long long)__float_as_uint(v); }
 
 // 7 compute warps + 1 halo warp (register allocation is per 4 warps: 8 warps x 128 registers
 // x 2 blocks fills the register file exactly)
@@ -100,15 +41,16 @@ constexpr size_t mag_vec_smem_bytes() {
 struct Raw {
   F2 B0[3], v0[3], rho, Bk[3], vk[3];
 };
-// A column is the element offset of its plane-0 cell, shared by every array of the launch
-// (vec_mag_supported checks that all views have the same x / y strides).
-using Col = long long;
-template <int N> using IC = std::integral_constant<int, N>;
 
 // MODE 0: first iterate (R_k = R_0, Bk / vk absent); 1: implicit midpoint; 2: implicit Euler
 template <int ND, int MODE, int LD, int CW>
 __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(const MagIterArgs a, const int xchunk) {
-  if (a.ctl_ro && (a.ctl_ro->done || (!a.first && !a.ctl_ro->mag_active))) return;
+  if (a.ctl_ro) {
+    if (a.ctl_ro->done) return;
+    if (a.fix_base >= 0) {
+      if (!a.ctl_ro->mag_fix || a.ctl_ro->mag_fix_base != a.fix_base) return;
+    } else if (!a.first && !a.ctl_ro->mag_active) return;
+  }
   constexpr int kComputeThreads = 32 * CW, kThreads = kComputeThreads + 32;
   constexpr int TY = VT<ND, CW>::TY, TQ = VT<ND, CW>::TQ, TZ = 2 * TQ;
   constexpr int WY = ND == 3 ? TY + 2 : 1, RS = TZ + 4, YO = ND == 3 ? 1 : 0, LA = ND - 1;
@@ -461,7 +403,7 @@ __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(co
     if (lane == 0) red[k][wid] = chs[k];
   }
   __syncthreads();
-  if (tid < 2) {
+  if (tid < 2 && a.change_slots) {
     float m = 0.f;
 #pragma unroll
     for (int i = 0; i < kThreads / 32; ++i) m = fmaxf(m, red[tid][i]);
@@ -470,20 +412,6 @@ __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(co
   }
 }
 
-// number of x chunks minimising (waves of blocks) x (planes per chunk + prologue planes)
-inline int pick_chunks(int nx, long long tiles, int blocks_per_sm, int prologue) {
-  const long long slots = 148LL * blocks_per_sm;
-  int best = 1;
-  long long best_cost = -1;
-  const int maxch = nx / 8 > 0 ? nx / 8 : 1;
-  for (int nch = 1; nch <= maxch; ++nch) {
-    const long long blocks = tiles * nch;
-    const long long waves = (blocks + slots - 1) / slots;
-    const long long cost = waves * ((nx + nch - 1) / nch + prologue);
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nch; }
-  }
-  return best;
-}
 
 template <int ND, int MODE, int LD, int CW>
 cudaError_t launch_mag(const MagIterArgs& a, cudaStream_t st) {
@@ -1021,14 +949,6 @@ cudaError_t launch_stage_vec(const StageArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
-inline bool view_ok(const View& v, int nd) {
-  const int la = nd - 1;
-  if (v.s[la] != 1 || (v.vs & 1) || !aligned8(v.p)) return false;
-  for (int ax = 0; ax < la; ++ax)
-    if (v.s[ax] & 1) return false;
-  return true;
-}
 
 }  // namespace vec
 
@@ -1068,6 +988,7 @@ cudaError_t launch_mag_iter_vec(const MagIterArgs& a, cudaStream_t st) {
 
 // fp32, 2-D / 3-D, in / out / in0 with the same 8-byte-aligned contiguous layout, even lane extent
 bool vec_stage_supported(const StageArgs& a) {
+  if (a.np.lim == LIM_VAN_ALBADA_PP) return false;  // multi-axis limiter: generic kernel (amx_kernels.cu)
   if (a.np.dtype != 0) return false;
   const int nd = a.g.nd;
   if (nd != 2 && nd != 3) return false;

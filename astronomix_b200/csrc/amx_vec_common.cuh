@@ -1,0 +1,102 @@
+// amx_vec_common.cuh -- helpers shared by the z-vectorised kernel files (amx_vec.cu, amx_pair.cu):
+// streamed 64-bit global / shared accessors, boundary index mapping, launch-shape helpers.
+#pragma once
+#include "amx_internal.h"
+#include "amx_math.cuh"
+
+#include <cstdint>
+#include <type_traits>
+
+#if AMX_STRICT
+#define AMX_NS amx_strict
+#else
+#define AMX_NS amx_fast
+#endif
+
+namespace AMX_NS {
+using namespace amx;
+namespace vec {
+
+
+AMX_DI F2 max2(F2 a, F2 b) { return mk2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+AMX_DI F2 abs2(F2 a) { return mk2(fabsf(a.x), fabsf(a.y)); }
+
+// streamed global loads: every input line is used once per block, so it must not take an L1
+// line (the L1 left beside ~180 KB of shared memory is smaller than the loads in flight)
+template <int LD>
+AMX_DI F2 ldg2(const float* p) {
+  F2 r;
+  if constexpr (LD == 0) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    r = mk2(v.x, v.y);
+  } else if constexpr (LD == 1) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  } else {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  }
+  return r;
+}
+template <int LD>
+AMX_DI float ldg1(const float* p) {
+  float r;
+  if constexpr (LD == 0) r = __ldg(p);
+  else asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+AMX_DI void stg2(float* p, F2 v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+AMX_DI F2 lds2(const float* p) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return mk2(v.x, v.y);
+}
+AMX_DI void sts2(float* p, F2 v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+
+AMX_DI int map_index(int i, int n, int bcl, int bcr, bool& flip) {
+  flip = false;
+  if (i < 0) {
+    if (bcl == BC_PERIODIC) return i + n;
+    if (bcl == BC_OPEN) return 0;
+    if (bcl == BC_REFLECTIVE) { flip = true; return -1 - i; }
+    return i;
+  }
+  if (i >= n) {
+    if (bcr == BC_PERIODIC) return i - n;
+    if (bcr == BC_OPEN) return n - 1;
+    if (bcr == BC_REFLECTIVE) { flip = true; return 2 * n - 1 - i; }
+    return i;
+  }
+  return i;
+}
+
+AMX_DI unsigned long long bits_of(float v) { return (unsigned long long)__float_as_uint(v); }
+
+// A column is the element offset of its plane-0 cell, shared by every array of the launch
+// (vec_mag_supported checks that all views have the same x / y strides).
+using Col = long long;
+template <int N> using IC = std::integral_constant<int, N>;
+
+// number of x chunks minimising (waves of blocks) x (planes per chunk + prologue planes)
+inline int pick_chunks(int nx, long long tiles, int blocks_per_sm, int prologue) {
+  const long long slots = 148LL * blocks_per_sm;
+  int best = 1;
+  long long best_cost = -1;
+  const int maxch = nx / 8 > 0 ? nx / 8 : 1;
+  for (int nch = 1; nch <= maxch; ++nch) {
+    const long long blocks = tiles * nch;
+    const long long waves = (blocks + slots - 1) / slots;
+    const long long cost = waves * ((nx + nch - 1) / nch + prologue);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nch; }
+  }
+  return best;
+}
+
+inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+inline bool view_ok(const View& v, int nd) {
+  const int la = nd - 1;
+  if (v.s[la] != 1 || (v.vs & 1) || !aligned8(v.p)) return false;
+  for (int ax = 0; ax < la; ++ax)
+    if (v.s[ax] & 1) return false;
+  return true;
+}
+
+}  // namespace vec
+}  // namespace AMX_NS

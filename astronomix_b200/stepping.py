@@ -35,6 +35,8 @@ class IntegrationInfo(NamedTuple):
     last_dt: float
     magnetic_iterations: int
     kernel_launches: int
+    pair_launches: int = 0    # fixed-point launches that made two evaluations (amx_pair.cu)
+    single_launches: int = 0  # fixed-point launches that made one evaluation
 
 
 #: statistics of the most recent time_integration call on this process
@@ -149,7 +151,7 @@ def time_integration(primitive_state, config, params, registered_variables: Regi
         _lib.check(lib.amx_integrate(C.byref(desc), C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()),
                                      float(params.t_end), -1, ws_ptr, _stream_ptr(), C.byref(stats)))
     last_info = IntegrationInfo(stats.steps, stats.time, stats.last_dt, stats.magnetic_iterations,
-                                stats.kernel_launches)
+                                stats.kernel_launches, stats.pair_launches, stats.single_launches)
     res = _from_device(out, kind)
     return StateStruct(primitive_state=res) if struct else res
 
@@ -170,7 +172,7 @@ def integrate_steps(primitive_state, config, params, registered_variables, num_s
                                              float(params.t_end), int(num_steps), ws_ptr, _stream_ptr(),
                                              C.byref(stats)))
     last_info = IntegrationInfo(stats.steps, stats.time, stats.last_dt, stats.magnetic_iterations,
-                                stats.kernel_launches)
+                                stats.kernel_launches, stats.pair_launches, stats.single_launches)
     return _from_device(out, kind)
 
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AMX_ABI_VERSION 1
+#define AMX_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define AMX_API __attribute__((visibility("default")))
@@ -93,6 +93,8 @@ typedef struct amx_stats {
   double time;                /* simulation time reached */
   double last_dt;
   int64_t kernel_launches;    /* libamx kernels enqueued by the call */
+  int64_t pair_launches;      /* fixed-point launches that made two evaluations (temporal blocking) */
+  int64_t single_launches;    /* fixed-point launches that made one evaluation */
 } amx_stats;
 
 AMX_API int amx_abi_version(void);
@@ -103,7 +105,7 @@ AMX_API int amx_device_check(void);
 /* Per-kernel-class device timing for bench.py: when enabled, amx_integrate / amx_step bracket
  * every launch of a class with CUDA events on the launch stream and accumulate the elapsed
  * time.  Classes: 0 hydro stage, 1 split sweep, 2 magnetic iteration, 3 magnetic write-back,
- * 4 wave-bound reduction, 5 control.  amx_profile_enable also resets the counters. */
+ * 4 wave-bound reduction, 5 control, 6 magnetic pair (two evaluations per launch).  amx_profile_enable also resets the counters. */
 AMX_API int amx_profile_enable(int on);
 AMX_API int amx_profile_read(int kernel_class, double* ms_total, int64_t* launches);
 

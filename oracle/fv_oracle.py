@@ -476,15 +476,74 @@ def evolve_gas_state_split(s, dt, gamma, o):
     return s
 
 
+def reconstruct_unsplit_pp(s, gamma, o):
+    """reconstruction.py:134-394 with limiter VAN_ALBADA_PP: van-Albada half-differences along every
+    axis, scaled per cell so that the interface states keep density, pressure (alpha_density,
+    kappa_pressure) and internal energy (beta) positive (Pang & Wu).  Returns the left / right
+    interface states of every axis.  The expressions are written exactly as the reference writes
+    them, so NumPy's trailing-axis broadcasting reproduces its index pairing: in A1 the per-AXIS
+    factor C_d * alpha_d * drho_d lines up with velocity COMPONENT d of the velocity differences
+    (A1 = sum_j (C_j alpha_j drho_j sum_i d_i v_j)^2), and in 1-D the sums run over the grid."""
+    t = s.dtype.type
+    dim = o.dim
+    grads = np.stack([calculate_limited_gradients(s, o, axis) for axis in range(1, dim + 1)])
+    diff = grads * o.grid_spacing / 2  # [axis][var][grid]
+    eps = 1e-14
+    rho, p = s[o.rho_i], s[o.p_i]
+    c = speed_of_sound(rho, p, gamma)
+    alpha_lax = np.stack([np.max(np.abs(s[axis]) + c) for axis in range(1, dim + 1)]).astype(s.dtype)
+    C = alpha_lax / np.sum(alpha_lax)
+    q = (t(2) if o.mhd else t(1)) / t(o.C_cfl)
+    drho, dp = diff[:, o.rho_i], diff[:, o.p_i]
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        drho_prot = np.where(np.abs(drho) > eps, drho, t(eps))
+        dp_prot = np.where(np.abs(dp) > eps, dp, t(eps))
+        alpha_density = np.where(np.abs(drho) > eps,
+                                 np.minimum(rho / (np.abs(drho_prot) * (1 + eps)), 1), 1).astype(s.dtype)
+        kappa_pressure = np.where(np.abs(dp) > eps,
+                                  np.minimum(p / (np.abs(dp_prot) * (1 + eps)), 1), 1).astype(s.dtype)
+        Cb = C.reshape((dim,) + (1,) * dim)
+        if dim == 1:
+            dv = diff[:, 1]  # velocity_index is an int in 1-D: [axis][grid]
+            A1 = np.sum(np.sum(Cb * alpha_density * drho * dv, axis=0) ** 2, axis=0)
+            A2 = np.sum(Cb * np.sum(dv ** 2, axis=1), axis=0)
+        else:
+            dv = diff[:, 1:1 + dim]  # [axis][component][grid]
+            A1 = np.sum(np.sum(Cb * alpha_density * drho * dv, axis=0) ** 2, axis=0)
+            A2 = np.sum(Cb * np.sum(dv ** 2, axis=1), axis=0)
+        dvs = diff[:, 1:1 + dim]
+        vsum = np.sum(np.sum(dvs ** 2, axis=1), axis=0)
+        A1 = np.where(vsum > eps, A1, t(eps))
+        A2 = np.where(vsum > eps, A2, t(eps))
+        beta = np.where(
+            vsum > eps,
+            np.minimum(np.sqrt(((q - 2) ** 2 * rho * p) / ((gamma - 1) * (2 * A1 + (q - 2) * rho ** 2 * A2))), 1),
+            1).astype(s.dtype)
+    diff = diff.copy()
+    diff[:, o.rho_i] = drho * alpha_density
+    diff[:, o.p_i] = dp * kappa_pressure
+    diff[:, 1:1 + dim] = dvs * beta
+    Ls, Rs = [], []
+    for axis in range(1, dim + 1):
+        left_center = s - diff[axis - 1]
+        right_center = s + diff[axis - 1]
+        Ls.append(roll(right_center, 1, axis))
+        Rs.append(left_center)
+    return Ls, Rs
+
+
 def evolve_gas_state_unsplit_inner(s, dt, gamma, o):
     """evolve_state.py:339-414 (one forward-Euler stage; all axes from the same state)."""
-    if o.limiter == VAN_ALBADA_PP:
-        raise NotImplementedError("VAN_ALBADA_PP reconstruction (SURVEY.md a14) is not restated yet")
     s = _bc(s, o)
     U = conserved_state_from_primitive(s, gamma, o)
+    if o.limiter == VAN_ALBADA_PP:
+        pls, prs = reconstruct_unsplit_pp(s, gamma, o)
     for axis in range(1, o.dim + 1):
         s = _bc(s, o)
-        L, R = reconstruct_unsplit_single(s, o, axis)
+        if o.limiter == VAN_ALBADA_PP:
+            L, R = pls[axis - 1], prs[axis - 1]
+        else:
+            L, R = reconstruct_unsplit_single(s, o, axis)
         F = riemann_solver(L, R, s, gamma, o, axis)
         dU = 1 / o.grid_spacing * stencil_add(F, (0, 1), (1.0, -1.0), axis) * dt
         U = U + dU

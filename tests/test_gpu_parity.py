@@ -353,3 +353,44 @@ def test_vec_hydro_fp32_vs_oracle(cuda, dim, n, rs, arith):
     s = pr.smooth_random(dim, n, seed=61 + dim, dtype=np.float32)
     config, params, rv = pr.make(dim, n, riemann_solver=rs)
     check(s, config, params, rv, 6, arith)
+
+
+# ---- fused pair of fixed-point evaluations (amx_pair.cu): fp32, 3-D, periodic ----
+@pytest.mark.parametrize("n", [24, 40, 72])
+@pytest.mark.parametrize("integrator", ["midpoint", "euler"])
+@pytest.mark.parametrize("greedy", ["0", "1"])
+def test_pair_equals_single_evaluations_bitwise_in_strict_mode(cuda, n, integrator, greedy):
+    """Two evaluations per launch (R_{k+1} kept on chip) against one evaluation per launch and against
+    the one-thread-per-cell kernels: identical bits and identical iteration counts.  The sizes give
+    ragged tiles in y (11-row tiles) and z (64-cell tiles); AMX_PAIR_GREEDY=1 makes odd evaluation
+    counts end on the first half of a pair, which exercises the single-evaluation re-run."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r);"
+        "from astronomix_b200 import problems as pr, stepping as ti, _lib, option_classes as oc;"
+        "s = pr.smooth_random(3, %d, mhd=True, seed=17, dtype=np.float32);"
+        "c, p, rv = pr.make(3, %d, mhd=True, fv_magnetic_integrator=%s);"
+        "out = ti.integrate_steps(s, c, p, rv, 4, arithmetic=_lib.AMX_ARITH_STRICT);"
+        "i = ti.last_info;"
+        "np.save(sys.argv[1], np.concatenate([out.ravel(), "
+        "np.array([i.magnetic_iterations, i.pair_launches, i.single_launches], dtype=np.float32)]))"
+    ) % (root, n, n, "oc.IMPLICIT_MIDPOINT" if integrator == "midpoint" else "oc.IMPLICIT_EULER")
+    pair, single, generic = _run_subprocess_variants(
+        code, [{"AMX_PAIR_GREEDY": greedy}, {"AMX_NO_PAIR": "1"}, {"AMX_FORCE_GENERIC": "1"}])
+    assert np.isfinite(pair).all()
+    assert pair[-2] > 0, "the pair kernel did not run"
+    assert single[-2] == 0 and generic[-2] == 0
+    assert np.array_equal(pair[:-2], single[:-2])      # state and iteration count
+    assert np.array_equal(pair[:-3], generic[:-3])
+    assert pair[-3] == generic[-3]
+
+
+@pytest.mark.parametrize("arith", ["fast", "strict"])
+def test_pair_blast_fp32_vs_oracle(cuda, arith):
+    """3-D MHD blast (the bench workload's shape) at 48^3 through the pair kernel vs the oracle:
+    tolerance of the north star, equal fixed-point iteration counts."""
+    config, params, rv = pr.make(3, 48, mhd=True)
+    s = pr.mhd_blast3d(48, np.float32, p_in=100.0, p_out=1.0, B0=10.0, r_inj=0.125)
+    check(s, config, params, rv, 6, arith)
+    assert ti.last_info.pair_launches > 0
