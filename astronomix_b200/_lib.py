@@ -103,13 +103,17 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = LIB_PATH
+    exp = os.environ.get("AMX_LIB_VARIANT")  # kernel A/B builds: libamx_<variant>.so (csrc/Makefile, EXP=...)
+    if exp:
+        path = os.path.join(os.path.dirname(LIB_PATH), f"libamx_{exp}.so")
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} not found: the CUDA library is not built. Run "
+            f"{path} not found: the CUDA library is not built. Run "
             "`python -c 'import __graft_entry__ as g; g.build()'` in the repo root. "
             "astronomix_b200 has no CPU fallback."
         )
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype = res

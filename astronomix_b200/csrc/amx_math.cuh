@@ -270,6 +270,17 @@ AMX_DI T limited_slope(T a, T b, int lim, const Consts<T>& c) {
   }
 }
 
+#if !AMX_STRICT && defined(AMX_MINMOD3)
+// FAST pairs: minmod(a, b) = median(a, b, 0) = a + b - max3(a, b, 0) - min3(a, b, 0): two 3-input
+// FMNMX3 per cell on the half-rate ALU pipe instead of four FMNMX, the sums as packed adds.  The sum
+// rounds (error <= ulp(a + b)); the exact min / max form stays in the STRICT flavour.
+AMX_DI F2 minmod(F2 a, F2 b) {
+  const F2 hi = mk2(fmaxf(fmaxf(a.x, b.x), 0.f), fmaxf(fmaxf(a.y, b.y), 0.f));
+  const F2 lo = mk2(fminf(fminf(a.x, b.x), 0.f), fminf(fminf(a.y, b.y), 0.f));
+  return ((a + b) - hi) - lo;
+}
+#endif
+
 // pairs: the non-minmod limiters branch per cell, so they run per half on the scalar code
 AMX_DI F2 limited_slope(F2 a, F2 b, int lim, const Consts<F2>& c) {
   if (lim == LIM_MINMOD) return minmod(a, b);

@@ -23,8 +23,9 @@
 //   E1(i+1)  Psi from ring A (planes i, i+1, i+2), R_{k+1}(i+1), norm 1, argument 2 -> ring B;
 //            R_0, rho, R_{k+1} of the own pair -> thread-private stash; loads of plane i+3 start
 //   E2(i)    Psi from ring B (planes i-1, i, i+1), R_{k+2}(i) -> global memory, norm 2
-// Rings hold 3 planes of (B, E) (6 fields); x neighbours are the own column in the other two
-// slots, y / z neighbours come from the centre slot.  y and z must be periodic (a ghost cell of an
+// Rings hold 3 planes of (B, E) (6 fields); the x-1 neighbour is the own column in another slot, the
+// x+1 neighbour was computed by the thread itself a moment earlier (registers), y / z neighbours
+// come from the centre slot.  y and z must be periodic (a ghost cell of an
 // open / reflective side is a COPY of an interior R_{k+1}, not a cell with its own stencil);
 // x is periodic or resident halo planes (slab ranks).  Anything else runs as two single launches.
 #include "amx_vec_common.cuh"
@@ -36,15 +37,21 @@ using namespace amx;
 
 namespace vec {
 
+// Ring layout (per slot): [group g = 0..2][window row][chunk][4 floats] with one 16-byte chunk per
+// pair holding (B_g.x, E_g.x, B_g.y, E_g.y): every shared-memory access of an evaluation is a
+// 128-bit one (own chunk, y / x neighbours) or a 64-bit one that returns the B AND E value of a
+// z neighbour (the .y halves of the chunk on the left, the .x halves of the chunk on the right):
+// 15 loads + 3 stores per evaluation instead of 30 + 6 (the kernel is bound by the number of
+// LSU instructions in flight, not by their bytes).
 template <int TY>
 struct PG {
   static constexpr int WYA = TY + 4, WYB = TY + 2;
-  static constexpr int RS = 72;  // window row: cell column c (0 .. 67) at float c + 2
+  static constexpr int RS = 144;  // window row: 36 chunks; window cell column c (0 .. 66, even) is chunk c/2 + 1
   static constexpr int PLA = WYA * RS, PLB = WYB * RS;
-  static constexpr int SLOTA = 6 * PLA, SLOTB = 6 * PLB;
+  static constexpr int SLOTA = 3 * PLA, SLOTB = 3 * PLB;
   static constexpr int NT = 32 * TY;   // tile threads
-  static constexpr int SP = 2 * NT;    // floats per stashed field
-  static constexpr int SS = 13 * SP;   // floats per stash slot
+  static constexpr int SP = 4 * NT;    // floats per stashed float4 field
+  static constexpr int SS = 7 * SP;    // floats per stash slot: 13 pairs packed into 7 float4
   static constexpr int kWarps = TY + 5, kThreads = 32 * kWarps;
   static constexpr size_t smem_bytes = (size_t)(3 * SLOTA + 3 * SLOTB + 2 * SS) * sizeof(float);
 };
@@ -53,10 +60,16 @@ struct RawP {
   F2 B0[3], v0[3], rho, Bk[3], vk[3];
 };
 
+AMX_DI float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+AMX_DI void sts4(float* p, F2 a, F2 b) { *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y); }
+
 // Psi of the argument whose (B, E) sit in a 3-slot ring: curl E and B x curl B of the own pair.
-// w / wm / wp point at field 0 of the own pair in the centre / x-1 / x+1 slots (_vector_maths.py:55-78).
+// w / wm point at group 0 of the own chunk in the centre / x-1 slots; the x+1 neighbours of the
+// own column (components 1, 2) were computed by this thread in this step and come in registers
+// (_vector_maths.py:55-78).
 template <int PL, int RS>
-AMX_DI void psi_ring(const float* w, const float* wm, const float* wp, float dpar, F2 (&curlE)[3], F2 (&cr)[3]) {
+AMX_DI void psi_ring(const float* w, const float* wm, const F2 (&Bp)[3], const F2 (&Ep)[3], float dpar,
+                     F2 (&curlE)[3], F2 (&cr)[3]) {
   auto cd = [&](F2 fp, F2 fm) -> F2 {
 #if AMX_STRICT
     const F2 h = bc2(0.5f) * (fp - fm);
@@ -68,22 +81,41 @@ AMX_DI void psi_ring(const float* w, const float* wm, const float* wp, float dpa
   F2 BC[3], EC[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    BC[k] = lds2(w + k * PL);
-    EC[k] = lds2(w + (3 + k) * PL);
+    const float4 o = lds4(w + k * PL);
+    BC[k] = mk2(o.x, o.z);
+    EC[k] = mk2(o.y, o.w);
   }
-  auto ddl = [&](int f, F2 own) -> F2 {
-    const float l = w[f * PL - 1], r = w[f * PL + 2];
-    return cd(mk2(own.y, r), mk2(l, own.x));
-  };
-  auto ddy = [&](int f) -> F2 { return cd(lds2(w + f * PL + RS), lds2(w + f * PL - RS)); };
-  auto ddx = [&](int f) -> F2 { return cd(lds2(wp + f * PL), lds2(wm + f * PL)); };
+  // z neighbours of groups 0, 1: (B.y, E.y) of the chunk on the left, (B.x, E.x) of the chunk on the right
+  F2 dlB[2], dlE[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const F2 l = lds2(w + k * PL - 2), r = lds2(w + k * PL + 4);
+    dlB[k] = cd(mk2(BC[k].y, r.x), mk2(l.x, BC[k].x));
+    dlE[k] = cd(mk2(EC[k].y, r.y), mk2(l.y, EC[k].x));
+  }
+  // y neighbours of groups 0, 2
+  F2 dyB[2], dyE[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float4 u = lds4(w + 2 * k * PL + RS), d = lds4(w + 2 * k * PL - RS);
+    dyB[k] = cd(mk2(u.x, u.z), mk2(d.x, d.z));
+    dyE[k] = cd(mk2(u.y, u.w), mk2(d.y, d.w));
+  }
+  // x neighbours of groups 1, 2
+  F2 dxB[2], dxE[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float4 m = lds4(wm + (1 + k) * PL);
+    dxB[k] = cd(Bp[1 + k], mk2(m.x, m.z));
+    dxE[k] = cd(Ep[1 + k], mk2(m.y, m.w));
+  }
   F2 curlB[3];
-  curlB[0] = ddy(2) - ddl(1, BC[1]);
-  curlB[1] = ddl(0, BC[0]) - ddx(2);
-  curlB[2] = ddx(1) - ddy(0);
-  curlE[0] = ddy(5) - ddl(4, EC[1]);
-  curlE[1] = ddl(3, EC[0]) - ddx(5);
-  curlE[2] = ddx(4) - ddy(3);
+  curlB[0] = dyB[1] - dlB[1];
+  curlB[1] = dlB[0] - dxB[1];
+  curlB[2] = dxB[0] - dyB[0];
+  curlE[0] = dyE[1] - dlE[1];
+  curlE[1] = dlE[0] - dxE[1];
+  curlE[2] = dxE[0] - dyE[0];
   cr[0] = BC[1] * curlB[2] - BC[2] * curlB[1];
   cr[1] = BC[2] * curlB[0] - BC[0] * curlB[2];
   cr[2] = BC[0] * curlB[1] - BC[1] * curlB[0];
@@ -98,9 +130,9 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
   constexpr int RS = G::RS, PLA = G::PLA, PLB = G::PLB, SLOTA = G::SLOTA, SLOTB = G::SLOTB;
   constexpr int SP = G::SP, SS = G::SS;
   extern __shared__ __align__(16) float smem[];
-  float* const ringA = smem;                    // [3][6][TY+4][RS]
-  float* const ringB = smem + 3 * SLOTA;        // [3][6][TY+2][RS]
-  float* const stash0 = ringB + 3 * SLOTB;      // [2][13][NT] pairs
+  float* const ringA = smem;                    // [3][3][TY+4][RS]
+  float* const ringB = smem + 3 * SLOTA;        // [3][3][TY+2][RS]
+  float* const stash0 = ringB + 3 * SLOTB;      // [2][7][NT] float4
 
   const Geom& g = a.g;
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -153,9 +185,9 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
   gy += gy < 0 ? g.n[1] : (gy >= g.n[1] ? -g.n[1] : 0);
   gz += gz < 0 ? g.n[2] : (gz >= g.n[2] ? -g.n[2] : 0);
   const Col col = gz + (long long)gy * sy;
-  const int smA = j * RS + c + 2;
-  const int smB = (j - 1) * RS + c + 2;
-  float* const stash = stash0 + 2 * (wid * 32 + lane);  // tile threads only
+  const int smA = j * RS + 2 * c + 4;        // chunk c/2 + 1
+  const int smB = (j - 1) * RS + 2 * c + 4;
+  float* const stash = stash0 + 4 * (wid * 32 + lane);  // tile threads only
 
   auto plane_off = [&](int p) -> long long {
     if (xwrap) p += p < 0 ? g.n[0] : (p >= g.n[0] ? -g.n[0] : 0);
@@ -182,27 +214,24 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
       }
     }
   };
-  // argument of an evaluation from the iterate (Bi, vi) and R_0; E = B x v (_vector_maths.py:6-12)
+  // argument of an evaluation from the iterate (Bi, vi) and R_0; E = B x v (_vector_maths.py:6-12);
+  // published to the ring as 3 chunks, returned for the x+1 neighbour of the next evaluation
   auto publish_arg = [&](float* dst, int PL, const F2 (&Bi)[3], const F2 (&vi)[3], const F2 (&B0)[3],
-                         const F2 (&v0)[3], bool from_r0) {
-    F2 B[3], v[3];
+                         const F2 (&v0)[3], bool from_r0, F2 (&B)[3], F2 (&E)[3]) {
+    F2 v[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       if (from_r0) { B[k] = B0[k]; v[k] = v0[k]; }
       else if constexpr (MID) { B[k] = (Bi[k] + B0[k]) * bc2(0.5f); v[k] = (vi[k] + v0[k]) * bc2(0.5f); }
       else { B[k] = Bi[k]; v[k] = vi[k]; }
     }
-    F2 E[3];
     E[0] = B[1] * v[2] - B[2] * v[1];
     E[1] = B[2] * v[0] - B[0] * v[2];
     E[2] = B[0] * v[1] - B[1] * v[0];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      sts2(dst + k * PL, B[k]);
-      sts2(dst + (3 + k) * PL, E[k]);
-    }
+    for (int k = 0; k < 3; ++k) sts4(dst + k * PL, mk2(B[k].x, E[k].x), mk2(B[k].y, E[k].y));
   };
-  // R_new = R_0 - dt * Psi and the squared change norms against (Bp, vp)
+  // R_new = R_0 - dt * Psi
   auto advance = [&](const F2 (&curlE)[3], const F2 (&cr)[3], const F2 (&B0)[3], const F2 (&v0)[3], F2 rho,
                      F2 (&Bn)[3], F2 (&vn)[3]) {
 #if !AMX_STRICT
@@ -220,6 +249,7 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
       vn[k] = v0[k] - dt2 * phiB;
     }
   };
+  // running maxima of the squared change norms against (Bp, vp)
   auto change = [&](const F2 (&Bp)[3], const F2 (&vp)[3], const F2 (&Bn)[3], const F2 (&vn)[3], F2& mB, F2& mv) {
     F2 dB = bc2(0.f), dv = bc2(0.f);
 #pragma unroll
@@ -239,7 +269,7 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
     rawX.B0[k] = rawX.v0[k] = rawX.Bk[k] = rawX.vk[k] = rawY.B0[k] = rawY.v0[k] = rawY.Bk[k] = rawY.vk[k] = bc2(0.f);
   rawX.rho = rawY.rho = bc2(1.f);
 
-  // ring slots of planes i-1, i, i+1, i+2 rotate with i: slot(p) = (p - xs + 6) % 3
+  // ring slot of plane p: (p - xs + 6) % 3.
   // sM / sC / sP: slots of planes i-1, i, i+1; plane i+2 shares the slot of plane i-1.
   // At i = xs - 4 these are the slots of planes xs-5, xs-4, xs-3.
   int sM = 1, sC = 2, sP = 0;
@@ -247,43 +277,42 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
   // rawN: plane i+2 (landing); rawC: plane i+1 (argument already published)
   auto step = [&](int i, RawP& rawN, RawP& rawC) {
     // ---- P1(i+2)
-    if (exists) publish_arg(ringA + sM * SLOTA + smA, PLA, rawN.Bk, rawN.vk, rawN.B0, rawN.v0, FIRST);
-    // ---- E1(i+1): ring A planes i (sC), i+1 (sP), i+2 (sM)
-    if (i >= xs - 2) {
-      if (e1) {
-        F2 curlE[3], cr[3], Bn[3], vn[3];
-        psi_ring<PLA, RS>(ringA + sP * SLOTA + smA, ringA + sC * SLOTA + smA, ringA + sM * SLOTA + smA, dpar, curlE, cr);
-        advance(curlE, cr, rawC.B0, rawC.v0, rawC.rho, Bn, vn);
-        publish_arg(ringB + sP * SLOTB + smB, PLB, Bn, vn, rawC.B0, rawC.v0, false);
-        if (e2) {
-          if constexpr (FIRST) change(rawC.B0, rawC.v0, Bn, vn, n1B, n1v);
-          else change(rawC.Bk, rawC.vk, Bn, vn, n1B, n1v);
-          float* st = stash + ((i + 1) & 1) * SS;
+    F2 Bx[3], Ex[3];  // the latest argument of the own pair: x+1 neighbour of the evaluation that follows
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            sts2(st + k * SP, rawC.B0[k]);
-            sts2(st + (3 + k) * SP, rawC.v0[k]);
-            sts2(st + (7 + k) * SP, Bn[k]);
-            sts2(st + (10 + k) * SP, vn[k]);
-          }
-          sts2(st + 6 * SP, rawC.rho);
-        }
+    for (int k = 0; k < 3; ++k) Bx[k] = Ex[k] = bc2(0.f);
+    if (exists) publish_arg(ringA + sM * SLOTA + smA, PLA, rawN.Bk, rawN.vk, rawN.B0, rawN.v0, FIRST, Bx, Ex);
+    // ---- E1(i+1): ring A planes i (sC), i+1 (sP); plane i+2 in (Bx, Ex)
+    if (i >= xs - 2 && e1) {
+      F2 curlE[3], cr[3], Bn[3], vn[3];
+      psi_ring<PLA, RS>(ringA + sP * SLOTA + smA, ringA + sC * SLOTA + smA, Bx, Ex, dpar, curlE, cr);
+      advance(curlE, cr, rawC.B0, rawC.v0, rawC.rho, Bn, vn);
+      publish_arg(ringB + sP * SLOTB + smB, PLB, Bn, vn, rawC.B0, rawC.v0, false, Bx, Ex);
+      if (e2) {
+        if constexpr (FIRST) change(rawC.B0, rawC.v0, Bn, vn, n1B, n1v);
+        else change(rawC.Bk, rawC.vk, Bn, vn, n1B, n1v);
+        float* st = stash + ((i + 1) & 1) * SS;
+        sts4(st, rawC.B0[0], rawC.B0[1]);
+        sts4(st + SP, rawC.B0[2], rawC.v0[0]);
+        sts4(st + 2 * SP, rawC.v0[1], rawC.v0[2]);
+        sts4(st + 3 * SP, rawC.rho, Bn[0]);
+        sts4(st + 4 * SP, Bn[1], Bn[2]);
+        sts4(st + 5 * SP, vn[0], vn[1]);
+        sts4(st + 6 * SP, vn[2], vn[2]);
       }
     }
     if (i + 3 <= xe + 1) issue(i + 3, rawC);
-    // ---- E2(i): ring B planes i-1 (sM), i (sC), i+1 (sP)
+    // ---- E2(i): ring B planes i-1 (sM), i (sC); plane i+1 in (Bx, Ex)
     if (i >= xs && e2) {
       const float* st = stash + (i & 1) * SS;
       F2 B0[3], v0[3], B1[3], v1[3], curlE[3], cr[3], Bn[3], vn[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        B0[k] = lds2(st + k * SP);
-        v0[k] = lds2(st + (3 + k) * SP);
-        B1[k] = lds2(st + (7 + k) * SP);
-        v1[k] = lds2(st + (10 + k) * SP);
-      }
-      const F2 rho = lds2(st + 6 * SP);
-      psi_ring<PLB, RS>(ringB + sC * SLOTB + smB, ringB + sM * SLOTB + smB, ringB + sP * SLOTB + smB, dpar, curlE, cr);
+      const float4 q0 = lds4(st), q1 = lds4(st + SP), q2 = lds4(st + 2 * SP), q3 = lds4(st + 3 * SP),
+                   q4 = lds4(st + 4 * SP), q5 = lds4(st + 5 * SP), q6 = lds4(st + 6 * SP);
+      B0[0] = mk2(q0.x, q0.y); B0[1] = mk2(q0.z, q0.w); B0[2] = mk2(q1.x, q1.y);
+      v0[0] = mk2(q1.z, q1.w); v0[1] = mk2(q2.x, q2.y); v0[2] = mk2(q2.z, q2.w);
+      const F2 rho = mk2(q3.x, q3.y);
+      B1[0] = mk2(q3.z, q3.w); B1[1] = mk2(q4.x, q4.y); B1[2] = mk2(q4.z, q4.w);
+      v1[0] = mk2(q5.x, q5.y); v1[1] = mk2(q5.z, q5.w); v1[2] = mk2(q6.x, q6.y);
+      psi_ring<PLB, RS>(ringB + sC * SLOTB + smB, ringB + sM * SLOTB + smB, Bx, Ex, dpar, curlE, cr);
       advance(curlE, cr, B0, v0, rho, Bn, vn);
       change(B1, v1, Bn, vn, n2B, n2v);
       const long long o = col + (long long)i * sx;
