@@ -93,6 +93,10 @@ PROTOTYPES = {
     "amx_split_sweep": (C.c_int, [_D, _P, _P, C.c_int, _P, C.c_double, _P, _P, _P, _P]),
     "amx_magnetic_iter": (C.c_int, [_D, _P, _P, _P, _P, _P, _P, _P, _P]),
     "amx_magnetic_final": (C.c_int, [_D, _P, _P, _P, _P, _P, _P]),
+    "amx_magnetic_iter_guarded": (C.c_int, [_D, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
+    "amx_magnetic_check": (C.c_int, [_D, _P, C.c_int, _P, _P]),
+    "amx_magnetic_final_guarded": (C.c_int, [_D, _P, _P, _P, _P, _P, _P, _P]),
+    "amx_magnetic_state": (C.c_int, [_D, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

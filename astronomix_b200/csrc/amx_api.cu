@@ -367,6 +367,21 @@ __global__ void mag_check_fused_kernel(Ctl* ctl, double tol, int c0, int nevals,
   }
 }
 
+// the same condition for slab ranks, on norms that were all-reduced across ranks (amx_magnetic_check)
+template <typename T>
+__global__ void mag_check_slab_kernel(Ctl* ctl, const T* change, double tol, int j) {
+  if (j == 0) { ctl->mag_active = 1; ctl->mag_iter = 0; }
+  if (!ctl->mag_active) return;
+  const T m = change[0] > change[1] ? change[0] : change[1];
+  if (m > (T)tol && ctl->mag_iter < 1000) {
+    ctl->mag_iter += 1;
+  } else {
+    ctl->mag_active = 0;
+    ctl->mag_final = j & 1;
+    if (m > (T)tol) ctl->not_converged = 1;
+  }
+}
+
 template <typename T>
 __global__ void set_dt_kernel(Ctl* ctl, const T* dt_dev) {
   ctl->dt_d = (double)*dt_dev;
@@ -1126,6 +1141,68 @@ int amx_magnetic_final(const amx_desc* d, void* gas_inout, const void* bv_final,
   a.alpha_slots = alpha_out ? E.aslots() : nullptr;
   CK(E.strict ? amx_strict::launch_mag_final(a, E.st) : amx_fast::launch_mag_final(a, E.st));
   if (alpha_out) CK(E.finalize_alpha(alpha_out, false));
+  return AMX_OK;
+}
+
+int amx_magnetic_iter_guarded(const amx_desc* d, const void* B0, const void* gas0, const void* bvk_or_null,
+                              void* bvk1, const void* dt_dev, void* change_out, int launch_index, void* ws,
+                              void* stream) {
+  int rc = check_common(d, B0, bvk1);
+  if (rc) return rc;
+  if (!ws || !dt_dev || !gas0 || !change_out) return fail(AMX_EINVAL, "null pointer");
+  if (!d->mhd) return fail(AMX_EINVAL, "descriptor is not MHD");
+  if (launch_index < 0 || (launch_index == 0) != (bvk_or_null == nullptr))
+    return fail(AMX_EINVAL, "launch 0 (and only launch 0) starts from R_0: bvk must be NULL exactly then");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  const View vB0 = E.user_internal(B0), vg = E.user_internal(gas0), vk1 = E.user_internal(bvk1);
+  View vk;
+  if (bvk_or_null) vk = E.user_internal(bvk_or_null);
+  CK(E.mag_iter(vB0, vg, bvk_or_null ? &vk : nullptr, vk1, dt_dev, launch_index, true));
+  CK(E.finalize_change(change_out, false));
+  return AMX_OK;
+}
+
+int amx_magnetic_check(const amx_desc* d, const void* change_dev, int launch_index, void* ws, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!ws || !change_dev || launch_index < 0) return fail(AMX_EINVAL, "null pointer / negative launch index");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  if (E.is32) mag_check_slab_kernel<float><<<1, 1, 0, E.st>>>(E.ctl, (const float*)change_dev, d->fp_tol, launch_index);
+  else mag_check_slab_kernel<double><<<1, 1, 0, E.st>>>(E.ctl, (const double*)change_dev, d->fp_tol, launch_index);
+  CK(cudaGetLastError());
+  return AMX_OK;
+}
+
+int amx_magnetic_final_guarded(const amx_desc* d, void* gas_inout, const void* bv0, const void* bv1, void* B_out,
+                               void* alpha_out, void* ws, void* stream) {
+  int rc = check_common(d, gas_inout, bv0);
+  if (rc) return rc;
+  if (!ws || !B_out || !bv1) return fail(AMX_EINVAL, "null pointer");
+  if (!d->mhd) return fail(AMX_EINVAL, "descriptor is not MHD");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  MagFinalArgs a;
+  a.g = E.g; a.np = E.np; a.gas = E.user_internal(gas_inout); a.B_out = E.user_internal(B_out);
+  a.X[0] = E.user_internal(bv0); a.X[1] = E.user_internal(bv1); a.ctl_ro = E.ctl; a.fixed_final = -1;
+  a.alpha_slots = alpha_out ? E.aslots() : nullptr;
+  CK(E.strict ? amx_strict::launch_mag_final(a, E.st) : amx_fast::launch_mag_final(a, E.st));
+  if (alpha_out) CK(E.finalize_alpha(alpha_out, false));
+  return AMX_OK;
+}
+
+int amx_magnetic_state(const amx_desc* d, void* ws, void* stream, int32_t* active_out, int32_t* iterations_out) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!ws || !active_out || !iterations_out) return fail(AMX_EINVAL, "null pointer");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  Ctl* m;
+  if ((rc = read_ctl(E, &m))) return rc;
+  *active_out = m->mag_active;
+  *iterations_out = m->mag_iter;
+  if (m->not_converged) return fail(AMX_ENOTCONVERGED, "magnetic fixed point hit the 1000-iteration cap");
   return AMX_OK;
 }
 

@@ -270,7 +270,7 @@ AMX_DI T limited_slope(T a, T b, int lim, const Consts<T>& c) {
   }
 }
 
-#if !AMX_STRICT && defined(AMX_MINMOD3)
+#if !AMX_STRICT
 // FAST pairs: minmod(a, b) = median(a, b, 0) = a + b - max3(a, b, 0) - min3(a, b, 0): two 3-input
 // FMNMX3 per cell on the half-rate ALU pipe instead of four FMNMX, the sums as packed adds.  The sum
 // rounds (error <= ulp(a + b)); the exact min / max form stays in the STRICT flavour.

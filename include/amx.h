@@ -174,6 +174,26 @@ AMX_API int amx_magnetic_iter(const amx_desc* d, const void* B0, const void* gas
 AMX_API int amx_magnetic_final(const amx_desc* d, void* gas_inout, const void* bv_final, void* B_out,
                        void* alpha_out, void* ws, void* stream);
 
+/* ---- device-resident fixed-point loop for slab ranks ------------------------------------
+ * The same loop as amx_step's, cut at the points where ranks exchange data, so that the caller
+ * can enqueue a speculative sequence without looking at the norms on the host:
+ *   iter_guarded(0) . all-reduce MAX . check(0) | halo exchange . iter_guarded(1) . all-reduce . check(1) | ...
+ * Launch `launch_index` >= 1 does nothing once the loop has ended; launch L writes iterate
+ * buffer L & 1.  The loop state lives in the control block of `ws`. */
+AMX_API int amx_magnetic_iter_guarded(const amx_desc* d, const void* B0, const void* gas0,
+                      const void* bvk_or_null, void* bvk1, const void* dt_dev, void* change_out,
+                      int launch_index, void* ws, void* stream);
+/* _magnetic_field_update.py:127-141 while-condition on the ALL-REDUCED norms (device, 2 values of
+ * desc->dtype) after launch `launch_index`; updates the loop state. */
+AMX_API int amx_magnetic_check(const amx_desc* d, const void* change_dev, int launch_index, void* ws,
+                      void* stream);
+/* amx_magnetic_final reading the converged iterate from whichever of bv0 / bv1 the loop ended in */
+AMX_API int amx_magnetic_final_guarded(const amx_desc* d, void* gas_inout, const void* bv0, const void* bv1,
+                      void* B_out, void* alpha_out, void* ws, void* stream);
+/* host look at the loop state (synchronises `stream`): still iterating?, while-body iterations so far */
+AMX_API int amx_magnetic_state(const amx_desc* d, void* ws, void* stream, int32_t* active_out,
+                      int32_t* iterations_out);
+
 #ifdef __cplusplus
 }
 #endif

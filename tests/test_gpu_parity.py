@@ -259,14 +259,21 @@ def test_slab_driver_single_gpu_equals_integrate_bitwise(cuda, dim, n, mhd, spli
     kw = dict(split=oc.SPLIT, time_integrator=oc.MUSCL) if split else {}
     s = pr.smooth_random(dim, n, mhd=mhd, seed=41, dtype=np.float32)
     config, params, rv = pr.make(dim, n, mhd=mhd, riemann_solver=oc.HLLC if not mhd else oc.HLL, **kw)
-    ref = ti.integrate_steps(s, config, params, rv, 4)
-    iters = ti.last_info.magnetic_iterations
-    drv = SlabDriver(config, params, rv, (n,) * dim, torch.float32, cuda)
-    drv.scatter(torch.from_numpy(s))
-    info = drv.run(max_steps=4)
-    out = drv.gather().cpu().numpy()
-    assert info.steps == 4 and info.magnetic_iterations == iters
-    assert np.array_equal(out, ref)
+    # STRICT arithmetic: every kernel family follows one operation order, so the slab driver (one
+    # evaluation per launch) and amx_integrate (pair launches where supported) agree to the bit;
+    # FAST lets the compiler contract each kernel's expressions its own way: agreement to round-off
+    for arith, exact in ((_lib.AMX_ARITH_STRICT, True), (_lib.AMX_ARITH_FAST, False)):
+        ref = ti.integrate_steps(s, config, params, rv, 4, arithmetic=arith)
+        iters = ti.last_info.magnetic_iterations
+        drv = SlabDriver(config, params, rv, (n,) * dim, torch.float32, cuda, arithmetic=arith)
+        drv.scatter(torch.from_numpy(s))
+        info = drv.run(max_steps=4)
+        out = drv.gather().cpu().numpy()
+        assert info.steps == 4 and info.magnetic_iterations == iters
+        if exact:
+            assert np.array_equal(out, ref)
+        else:
+            assert pr.rel_l1(out, ref, dim, mhd) < 1e-6
 
 
 def test_slab_driver_lax_friedrichs(cuda):

@@ -86,6 +86,32 @@ class OracleBackend:
         bvk1[:3, NG:-NG] = torch.from_numpy(B1[inner].copy())
         bvk1[3:, NG:-NG] = torch.from_numpy(v1[inner].copy())
 
+    # device-resident loop state of libamx (Ctl), restated on the host
+    def magnetic_iter_guarded(self, B0, gas0, bvk, bvk1, dt, change_out, launch_index):
+        assert (launch_index == 0) == (bvk is None)
+        if launch_index == 0:
+            self.active, self.iters, self.final = True, 0, 0
+        if launch_index > 0 and not self.active:
+            change_out.zero_()  # a skipped launch leaves zeroed slots behind
+            return
+        self.magnetic_iter(B0, gas0, bvk, bvk1, dt, change_out)
+
+    def magnetic_check(self, change, launch_index):
+        if not self.active:
+            return
+        tol = 1e-5 if self.o.numerical_precision == fo.SINGLE_PRECISION else 1e-10
+        m = self.t(max(change[0].item(), change[1].item()))
+        if m > self.t(tol) and self.iters < 1000:
+            self.iters += 1
+        else:
+            self.active, self.final = False, launch_index & 1
+
+    def magnetic_state(self):
+        return self.active, self.iters
+
+    def magnetic_final_guarded(self, gas, bv0, bv1, B_out, alpha_out):
+        self.magnetic_final(gas, (bv0, bv1)[self.final], B_out, alpha_out)
+
     def magnetic_final(self, gas, bv_final, B_out, alpha_out):
         o, t = self.o, self.t
         g, X = self._np(gas), self._np(bv_final)

@@ -1,4 +1,5 @@
-"""torchrun --nproc-per-node N tools/slab_check.py : N-GPU slab run == 1-GPU amx_integrate, bitwise."""
+"""torchrun --nproc-per-node N tools/slab_check.py : N-GPU slab run == 1-GPU amx_integrate, bitwise
+(STRICT arithmetic: one operation order in every kernel family)."""
 import os
 import sys
 
@@ -7,6 +8,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from astronomix_b200 import _lib
 from astronomix_b200 import option_classes as oc
 from astronomix_b200 import problems as pr
 from astronomix_b200 import stepping as ti
@@ -22,12 +24,12 @@ for dim, n, mhd, rs, steps in [(3, 64, True, oc.HLL, 6), (2, 512, True, oc.HLL, 
                                (3, 64, True, oc.LAX_FRIEDRICHS, 4)]:
     s = pr.smooth_random(dim, n, mhd=mhd, seed=3, dtype=np.float32)
     config, params, rv = pr.make(dim, n, mhd=mhd, riemann_solver=rs)
-    drv = SlabDriver(config, params, rv, (n,) * dim, torch.float32, dev)
+    drv = SlabDriver(config, params, rv, (n,) * dim, torch.float32, dev, arithmetic=_lib.AMX_ARITH_STRICT)
     drv.scatter(torch.from_numpy(s))
     info = drv.run(max_steps=steps)
     out = drv.gather().cpu().numpy()
     if rank == 0:
-        ref = ti.integrate_steps(s, config, params, rv, steps)
+        ref = ti.integrate_steps(s, config, params, rv, steps, arithmetic=_lib.AMX_ARITH_STRICT)
         same = np.array_equal(out, ref)
         ok &= same and info.magnetic_iterations == ti.last_info.magnetic_iterations
         print(f"dim={dim} n={n} mhd={mhd} rs={rs}: {dist.get_world_size()}-GPU slab == 1-GPU bitwise: {same}; "
