@@ -152,7 +152,38 @@ class SlabDriver:
         self.backend = backend if backend is not None else AmxBackend(config, params, self.local_n, dtype, device,
                                                                      arithmetic)
         shape = (self.nxl + 2 * NG,) + self.global_n[1:]
-        z = lambda rows: torch.zeros((rows,) + shape, dtype=dtype, device=device)  # noqa: E731
+        import os
+        # Peer-to-peer halo exchange: the slab arrays live in symmetric memory (every rank maps its
+        # neighbours' buffers over NVLink), a rank stores its edge planes straight into the
+        # neighbours' ghost planes and one device-side barrier closes the exchange.  No staging
+        # copies, no NCCL launch; AMX_SLAB_P2P=0 (or a failed rendezvous) keeps NCCL send/recv.
+        self._symm = []  # (base tensor, handle)
+        self._peer_views = {}
+        self.p2p = (self.world > 1 and torch.device(device).type == "cuda"
+                    and os.environ.get("AMX_SLAB_P2P", "1") != "0")
+        if self.p2p:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self._symm_mem = symm_mem
+                self._symm_group = group if group is not None else dist.group.WORLD
+            except Exception as e:  # pragma: no cover - depends on the torch build
+                print(f"[slab] symmetric memory unavailable ({e!r}); NCCL send/recv halo exchange", flush=True)
+                self.p2p = False
+
+        def z(rows):
+            if self.p2p:
+                try:
+                    t = self._symm_mem.empty((rows,) + shape, dtype=dtype, device=device)
+                    t.zero_()
+                    h = self._symm_mem.rendezvous(t, self._symm_group)
+                    self._symm.append((t, h))
+                    return t
+                except Exception as e:  # pragma: no cover
+                    print(f"[slab] symmetric-memory rendezvous failed ({e!r}); NCCL send/recv halo exchange",
+                          flush=True)
+                    self.p2p = False
+            return torch.zeros((rows,) + shape, dtype=dtype, device=device)
+
         self.S = [z(self.nv), z(self.nv)]
         self.A, self.G = z(self.ng), z(self.ng)
         self.X = [z(6), z(6)] if self.mhd else None
@@ -163,6 +194,9 @@ class SlabDriver:
         self.collectives = 0
         self._halo = {}
         self.expect_evals = 3 if dtype == torch.float32 else 7  # fixed-point evaluations expected per step
+        import os
+        # AMX_SLAB_PACK=0: per-row messages without staging copies (A/B switch, see exchange)
+        self.pack_halos = os.environ.get("AMX_SLAB_PACK", "1") != "0"
 
     # ------------------------------------------------------------------ communication
     def _halo_buffers(self, t):
@@ -172,6 +206,37 @@ class SlabDriver:
             shape = (t.shape[0], NG) + tuple(t.shape[2:])
             self._halo[key] = [torch.empty(shape, dtype=t.dtype, device=t.device) for _ in range(4)]
         return self._halo[key]
+
+    def _exchange_p2p(self, t, left, right, send_l, send_r):
+        """Store this rank's edge planes of ``t`` (a row slice of a symmetric-memory array) into the
+        neighbours' ghost planes and close with a barrier over the group.  Write-after-read on the
+        ghost planes is safe without a leading barrier: between a kernel that reads an array's
+        ghosts and the next exchange of that array there is always another exchange or all-reduce,
+        which the writer cannot pass before the reader has reached it."""
+        n = self.nxl
+        for base, h in self._symm:
+            off = t.data_ptr() - base.data_ptr()
+            if 0 <= off < base.numel() * base.element_size():
+                break
+        else:
+            return False
+        row_bytes = base[0].numel() * base.element_size()
+        r0 = off // row_bytes
+        rows = t.shape[0]
+
+        def peer(rank):
+            key = (base.data_ptr(), rank)
+            if key not in self._peer_views:
+                self._peer_views[key] = h.get_buffer(rank, tuple(base.shape), base.dtype)
+            return self._peer_views[key][r0:r0 + rows]
+
+        if send_l:   # my first active planes are the left neighbour's right ghost planes
+            peer(left)[:, n + NG:].copy_(t[:, NG:2 * NG])
+        if send_r:   # my last active planes are the right neighbour's left ghost planes
+            peer(right)[:, :NG].copy_(t[:, n:n + NG])
+        h.barrier(channel=0)
+        self.collectives += 1
+        return True
 
     def _allreduce_max(self, t):
         if self.world > 1:
@@ -193,12 +258,33 @@ class SlabDriver:
         else:
             send_l = periodic or not at_left
             send_r = periodic or not at_right
+            if self.p2p and self._exchange_p2p(t, left, right, send_l, send_r):
+                send_l = send_r = False  # done
             # one packed buffer per direction (a single strided copy each) instead of one message
             # per row: 4 NCCL point-to-point operations per exchange, grouped into one launch.
             # The k-th send to a peer pairs with the k-th receive from it (with 2 ranks both
             # neighbours are the same peer): sends are posted as (to left, to right), receives as
             # (from right, from left).
-            buf = self._halo_buffers(t)
+            ops = []
+            if not self.pack_halos:
+                # one message per row straight from / into the strided array (each row's two planes
+                # are contiguous): no staging copies on the device, 4 x rows operations in the group
+                for r in range(t.shape[0]):
+                    if send_l:
+                        ops.append(dist.P2POp(dist.isend, t[r, NG:2 * NG], left, self.group))
+                    if send_r:
+                        ops.append(dist.P2POp(dist.isend, t[r, n:n + NG], right, self.group))
+                for r in range(t.shape[0]):
+                    if send_r:
+                        ops.append(dist.P2POp(dist.irecv, t[r, n + NG:], right, self.group))
+                    if send_l:
+                        ops.append(dist.P2POp(dist.irecv, t[r, :NG], left, self.group))
+                if ops:
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                    self.collectives += 1
+                send_l = send_r = False  # nothing staged
+            buf = self._halo_buffers(t) if (send_l or send_r) else None
             ops = []
             if send_l:
                 buf[0].copy_(t[:, NG:2 * NG])
