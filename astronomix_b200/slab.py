@@ -524,5 +524,7 @@ def bench_weak(n, K, W, device):
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"}
     return {"ms": ms, "e2e_ms": e2e_ms, "h2d_bytes": local.nbytes, "d2h_bytes": local.nbytes, "launches": launches,
             "clocks": clocks, "roofline": roofline, "kernels": {}, "mag_iters": iters,
-            "config": {"collectives_per_step": colls / K, "halo": "2 planes per side per exchange, NCCL send/recv",
+            "config": {"collectives_per_step": colls / K, "halo": "2 planes per side per exchange, " + (
+                           "edge planes stored into the neighbours' ghost planes over NVLink (symmetric memory) "
+                           "+ device-side barrier" if drv.p2p else "NCCL send/recv (packed)"),
                        "reductions": "NCCL all-reduce MAX of 3 (dt) + 2 (fixed point) scalars"}}
