@@ -43,8 +43,11 @@ struct Raw {
 };
 
 // MODE 0: first iterate (R_k = R_0, Bk / vk absent); 1: implicit midpoint; 2: implicit Euler
+#ifndef AMX_MAG_MINB8
+#define AMX_MAG_MINB8 1  // blocks per SM of the 8-compute-warp flavour (AMX_VEC_CW=8)
+#endif
 template <int ND, int MODE, int LD, int CW>
-__global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : 1) mag_iter_vec(const MagIterArgs a, const int xchunk) {
+__global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : AMX_MAG_MINB8) mag_iter_vec(const MagIterArgs a, const int xchunk) {
   if (a.ctl_ro) {
     if (a.ctl_ro->done) return;
     if (a.fix_base >= 0) {
@@ -434,7 +437,7 @@ cudaError_t launch_mag(const MagIterArgs& a, cudaStream_t st) {
   grid.x = (a.g.n[LA] + TZ - 1) / TZ;
   const int ytiles = ND == 3 ? (a.g.n[1] + TY - 1) / TY : 1;
   const long long tiles = (long long)grid.x * ytiles;
-  const int nch = pick_chunks(a.g.n[0], tiles, CW == 7 ? 2 : 1, 3);
+  const int nch = pick_chunks(a.g.n[0], tiles, CW == 7 ? 2 : AMX_MAG_MINB8, 3);
   const int xchunk = (a.g.n[0] + nch - 1) / nch;
   const int nchunks = (a.g.n[0] + xchunk - 1) / xchunk;
   if (ND == 3) { grid.y = ytiles; grid.z = nchunks; }
@@ -500,7 +503,13 @@ AMX_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memor
 template <int N>
 AMX_DI void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kHydroCW = 7;  // compute warps (+ 1 halo warp = 256 threads, 2 blocks per SM)
+#ifndef AMX_HYDRO_CW
+#define AMX_HYDRO_CW 7
+#endif
+#ifndef AMX_HYDRO_MINB
+#define AMX_HYDRO_MINB 2
+#endif
+constexpr int kHydroCW = AMX_HYDRO_CW;  // compute warps (+ 1 halo warp); AMX_HYDRO_MINB blocks per SM
 
 template <int ND>
 struct HG {
@@ -517,7 +526,7 @@ struct HG {
 };
 
 template <int ND, int RS, int LIM, bool COMBINE>
-__global__ void __launch_bounds__(32 * kHydroCW + 32, 2) hydro_stage_vec(const StageArgs a, const int xchunk) {
+__global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stage_vec(const StageArgs a, const int xchunk) {
   if (a.ctl_ro && a.ctl_ro->done) return;
   using G = HG<ND>;
   constexpr int NV = G::NV, TY = G::TY, TQ = G::TQ, TZ = G::TZ, YO = G::YO, RSW = G::RSW, PLW = G::PLW;
@@ -940,7 +949,7 @@ cudaError_t launch_stage_vec(const StageArgs& a, cudaStream_t st) {
   const int LA = ND - 1;
   grid.x = (a.g.n[LA] + G::TZ - 1) / G::TZ;
   const int ytiles = ND == 3 ? (a.g.n[1] + G::TY - 1) / G::TY : 1;
-  const int nch = pick_chunks(a.g.n[0], (long long)grid.x * ytiles, 2, 4);
+  const int nch = pick_chunks(a.g.n[0], (long long)grid.x * ytiles, AMX_HYDRO_MINB, 4);
   const int xchunk = (a.g.n[0] + nch - 1) / nch;
   const int nchunks = (a.g.n[0] + xchunk - 1) / xchunk;
   if (ND == 3) { grid.y = ytiles; grid.z = nchunks; }
