@@ -124,7 +124,7 @@ AMX_DI void psi_ring(const float* w, const float* wm, const F2 (&Bp)[3], const F
 // FIRST: evaluation 1 starts from R_k = R_0 (launch 0 of the fixed point).  MID: implicit midpoint
 // (argument (R + R_0)/2) or implicit Euler (argument R).
 template <bool FIRST, bool MID, int TY, int LD>
-__global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIterArgs a, const int xchunk) {
+__global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf) {
   if (a.ctl_ro && (a.ctl_ro->done || (!a.first && !a.ctl_ro->mag_active))) return;
   using G = PG<TY>;
   constexpr int RS = G::RS, PLA = G::PLA, PLB = G::PLB, SLOTA = G::SLOTA, SLOTB = G::SLOTB;
@@ -193,8 +193,28 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
     if (xwrap) p += p < 0 ? g.n[0] : (p >= g.n[0] ? -g.n[0] : 0);
     return col + (long long)p * sx;
   };
+  // One block per SM and one barrier per plane leave nothing to overlap a DRAM miss with: the
+  // lines of plane p + pf are pulled into L2 while plane p is loaded into registers (one lane per
+  // 128-byte line asks; the side warp's pairs each sit in a line of their own).
+  const bool pf_lane = exists && (wid >= TY + 4 || (lane & 15) == 0);
   auto issue = [&](int p, RawP& r) {
     if (!exists) return;
+    if (pf > 0 && pf_lane && p + pf <= xe + 1) {
+      const long long q = plane_off(p + pf);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(fB0 + q + k * vB0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(fG + q + (k + 1) * vG));
+      }
+      if (need_rho) asm volatile("prefetch.global.L2 [%0];" ::"l"(fG + q));
+      if constexpr (!FIRST) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fBk + q + k * vBk));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fvk + q + k * vvk));
+        }
+      }
+    }
     const long long o = plane_off(p);
     const float* pb = fB0 + o;
     const float* pg = fG + o;
@@ -371,7 +391,8 @@ cudaError_t launch_pair_ld(const MagIterArgs& a, cudaStream_t st) {
   const int nch = pick_chunks(a.g.n[0], (long long)grid.x * grid.y, 1, 3);
   const int xchunk = (a.g.n[0] + nch - 1) / nch;
   grid.z = (a.g.n[0] + xchunk - 1) / xchunk;
-  kern<<<grid, G::kThreads, G::smem_bytes, st>>>(a, xchunk);
+  static const int pf = [] { const char* e = getenv("AMX_PAIR_PF"); return e ? atoi(e) : 2; }();
+  kern<<<grid, G::kThreads, G::smem_bytes, st>>>(a, xchunk, pf);
   return cudaGetLastError();
 }
 
