@@ -370,7 +370,7 @@ __global__ void mag_check_fused_kernel(Ctl* ctl, double tol, int c0, int nevals,
 // the same condition for slab ranks, on norms that were all-reduced across ranks (amx_magnetic_check)
 template <typename T>
 __global__ void mag_check_slab_kernel(Ctl* ctl, const T* change, double tol, int j) {
-  if (j == 0) { ctl->mag_active = 1; ctl->mag_iter = 0; }
+  if (j == 0) { ctl->mag_active = 1; ctl->mag_iter = 0; ctl->mag_fix = 0; }
   if (!ctl->mag_active) return;
   const T m = change[0] > change[1] ? change[0] : change[1];
   if (m > (T)tol && ctl->mag_iter < 1000) {
@@ -379,6 +379,31 @@ __global__ void mag_check_slab_kernel(Ctl* ctl, const T* change, double tol, int
     ctl->mag_active = 0;
     ctl->mag_final = j & 1;
     if (m > (T)tol) ctl->not_converged = 1;
+  }
+}
+
+// pair launches of slab ranks: the condition after each of the two evaluations, on all-reduced norms
+template <typename T>
+__global__ void mag_check_pair_slab_kernel(Ctl* ctl, const T* n, double tol, int c0, int nb) {
+  if (c0 == 0) { ctl->mag_active = 1; ctl->mag_iter = 0; ctl->mag_fix = 0; }
+  if (!ctl->mag_active) return;
+  const T m1 = n[0] > n[1] ? n[0] : n[1];
+  if (!(m1 > (T)tol && ctl->mag_iter < 1000)) {
+    ctl->mag_active = 0;
+    ctl->mag_final = nb;
+    if (m1 > (T)tol) ctl->not_converged = 1;
+    ctl->mag_fix = 1;
+    ctl->mag_fix_base = c0;
+    return;
+  }
+  ctl->mag_iter += 1;
+  const T m2 = n[2] > n[3] ? n[2] : n[3];
+  if (m2 > (T)tol && ctl->mag_iter < 1000) {
+    ctl->mag_iter += 1;
+  } else {
+    ctl->mag_active = 0;
+    ctl->mag_final = nb;
+    if (m2 > (T)tol) ctl->not_converged = 1;
   }
 }
 
@@ -603,6 +628,14 @@ struct Engine {
     const Ctl* c = guarded ? ctl : nullptr;
     if (is32) finalize_slots_kernel<float, 2><<<1, 256, 0, st>>>(cslots(), ctl->change, nullptr, (float*)change_t_out, c);
     else finalize_slots_kernel<double, 2><<<1, 256, 0, st>>>(cslots(), ctl->change, nullptr, (double*)change_t_out, c);
+    return cudaGetLastError();
+  }
+
+  cudaError_t finalize_change2(void* change_t_out) {
+    ++launches;
+    unsigned long long* s2 = &ctl->change2_slots[0][0];
+    if (is32) finalize_slots_kernel<float, 2><<<1, 256, 0, st>>>(s2, ctl->change, nullptr, (float*)change_t_out, nullptr);
+    else finalize_slots_kernel<double, 2><<<1, 256, 0, st>>>(s2, ctl->change, nullptr, (double*)change_t_out, nullptr);
     return cudaGetLastError();
   }
 
@@ -1189,6 +1222,75 @@ int amx_magnetic_final_guarded(const amx_desc* d, void* gas_inout, const void* b
   a.alpha_slots = alpha_out ? E.aslots() : nullptr;
   CK(E.strict ? amx_strict::launch_mag_final(a, E.st) : amx_fast::launch_mag_final(a, E.st));
   if (alpha_out) CK(E.finalize_alpha(alpha_out, false));
+  return AMX_OK;
+}
+
+int amx_magnetic_pair_supported(const amx_desc* d) {
+  if (validate(d) || !d->mhd || d->dtype != AMX_F32 || d->ndim != 3) return 0;
+  Engine E(d, nullptr, nullptr);
+  MagIterArgs a;
+  a.g = E.g; a.np = E.np;
+  // layout rules are those of the internal slab layout: dense, even extents; probe with aligned dummies
+  int pad[3];
+  internal_pad(d, pad);
+  const View v = make_view(reinterpret_cast<void*>(uintptr_t(256)), d, pad, 0, 0);
+  a.B0 = a.gas0 = a.Bk = a.vk = a.Bk1 = a.vk1 = v;
+  a.ctl_ro = nullptr; a.first = 0; a.midpoint = 1; a.dt = nullptr;
+  a.change_slots = a.change_slots2 = reinterpret_cast<unsigned long long*>(uintptr_t(256));
+  a.fix_base = -1;
+  return E.pair_supported(a) ? 1 : 0;
+}
+
+int amx_magnetic_pair_guarded(const amx_desc* d, const void* B0, const void* gas0, const void* bvk_or_null,
+                              void* bvk2, const void* dt_dev, void* change4_out, int evals_before, void* ws,
+                              void* stream) {
+  int rc = check_common(d, B0, bvk2);
+  if (rc) return rc;
+  if (!ws || !dt_dev || !gas0 || !change4_out) return fail(AMX_EINVAL, "null pointer");
+  if (!d->mhd) return fail(AMX_EINVAL, "descriptor is not MHD");
+  if (evals_before < 0 || (evals_before == 0) != (bvk_or_null == nullptr))
+    return fail(AMX_EINVAL, "the first pair (and only the first) starts from R_0: bvk must be NULL exactly then");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  const View vB0 = E.user_internal(B0), vg = E.user_internal(gas0), vk2 = E.user_internal(bvk2);
+  View vk;
+  if (bvk_or_null) vk = E.user_internal(bvk_or_null);
+  if (!E.pair_supported(E.mag_args(vB0, vg, bvk_or_null ? &vk : nullptr, vk2, dt_dev, evals_before, true)))
+    return fail(AMX_EUNSUPPORTED, "pair launches need 3-D fp32 with periodic y / z and halo or periodic x");
+  CK(E.mag_pair(vB0, vg, bvk_or_null ? &vk : nullptr, vk2, dt_dev, evals_before));
+  const size_t esz = E.L.esz;
+  CK(E.finalize_change(change4_out, false));
+  CK(E.finalize_change2(static_cast<char*>(change4_out) + 2 * esz));
+  return AMX_OK;
+}
+
+int amx_magnetic_check_pair(const amx_desc* d, const void* change4_dev, int evals_before, int buffer_index,
+                            void* ws, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!ws || !change4_dev || evals_before < 0 || buffer_index < 0 || buffer_index > 1)
+    return fail(AMX_EINVAL, "null pointer / bad index");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  if (E.is32) mag_check_pair_slab_kernel<float><<<1, 1, 0, E.st>>>(E.ctl, (const float*)change4_dev, d->fp_tol, evals_before, buffer_index);
+  else mag_check_pair_slab_kernel<double><<<1, 1, 0, E.st>>>(E.ctl, (const double*)change4_dev, d->fp_tol, evals_before, buffer_index);
+  CK(cudaGetLastError());
+  return AMX_OK;
+}
+
+int amx_magnetic_fix_guarded(const amx_desc* d, const void* B0, const void* gas0, const void* bvk_or_null,
+                             void* bvk1, const void* dt_dev, int evals_before, void* ws, void* stream) {
+  int rc = check_common(d, B0, bvk1);
+  if (rc) return rc;
+  if (!ws || !dt_dev || !gas0) return fail(AMX_EINVAL, "null pointer");
+  if (evals_before < 0 || (evals_before == 0) != (bvk_or_null == nullptr))
+    return fail(AMX_EINVAL, "bvk must be NULL exactly when evals_before == 0");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  const View vB0 = E.user_internal(B0), vg = E.user_internal(gas0), vk1 = E.user_internal(bvk1);
+  View vk;
+  if (bvk_or_null) vk = E.user_internal(bvk_or_null);
+  CK(E.mag_fix(vB0, vg, bvk_or_null ? &vk : nullptr, vk1, dt_dev, evals_before));
   return AMX_OK;
 }
 

@@ -106,6 +106,26 @@ class AmxBackend:
                                                        self._p(B_out), self._p(alpha_out), self.ws_ptr, self._s()))
         self.launches += 2 if alpha_out is not None else 1
 
+    def pair_supported(self):
+        return bool(self.lib.amx_magnetic_pair_supported(C.byref(self.desc)))
+
+    def magnetic_pair_guarded(self, B0, gas0, bvk, bvk2, dt, change4_out, evals_before):
+        _lib.check(self.lib.amx_magnetic_pair_guarded(C.byref(self.desc), self._p(B0), self._p(gas0), self._p(bvk),
+                                                      self._p(bvk2), self._p(dt), self._p(change4_out),
+                                                      int(evals_before), self.ws_ptr, self._s()))
+        self.launches += 3
+
+    def magnetic_check_pair(self, change4, evals_before, buffer_index):
+        _lib.check(self.lib.amx_magnetic_check_pair(C.byref(self.desc), self._p(change4), int(evals_before),
+                                                    int(buffer_index), self.ws_ptr, self._s()))
+        self.launches += 1
+
+    def magnetic_fix_guarded(self, B0, gas0, bvk, bvk1, dt, evals_before):
+        _lib.check(self.lib.amx_magnetic_fix_guarded(C.byref(self.desc), self._p(B0), self._p(gas0), self._p(bvk),
+                                                     self._p(bvk1), self._p(dt), int(evals_before), self.ws_ptr,
+                                                     self._s()))
+        self.launches += 1
+
     def magnetic_state(self):
         """(still iterating, while-body iterations so far); synchronises the stream"""
         active, iters = C.c_int32(), C.c_int32()
@@ -189,6 +209,7 @@ class SlabDriver:
         self.X = [z(6), z(6)] if self.mhd else None
         self.alpha = torch.zeros(3, dtype=dtype, device=device)
         self.change = torch.zeros(2, dtype=dtype, device=device)
+        self.change4 = torch.zeros(4, dtype=dtype, device=device)
         self.dt = torch.zeros((), dtype=dtype, device=device)
         self.time = torch.zeros((), dtype=dtype, device=device)
         self.collectives = 0
@@ -197,6 +218,10 @@ class SlabDriver:
         import os
         # AMX_SLAB_PACK=0: per-row messages without staging copies (A/B switch, see exchange)
         self.pack_halos = os.environ.get("AMX_SLAB_PACK", "1") != "0"
+        # two fixed-point evaluations per launch where the kernel supports the problem (AMX_SLAB_PAIRS=0: off)
+        self.pair_greedy = False  # tests: pair launches regardless of the expected count (exercises the re-run)
+        self.pairs = (self.mhd and os.environ.get("AMX_SLAB_PAIRS", "1") != "0"
+                      and bool(getattr(self.backend, "pair_supported", lambda: False)()))
 
     # ------------------------------------------------------------------ communication
     def _halo_buffers(self, t):
@@ -392,24 +417,38 @@ class SlabDriver:
         # Q12: on a reflective x boundary the reference flips component 1 (y) of 3-vectors
         self.exchange(B0, flip_rows=(1,))
         self.exchange(gas, flip_rows=(2,))
-        nl = 0
+        nl, c = 0, 0  # launches / evaluations enqueued; launch L writes iterate buffer X[L & 1]
 
-        def launch():
-            nonlocal nl
+        def launch(pair):
+            nonlocal nl, c
             src = None if nl == 0 else self.X[(nl - 1) & 1]
+            dst = self.X[nl & 1]
             if src is not None:
                 self.exchange(src, flip_rows=(1, 4))
-            b.magnetic_iter_guarded(B0, gas, src, self.X[nl & 1], self.dt, self.change, nl)
-            self._allreduce_max(self.change)
-            b.magnetic_check(self.change, nl)
+            if pair:
+                # two evaluations, the intermediate iterate stays on chip (amx_pair.cu); if the loop
+                # ends on the first of them, that one is re-run alone into the same buffer
+                b.magnetic_pair_guarded(B0, gas, src, dst, self.dt, self.change4, c)
+                self._allreduce_max(self.change4)
+                b.magnetic_check_pair(self.change4, c, nl & 1)
+                b.magnetic_fix_guarded(B0, gas, src, dst, self.dt, c)
+                c += 2
+            else:
+                b.magnetic_iter_guarded(B0, gas, src, dst, self.dt, self.change, nl)
+                self._allreduce_max(self.change)
+                b.magnetic_check(self.change, nl)
+                c += 1
             nl += 1
 
-        for _ in range(self.expect_evals + 1):
-            launch()
+        pairs = self.pairs
+        while c < self.expect_evals:
+            launch(pairs and (self.expect_evals - c >= 2 or self.pair_greedy))
+        launch(pairs)  # slack
         active, it = b.magnetic_state()
         while active:
-            launch()
-            launch()
+            launch(pairs)
+            if not pairs:
+                launch(False)
             active, it = b.magnetic_state()
         self.expect_evals = it + 1
         b.magnetic_final_guarded(gas, self.X[0], self.X[1], B_out, self.alpha if self.lf else None)

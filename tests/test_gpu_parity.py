@@ -276,6 +276,24 @@ def test_slab_driver_single_gpu_equals_integrate_bitwise(cuda, dim, n, mhd, spli
             assert pr.rel_l1(out, ref, dim, mhd) < 1e-6
 
 
+def test_slab_driver_pair_rerun_path(cuda):
+    """Slab driver with pair launches forced (pair_greedy): steps whose evaluation count is odd end on
+    the first half of a pair and take the device-side re-run; bitwise equal to amx_integrate (STRICT)."""
+    import torch
+    from astronomix_b200.slab import SlabDriver
+    s = pr.smooth_random(3, 40, mhd=True, seed=43, dtype=np.float32)
+    config, params, rv = pr.make(3, 40, mhd=True)
+    ref = ti.integrate_steps(s, config, params, rv, 5, arithmetic=_lib.AMX_ARITH_STRICT)
+    iters = ti.last_info.magnetic_iterations
+    drv = SlabDriver(config, params, rv, (40,) * 3, torch.float32, cuda, arithmetic=_lib.AMX_ARITH_STRICT)
+    assert drv.pairs
+    drv.pair_greedy = True
+    drv.scatter(torch.from_numpy(s))
+    info = drv.run(max_steps=5)
+    assert info.steps == 5 and info.magnetic_iterations == iters
+    assert np.array_equal(drv.gather().cpu().numpy(), ref)
+
+
 def test_slab_driver_lax_friedrichs(cuda):
     import torch
     from astronomix_b200.slab import SlabDriver
