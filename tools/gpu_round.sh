@@ -13,7 +13,7 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_be
 cat $O/${TAG}_bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu > $O/${TAG}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'hydro_stage_vec|mag_iter_vec|mag_final' -s 8 -c 6 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'hydro_stage_vec|mag_pair_vec|mag_final' -s 8 -c 5 \
   -f -o $O/${TAG}_full python bench.py --steps 2 --warmup 1 --no-cpu > $O/${TAG}_ncu_full.log 2>&1
 tail -2 $O/${TAG}_ncu_full.log
 ls -la $O
