@@ -62,6 +62,7 @@ class AmxStats(C.Structure):
         ("kernel_launches", C.c_int64),
         ("pair_launches", C.c_int64),
         ("single_launches", C.c_int64),
+        ("final_launches", C.c_int64),
     ]
 
 

@@ -84,7 +84,7 @@ struct Layout {
   size_t esz;              // element size
   size_t row_bytes;        // cells * esz rounded up to 256
   // byte offsets into ws
-  size_t off_ctl, off_S[2], off_A, off_G, off_X[2], total;
+  size_t off_ctl, off_S[2], off_A, off_G, off_Gf, off_X[2], total;
 };
 
 size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
@@ -150,6 +150,7 @@ Layout make_layout(const amx_desc* d) {
   for (int k = 0; k < 2; ++k) { L.off_S[k] = off; off += L.row_bytes * L.nv; }
   L.off_A = off; off += L.row_bytes * L.ng;
   L.off_G = off; off += L.row_bytes * L.ng;
+  L.off_Gf = off; off += d->mhd ? L.row_bytes * L.ng : 0;  // gas after the magnetic write-back
   for (int k = 0; k < 2; ++k) { L.off_X[k] = off; off += d->mhd ? L.row_bytes * 6 : 0; }
   L.total = off;
   return L;
@@ -292,6 +293,7 @@ __global__ void step_begin_kernel(Ctl* ctl, DtPar p, long long max_steps) {
   ctl->mag_active = 1;
   ctl->mag_iter = 0;
   ctl->mag_fix = 0;
+  ctl->final_emitted = 0;
 }
 
 template <typename T>
@@ -321,7 +323,7 @@ __global__ void dt_only_kernel(const T* alpha_t, const T* time_t, DtPar p, T* dt
 // reference does.  A pair whose first evaluation already ends the loop leaves R_{k+2} in the
 // buffer: mag_fix asks for that one evaluation to be re-run alone into the same buffer.
 template <typename T>
-__global__ void mag_check_fused_kernel(Ctl* ctl, double tol, int c0, int nevals, int nb) {
+__global__ void mag_check_fused_kernel(Ctl* ctl, double tol, int c0, int nevals, int nb, int emit) {
   if (ctl->done || !ctl->mag_active) return;  // the launch before this one exited without touching the slots
   __shared__ T red[4][8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -363,6 +365,7 @@ __global__ void mag_check_fused_kernel(Ctl* ctl, double tol, int c0, int nevals,
       ctl->mag_active = 0;
       ctl->mag_final = nb;
       if (m2 > (T)tol) ctl->not_converged = 1;
+      ctl->final_emitted = emit;  // the launch also wrote the write-back of exactly this iterate
     }
   }
 }
@@ -415,6 +418,7 @@ __global__ void set_dt_kernel(Ctl* ctl, const T* dt_dev) {
   ctl->mag_active = 1;
   ctl->mag_iter = 0;
   ctl->mag_fix = 0;
+  ctl->final_emitted = 0;
 }
 
 // ---------------------------------------------------------------- layout kernels
@@ -723,6 +727,7 @@ struct Engine {
     a.midpoint = d->magnetic_integrator == AMX_IMPLICIT_MIDPOINT;
     a.dt = dt; a.change_slots = cslots(); a.change_slots2 = &ctl->change2_slots[0][0];
     a.fix_base = -1;
+    a.emit = 0; a.emit_gas = B0; a.emit_B = B0;
     return a;
   }
   bool pair_supported(const MagIterArgs& a) const {
@@ -730,8 +735,10 @@ struct Engine {
     return strict ? amx_strict::pair_mag_supported(a) : amx_fast::pair_mag_supported(a);
   }
   // two evaluations in one launch (amx_pair.cu); c0 = evaluations completed before it
-  cudaError_t mag_pair(const View& B0, const View& gas0, const View* Xk, const View& Xk2, const void* dt, int c0) {
-    const MagIterArgs a = mag_args(B0, gas0, Xk, Xk2, dt, c0, true);
+  cudaError_t mag_pair(const View& B0, const View& gas0, const View* Xk, const View& Xk2, const void* dt, int c0,
+                       const View* emit_gas = nullptr, const View* emit_B = nullptr) {
+    MagIterArgs a = mag_args(B0, gas0, Xk, Xk2, dt, c0, true);
+    if (emit_gas) { a.emit = 1; a.emit_gas = *emit_gas; a.emit_B = *emit_B; }
     ++launches;
     ProfScope ps(PC_MAG_PAIR, st);
     return strict ? amx_strict::launch_mag_pair_vec(a, st) : amx_fast::launch_mag_pair_vec(a, st);
@@ -745,11 +752,11 @@ struct Engine {
     ProfScope ps(PC_MAG_ITER, st);
     return strict ? amx_strict::launch_mag_iter_vec(a, st) : amx_fast::launch_mag_iter_vec(a, st);
   }
-  cudaError_t mag_check_fused(int c0, int nevals, int nb) {
+  cudaError_t mag_check_fused(int c0, int nevals, int nb, int emit = 0) {
     ++launches;
     const double tol = d->fp_tol;
-    if (is32) mag_check_fused_kernel<float><<<1, 256, 0, st>>>(ctl, tol, c0, nevals, nb);
-    else mag_check_fused_kernel<double><<<1, 256, 0, st>>>(ctl, tol, c0, nevals, nb);
+    if (is32) mag_check_fused_kernel<float><<<1, 256, 0, st>>>(ctl, tol, c0, nevals, nb, emit);
+    else mag_check_fused_kernel<double><<<1, 256, 0, st>>>(ctl, tol, c0, nevals, nb, emit);
     return cudaGetLastError();
   }
 
@@ -765,12 +772,15 @@ struct Engine {
     return strict ? amx_strict::launch_mag_iter(a, st) : amx_fast::launch_mag_iter(a, st);
   }
 
-  cudaError_t mag_final(const View& gas, const View& B_out, const View X[2], int fixed_final, bool want_alpha,
-                        void* alpha_t_out, bool guarded) {
+  // gas (rho, v_0, p) + converged iterate -> gas_out (rho, v_n, p_2), B_out; skipped on the device when
+  // an emitting pair launch already did it (skip_if_emitted)
+  cudaError_t mag_final(const View& gas, const View& gas_out, const View& B_out, const View X[2], int fixed_final,
+                        bool want_alpha, void* alpha_t_out, bool skip_if_emitted) {
     MagFinalArgs a;
-    a.g = g; a.np = np; a.gas = gas; a.B_out = B_out; a.X[0] = X[0]; a.X[1] = X[1];
+    a.g = g; a.np = np; a.gas = gas; a.gas_out = gas_out; a.B_out = B_out; a.X[0] = X[0]; a.X[1] = X[1];
     a.ctl_ro = ctl; a.fixed_final = fixed_final; a.alpha_slots = want_alpha ? aslots() : nullptr;
-    (void)guarded;
+    a.skip_if_emitted = skip_if_emitted ? 1 : 0;
+    a.final_runs = &ctl->final_runs;
     ++launches;
     {
       ProfScope ps(PC_MAG_FINAL, st);
@@ -807,6 +817,7 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
   }
   // Strang: hydro(dt/2) on the gas rows . magnetic(dt) . hydro(dt/2)
   const View X[2] = {E.internal(L.off_X[0]), E.internal(L.off_X[1])};
+  const View Gf = E.internal(L.off_Gf);
   const View Bin = rows_of(sin, L.ng, L.esz), Bout = rows_of(sout, L.ng, L.esz);
   // second half-step needs two scratch buffers besides G: A and the gas rows of ... X is free by then
   CK(E.hydro(sin, G, A, X[0], 0.5, false));
@@ -815,13 +826,26 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
   // plus one launch of slack, every launch followed by the device-side while-condition; launches
   // past convergence exit at once.  Launch number L writes iterate buffer X[L & 1].
   const bool pairs = E.pair_supported(E.mag_args(Bin, G, nullptr, X[0], E.dt_ptr(), 0, true));
+  // The pair launch expected to end the loop also writes the write-back of its result (gas -> Gf,
+  // B -> the output state), which saves the separate mag_final pass (18 words per cell) whenever
+  // the expectation holds; Lax-Friedrichs / PP need the wave bounds of the written-back gas and
+  // keep mag_final.  AMX_NO_EMIT=1 switches it off.
+  static const bool no_emit = [] { const char* e = getenv("AMX_NO_EMIT"); return e && e[0] == '1'; }();
+  bool emit_ok = pairs && !E.lf && !no_emit;
+  if (emit_ok) {
+    MagIterArgs probe = E.mag_args(Bin, G, nullptr, X[0], E.dt_ptr(), 0, true);
+    probe.emit = 1; probe.emit_gas = Gf; probe.emit_B = Bout;
+    emit_ok = E.pair_supported(probe);
+  }
+  const int expect = std::max(1, *kspec);
   int c = 0, nl = 0;  // evaluations / launches enqueued
   auto enqueue = [&](bool pair) -> int {
     const View* src = nl == 0 ? nullptr : &X[(nl - 1) & 1];
     const View& dst = X[nl & 1];
     if (pair) {
-      CK(E.mag_pair(Bin, G, src, dst, E.dt_ptr(), c));
-      CK(E.mag_check_fused(c, 2, nl & 1));
+      const bool emit = emit_ok && c + 2 == expect;
+      CK(E.mag_pair(Bin, G, src, dst, E.dt_ptr(), c, emit ? &Gf : nullptr, emit ? &Bout : nullptr));
+      CK(E.mag_check_fused(c, 2, nl & 1, emit ? 1 : 0));
       CK(E.mag_fix(Bin, G, src, dst, E.dt_ptr(), c));
       c += 2;
     } else {
@@ -832,7 +856,6 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
     ++nl;
     return AMX_OK;
   };
-  const int expect = std::max(1, *kspec);
   int rc;
   while (c < expect)
     if ((rc = enqueue(pairs && (expect - c >= 2 || pair_greedy())))) return rc;
@@ -841,8 +864,8 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
   // per-step host round trip costs
   static const bool nosync = [] { const char* e = getenv("AMX_NOSYNC"); return e && e[0] == '1'; }();
   if (nosync) {
-    CK(E.mag_final(G, Bout, X, -1, E.lf, nullptr, true));
-    CK(E.hydro(G, sout, A, X[0], 0.5, true));
+    CK(E.mag_final(G, Gf, Bout, X, -1, E.lf, nullptr, true));
+    CK(E.hydro(Gf, sout, A, X[0], 0.5, true));
     return AMX_OK;
   }
   Ctl* m;
@@ -855,9 +878,9 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
     if (rc) return rc;
   }
   if (!m->done) *kspec = m->mag_iter + 1;
-  CK(E.mag_final(G, Bout, X, -1, E.lf, nullptr, true));
+  CK(E.mag_final(G, Gf, Bout, X, -1, E.lf, nullptr, true));
   // X buffers are free again: reuse X[0] rows as sweep scratch
-  CK(E.hydro(G, sout, A, X[0], 0.5, true));
+  CK(E.hydro(Gf, sout, A, X[0], 0.5, true));
   return AMX_OK;
 }
 
@@ -1021,6 +1044,7 @@ int amx_step(const amx_desc* d, const void* seam_in, void* seam_out, const void*
     stats->kernel_launches = E.launches;
     stats->pair_launches = m->pair_runs;
     stats->single_launches = m->single_runs;
+    stats->final_launches = m->final_runs;
     if (m->not_converged) return fail(AMX_ENOTCONVERGED, "magnetic fixed point hit the 1000-iteration cap");
   }
   return AMX_OK;
@@ -1084,6 +1108,7 @@ int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpadded_out
     stats->kernel_launches = E.launches;
     stats->pair_launches = m->pair_runs;
     stats->single_launches = m->single_runs;
+    stats->final_launches = m->final_runs;
   }
   if (m->not_converged) return fail(AMX_ENOTCONVERGED, "magnetic fixed point hit the 1000-iteration cap");
   return AMX_OK;
@@ -1170,6 +1195,7 @@ int amx_magnetic_final(const amx_desc* d, void* gas_inout, const void* bv_final,
   const View X[2] = {E.user_internal(bv_final), E.user_internal(bv_final)};
   MagFinalArgs a;
   a.g = E.g; a.np = E.np; a.gas = E.user_internal(gas_inout); a.B_out = E.user_internal(B_out);
+  a.gas_out = a.gas; a.skip_if_emitted = 0; a.final_runs = nullptr;
   a.X[0] = X[0]; a.X[1] = X[1]; a.ctl_ro = nullptr; a.fixed_final = 0;
   a.alpha_slots = alpha_out ? E.aslots() : nullptr;
   CK(E.strict ? amx_strict::launch_mag_final(a, E.st) : amx_fast::launch_mag_final(a, E.st));
@@ -1218,6 +1244,7 @@ int amx_magnetic_final_guarded(const amx_desc* d, void* gas_inout, const void* b
   Engine E(d, ws, stream);
   MagFinalArgs a;
   a.g = E.g; a.np = E.np; a.gas = E.user_internal(gas_inout); a.B_out = E.user_internal(B_out);
+  a.gas_out = a.gas; a.skip_if_emitted = 0; a.final_runs = nullptr;
   a.X[0] = E.user_internal(bv0); a.X[1] = E.user_internal(bv1); a.ctl_ro = E.ctl; a.fixed_final = -1;
   a.alpha_slots = alpha_out ? E.aslots() : nullptr;
   CK(E.strict ? amx_strict::launch_mag_final(a, E.st) : amx_fast::launch_mag_final(a, E.st));
@@ -1228,7 +1255,7 @@ int amx_magnetic_final_guarded(const amx_desc* d, void* gas_inout, const void* b
 int amx_magnetic_pair_supported(const amx_desc* d) {
   if (validate(d) || !d->mhd || d->dtype != AMX_F32 || d->ndim != 3) return 0;
   Engine E(d, nullptr, nullptr);
-  MagIterArgs a;
+  MagIterArgs a{};
   a.g = E.g; a.np = E.np;
   // layout rules are those of the internal slab layout: dense, even extents; probe with aligned dummies
   int pad[3];

@@ -48,10 +48,11 @@ struct Ctl {
   int not_converged;         // sticky: 1000-iteration cap was hit
   int mag_fix;               // the loop ended on the FIRST evaluation of pair launch `mag_fix_base`:
   int mag_fix_base;          //   that evaluation is re-run alone (evaluations completed before the pair)
-  int pad0;
+  int final_emitted;         // the pair launch that ended the loop already wrote the write-back (amx_pair.cu EMIT)
   long long steps;
   long long mag_iters_total;
   long long pair_runs, single_runs;  // fixed-point launches that did work (bench.py byte accounting)
+  long long final_runs;              // write-back launches that did work (not pre-empted by an emitting pair)
   unsigned long long alpha_slots[3][kAlphaSlots];  // bit patterns of non-negative T values
   unsigned long long change_slots[2][kAlphaSlots];
   unsigned long long change2_slots[2][kAlphaSlots];  // second evaluation of a pair launch (amx_pair.cu)
@@ -97,16 +98,23 @@ struct MagIterArgs {
   unsigned long long* change_slots;   // [2][kAlphaSlots]; nullable (no norms wanted)
   unsigned long long* change_slots2;  // pair launch: norms of the second evaluation
   int fix_base;  // >= 0: run only if ctl->mag_fix && ctl->mag_fix_base == fix_base (see Ctl)
+  // pair launch expected to end the loop: its second evaluation also writes what mag_final would
+  // (_magnetic_field_update.py:208-240): gas rows (rho, v_n, p_2) to emit_gas, B_n to emit_B
+  int emit;
+  View emit_gas, emit_B;
 };
 
 struct MagFinalArgs {
   Geom g;
   NumPar np;
-  View gas;       // in/out: v rows and p row are rewritten
+  View gas;       // in: rho, v_0, p
+  View gas_out;   // out: rho, v_n, p_2 (may be the same array as gas)
   View B_out;     // 3 rows
   View X[2];      // the two iterate buffers, 6 rows each (B then v)
   const Ctl* ctl_ro;
   int fixed_final;  // >= 0: use this buffer index instead of ctl->mag_final
+  int skip_if_emitted;  // do nothing when ctl->final_emitted (an emitting pair launch did the work)
+  long long* final_runs;  // nullable: counts launches that did work
   unsigned long long* alpha_slots;
 };
 

@@ -528,7 +528,8 @@ __global__ void __launch_bounds__(256) mag_iter_kernel(const MagIterArgs a) {
 // _magnetic_field_update.py:208-240 (gamma hard-coded 5/3, Q4; 2-D drops v_z, Q5)
 template <typename T, int ND>
 __global__ void __launch_bounds__(256) mag_final_kernel(const MagFinalArgs a) {
-  if (a.ctl_ro && a.ctl_ro->done) return;
+  if (a.ctl_ro && (a.ctl_ro->done || (a.skip_if_emitted && a.ctl_ro->final_emitted))) return;
+  if (a.final_runs && blockIdx.x == 0 && threadIdx.x == 0) *a.final_runs += 1;
   const Consts<T> c = make_consts<T>(a.np);
   Idx3 cell;
   const bool active = decode_cell<ND>(a.g, cell);
@@ -539,8 +540,9 @@ __global__ void __launch_bounds__(256) mag_final_kernel(const MagFinalArgs a) {
     const int fin = a.fixed_final >= 0 ? a.fixed_final : a.ctl_ro->mag_final;
     const View& X = a.X[fin];
     const long long ox = offset_of<ND>(X, cell), og = offset_of<ND>(a.gas, cell), ob = offset_of<ND>(a.B_out, cell);
+    const long long oo = offset_of<ND>(a.gas_out, cell);
     const T* px = static_cast<const T*>(X.p) + ox;
-    T* pg = static_cast<T*>(a.gas.p) + og;
+    T* po = static_cast<T*>(a.gas_out.p) + oo;
     T* pb = static_cast<T*>(a.B_out.p) + ob;
     Gas<T, ND> s = load_gas<T, ND>(a.gas, og);
     T n0 = T(0), nn = T(0), vn[3];
@@ -552,19 +554,12 @@ __global__ void __launch_bounds__(256) mag_final_kernel(const MagFinalArgs a) {
       n0 = n0 + sq(rabs(v0k));
       nn = nn + sq(rabs(vn[k]));
     }
-    const T g53m1 = (T)(5.0 / 3.0 - 1.0);
-    const T rho = s.q[0];
-#if AMX_STRICT
-    n0 = sq(rsqrt_(n0));
-    nn = sq(rsqrt_(nn));
-#endif
-    const T E = rdiv(s.q[ND + 1], g53m1) + (T(0.5) * rho) * n0;
-    const T E2 = E - (T(0.5) * rho) * n0 + (T(0.5) * rho) * nn;
-    const T p2 = (g53m1 * rho) * (rdiv(E2, rho) - T(0.5) * nn);
+    const T p2 = magnetic_writeback_pressure(s.q[0], s.q[ND + 1], n0, nn);
+    if (a.gas_out.p != a.gas.p) po[0] = s.q[0];
 #pragma unroll
-    for (int k = 0; k < ND; ++k) { s.q[k + 1] = vn[k]; pg[(k + 1) * a.gas.vs] = vn[k]; }
+    for (int k = 0; k < ND; ++k) { s.q[k + 1] = vn[k]; po[(k + 1) * a.gas_out.vs] = vn[k]; }
     s.q[ND + 1] = p2;
-    pg[(ND + 1) * a.gas.vs] = p2;
+    po[(ND + 1) * a.gas_out.vs] = p2;
     if (a.alpha_slots) {
 #pragma unroll
       for (int k = 0; k < ND; ++k) wb[k] = wave_bound(s, k + 1, c);

@@ -230,6 +230,22 @@ AMX_DI Gas<T, ND> euler_flux(const Gas<T, ND>& s, int ax, const Consts<T>& c) {
   return F;
 }
 
+// _magnetic_field_update.py:208-240: pressure after the magnetic step from the energy bookkeeping
+// E2 = E - rho |v_0|^2 / 2 + rho |v_n|^2 / 2 with gamma hard-coded to 5/3 (Q4).  n0 / nn are the
+// sums of squares of the old / new velocity components (norm-then-square in the reference: the
+// STRICT flavour takes the square root and squares again).
+template <typename T>
+AMX_DI T magnetic_writeback_pressure(T rho, T p, T n0, T nn) {
+  const T g53m1 = (T)(5.0 / 3.0 - 1.0);
+#if AMX_STRICT
+  n0 = sq(rsqrt_(n0));
+  nn = sq(rsqrt_(nn));
+#endif
+  const T E = rdiv(p, g53m1) + (T(0.5) * rho) * n0;
+  const T E2 = E - (T(0.5) * rho) * n0 + (T(0.5) * rho) * nn;
+  return (g53m1 * rho) * (rdiv(E2, rho) - T(0.5) * nn);
+}
+
 // ---------------------------------------------------------------- limiters
 // _finite_volume/_state_evolution/limiters.py:14-15.  0.5*(sgn a + sgn b)*min(|a|,|b|) is
 // min(a,b) for two positives, max(a,b) for two negatives and (signed) zero otherwise.

@@ -123,7 +123,7 @@ AMX_DI void psi_ring(const float* w, const float* wm, const F2 (&Bp)[3], const F
 
 // FIRST: evaluation 1 starts from R_k = R_0 (launch 0 of the fixed point).  MID: implicit midpoint
 // (argument (R + R_0)/2) or implicit Euler (argument R).
-template <bool FIRST, bool MID, int TY, int LD>
+template <bool FIRST, bool MID, int TY, bool EMIT>
 __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf) {
   if (a.ctl_ro && (a.ctl_ro->done || (!a.first && !a.ctl_ro->mag_active))) return;
   using G = PG<TY>;
@@ -220,17 +220,17 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
     const float* pg = fG + o;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      r.B0[k] = ldg2<LD>(pb + k * vB0);
-      r.v0[k] = ldg2<LD>(pg + (k + 1) * vG);
+      r.B0[k] = ldg2<0>(pb + k * vB0);
+      r.v0[k] = ldg2<0>(pg + (k + 1) * vG);
     }
-    if (need_rho) r.rho = ldg2<LD>(pg);
+    if (need_rho) r.rho = ldg2<0>(pg);
     if constexpr (!FIRST) {
       const float* pbk = fBk + o;
       const float* pvk = fvk + o;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        r.Bk[k] = ldg2<LD>(pbk + k * vBk);
-        r.vk[k] = ldg2<LD>(pvk + k * vvk);
+        r.Bk[k] = ldg2<0>(pbk + k * vBk);
+        r.vk[k] = ldg2<0>(pvk + k * vvk);
       }
     }
   };
@@ -341,6 +341,30 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
         stg2(fB1 + o + k * vB1, Bn[k]);
         stg2(fv1 + o + k * vv1, vn[k]);
       }
+      if constexpr (EMIT) {
+        // this launch is expected to end the loop: write what mag_final would from R_{k+2}
+        // (rho, v_n, p_2 -> emit_gas; B_n -> emit_B); valid only if the while-condition agrees
+        // (Ctl::final_emitted), else mag_final runs as usual
+        const F2 pr = ldg2<0>(fG + o + 4 * vG);
+        F2 n0 = bc2(0.f), nn = bc2(0.f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          n0 = n0 + abs2(v0[k]) * abs2(v0[k]);
+          nn = nn + abs2(vn[k]) * abs2(vn[k]);
+        }
+        const F2 p2 = mk2(magnetic_writeback_pressure(rho.x, pr.x, n0.x, nn.x),
+                          magnetic_writeback_pressure(rho.y, pr.y, n0.y, nn.y));
+        float* const eg = static_cast<float*>(a.emit_gas.p) + o;
+        float* const eb = static_cast<float*>(a.emit_B.p) + o;
+        const long long veg = a.emit_gas.vs, veb = a.emit_B.vs;
+        stg2(eg, rho);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          stg2(eg + (k + 1) * veg, vn[k]);
+          stg2(eb + k * veb, Bn[k]);
+        }
+        stg2(eg + 4 * veg, p2);
+      }
     }
     __syncthreads();
     const int t = sM; sM = sC; sC = sP; sP = t;
@@ -375,10 +399,10 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
   }
 }
 
-template <bool FIRST, bool MID, int TY, int LD>
-cudaError_t launch_pair_ld(const MagIterArgs& a, cudaStream_t st) {
+template <bool FIRST, bool MID, int TY, bool EMIT>
+cudaError_t launch_pair_e(const MagIterArgs& a, cudaStream_t st) {
   using G = PG<TY>;
-  auto kern = mag_pair_vec<FIRST, MID, TY, LD>;
+  auto kern = mag_pair_vec<FIRST, MID, TY, EMIT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
@@ -391,16 +415,15 @@ cudaError_t launch_pair_ld(const MagIterArgs& a, cudaStream_t st) {
   const int nch = pick_chunks(a.g.n[0], (long long)grid.x * grid.y, 1, 3);
   const int xchunk = (a.g.n[0] + nch - 1) / nch;
   grid.z = (a.g.n[0] + xchunk - 1) / xchunk;
+  // AMX_PAIR_PF: planes ahead whose lines are pulled into L2 (0: off)
   static const int pf = [] { const char* e = getenv("AMX_PAIR_PF"); return e ? atoi(e) : 2; }();
   kern<<<grid, G::kThreads, G::smem_bytes, st>>>(a, xchunk, pf);
   return cudaGetLastError();
 }
 
-// AMX_PAIR_LD=1: stream the inputs past L1 (ld.global.nc.L1::no_allocate); default: plain __ldg
 template <bool FIRST, bool MID, int TY>
 cudaError_t launch_pair(const MagIterArgs& a, cudaStream_t st) {
-  static const int ld = [] { const char* e = getenv("AMX_PAIR_LD"); return e ? atoi(e) : 0; }();
-  return ld == 1 ? launch_pair_ld<FIRST, MID, TY, 1>(a, st) : launch_pair_ld<FIRST, MID, TY, 0>(a, st);
+  return a.emit ? launch_pair_e<FIRST, MID, TY, true>(a, st) : launch_pair_e<FIRST, MID, TY, false>(a, st);
 }
 
 constexpr int kPairTY = 11;
@@ -416,6 +439,11 @@ bool pair_mag_supported(const MagIterArgs& a) {
   const bool xper = a.g.bc[0][0] == BC_PERIODIC && a.g.bc[0][1] == BC_PERIODIC;
   const bool xhalo = a.g.bc[0][0] == BC_HALO && a.g.bc[0][1] == BC_HALO;
   if (!xper && !xhalo) return false;
+  if (a.emit) {
+    if (!vec::view_ok(a.emit_gas, 3) || !vec::view_ok(a.emit_B, 3)) return false;
+    for (int ax = 0; ax < 2; ++ax)
+      if (a.emit_gas.s[ax] != a.B0.s[ax] || a.emit_B.s[ax] != a.B0.s[ax]) return false;
+  }
   return a.g.n[0] >= 4 && a.g.n[1] >= 4 && a.g.n[2] >= 8;
 }
 

@@ -37,6 +37,7 @@ class IntegrationInfo(NamedTuple):
     kernel_launches: int
     pair_launches: int = 0    # fixed-point launches that made two evaluations (amx_pair.cu)
     single_launches: int = 0  # fixed-point launches that made one evaluation
+    final_launches: int = 0   # magnetic write-back launches that did work
 
 
 #: statistics of the most recent time_integration call on this process
@@ -151,7 +152,8 @@ def time_integration(primitive_state, config, params, registered_variables: Regi
         _lib.check(lib.amx_integrate(C.byref(desc), C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()),
                                      float(params.t_end), -1, ws_ptr, _stream_ptr(), C.byref(stats)))
     last_info = IntegrationInfo(stats.steps, stats.time, stats.last_dt, stats.magnetic_iterations,
-                                stats.kernel_launches, stats.pair_launches, stats.single_launches)
+                                stats.kernel_launches, stats.pair_launches, stats.single_launches,
+                                stats.final_launches)
     res = _from_device(out, kind)
     return StateStruct(primitive_state=res) if struct else res
 
@@ -172,7 +174,8 @@ def integrate_steps(primitive_state, config, params, registered_variables, num_s
                                              float(params.t_end), int(num_steps), ws_ptr, _stream_ptr(),
                                              C.byref(stats)))
     last_info = IntegrationInfo(stats.steps, stats.time, stats.last_dt, stats.magnetic_iterations,
-                                stats.kernel_launches, stats.pair_launches, stats.single_launches)
+                                stats.kernel_launches, stats.pair_launches, stats.single_launches,
+                                stats.final_launches)
     return _from_device(out, kind)
 
 

@@ -269,7 +269,10 @@ def run_native(args):
         kernels["magnetic_iter"]["launches_with_work"] = singles
         first = 0 if pairs else K
         alg["magnetic_iter"] = (first * 13 + (singles - first) * 19) / singles * w * cells
-    alg["magnetic_final"] = (6 + ng + 3 + 1 + 3) * w * cells  # reads iterate + gas, writes v, p, B
+    alg["magnetic_final"] = (6 + ng + ng + 3) * w * cells  # reads iterate + gas, writes gas (rho, v, p) + B
+    if "magnetic_final" in kernels:
+        # write-back launches pre-empted by an emitting pair launch exit at once
+        kernels["magnetic_final"]["launches_with_work"] = max(1, int(stats.final_launches))
     for k in kernels:
         if k in alg:
             work = kernels[k].get("launches_with_work", kernels[k]["launches"])

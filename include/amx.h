@@ -95,6 +95,8 @@ typedef struct amx_stats {
   int64_t kernel_launches;    /* libamx kernels enqueued by the call */
   int64_t pair_launches;      /* fixed-point launches that made two evaluations (temporal blocking) */
   int64_t single_launches;    /* fixed-point launches that made one evaluation */
+  int64_t final_launches;     /* write-back launches that did work (the others were pre-empted by a pair
+                                 launch that wrote the write-back of its own result) */
 } amx_stats;
 
 AMX_API int amx_abi_version(void);

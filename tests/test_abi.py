@@ -32,7 +32,7 @@ def test_struct_layout_matches_header():
     # 4*(1+1+3+1+1+1+1+1+1+1+6+1+1+1+1+1+1+8) = 128 bytes of int32, then 5 doubles
     assert C.sizeof(_lib.AmxDesc) == 128 + 40
     assert _lib.AmxDesc.dx.offset == 128
-    assert C.sizeof(_lib.AmxStats) == 56
+    assert C.sizeof(_lib.AmxStats) == 64
 
 
 def _desc(**kw):
