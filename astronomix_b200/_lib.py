@@ -96,10 +96,10 @@ PROTOTYPES = {
     "amx_magnetic_final": (C.c_int, [_D, _P, _P, _P, _P, _P, _P]),
     "amx_magnetic_iter_guarded": (C.c_int, [_D, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
     "amx_magnetic_check": (C.c_int, [_D, _P, C.c_int, _P, _P]),
-    "amx_magnetic_final_guarded": (C.c_int, [_D, _P, _P, _P, _P, _P, _P, _P]),
+    "amx_magnetic_final_guarded": (C.c_int, [_D, _P, _P, _P, _P, _P, _P, _P, _P]),
     "amx_magnetic_pair_supported": (C.c_int, [_D]),
-    "amx_magnetic_pair_guarded": (C.c_int, [_D, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
-    "amx_magnetic_check_pair": (C.c_int, [_D, _P, C.c_int, C.c_int, _P, _P]),
+    "amx_magnetic_pair_guarded": (C.c_int, [_D, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "amx_magnetic_check_pair": (C.c_int, [_D, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "amx_magnetic_fix_guarded": (C.c_int, [_D, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
     "amx_magnetic_state": (C.c_int, [_D, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }

@@ -373,7 +373,7 @@ __global__ void mag_check_fused_kernel(Ctl* ctl, double tol, int c0, int nevals,
 // the same condition for slab ranks, on norms that were all-reduced across ranks (amx_magnetic_check)
 template <typename T>
 __global__ void mag_check_slab_kernel(Ctl* ctl, const T* change, double tol, int j) {
-  if (j == 0) { ctl->mag_active = 1; ctl->mag_iter = 0; ctl->mag_fix = 0; }
+  if (j == 0) { ctl->mag_active = 1; ctl->mag_iter = 0; ctl->mag_fix = 0; ctl->final_emitted = 0; }
   if (!ctl->mag_active) return;
   const T m = change[0] > change[1] ? change[0] : change[1];
   if (m > (T)tol && ctl->mag_iter < 1000) {
@@ -387,8 +387,8 @@ __global__ void mag_check_slab_kernel(Ctl* ctl, const T* change, double tol, int
 
 // pair launches of slab ranks: the condition after each of the two evaluations, on all-reduced norms
 template <typename T>
-__global__ void mag_check_pair_slab_kernel(Ctl* ctl, const T* n, double tol, int c0, int nb) {
-  if (c0 == 0) { ctl->mag_active = 1; ctl->mag_iter = 0; ctl->mag_fix = 0; }
+__global__ void mag_check_pair_slab_kernel(Ctl* ctl, const T* n, double tol, int c0, int nb, int emit) {
+  if (c0 == 0) { ctl->mag_active = 1; ctl->mag_iter = 0; ctl->mag_fix = 0; ctl->final_emitted = 0; }
   if (!ctl->mag_active) return;
   const T m1 = n[0] > n[1] ? n[0] : n[1];
   if (!(m1 > (T)tol && ctl->mag_iter < 1000)) {
@@ -407,6 +407,7 @@ __global__ void mag_check_pair_slab_kernel(Ctl* ctl, const T* n, double tol, int
     ctl->mag_active = 0;
     ctl->mag_final = nb;
     if (m2 > (T)tol) ctl->not_converged = 1;
+    ctl->final_emitted = emit;
   }
 }
 
@@ -1234,17 +1235,17 @@ int amx_magnetic_check(const amx_desc* d, const void* change_dev, int launch_ind
   return AMX_OK;
 }
 
-int amx_magnetic_final_guarded(const amx_desc* d, void* gas_inout, const void* bv0, const void* bv1, void* B_out,
-                               void* alpha_out, void* ws, void* stream) {
-  int rc = check_common(d, gas_inout, bv0);
+int amx_magnetic_final_guarded(const amx_desc* d, const void* gas_in, void* gas_out, const void* bv0,
+                               const void* bv1, void* B_out, void* alpha_out, void* ws, void* stream) {
+  int rc = check_common(d, gas_in, bv0);
   if (rc) return rc;
-  if (!ws || !B_out || !bv1) return fail(AMX_EINVAL, "null pointer");
+  if (!ws || !B_out || !bv1 || !gas_out) return fail(AMX_EINVAL, "null pointer");
   if (!d->mhd) return fail(AMX_EINVAL, "descriptor is not MHD");
   if ((rc = amx_device_check())) return rc;
   Engine E(d, ws, stream);
   MagFinalArgs a;
-  a.g = E.g; a.np = E.np; a.gas = E.user_internal(gas_inout); a.B_out = E.user_internal(B_out);
-  a.gas_out = a.gas; a.skip_if_emitted = 0; a.final_runs = nullptr;
+  a.g = E.g; a.np = E.np; a.gas = E.user_internal(gas_in); a.B_out = E.user_internal(B_out);
+  a.gas_out = E.user_internal(gas_out); a.skip_if_emitted = 1; a.final_runs = nullptr;
   a.X[0] = E.user_internal(bv0); a.X[1] = E.user_internal(bv1); a.ctl_ro = E.ctl; a.fixed_final = -1;
   a.alpha_slots = alpha_out ? E.aslots() : nullptr;
   CK(E.strict ? amx_strict::launch_mag_final(a, E.st) : amx_fast::launch_mag_final(a, E.st));
@@ -1269,8 +1270,8 @@ int amx_magnetic_pair_supported(const amx_desc* d) {
 }
 
 int amx_magnetic_pair_guarded(const amx_desc* d, const void* B0, const void* gas0, const void* bvk_or_null,
-                              void* bvk2, const void* dt_dev, void* change4_out, int evals_before, void* ws,
-                              void* stream) {
+                              void* bvk2, const void* dt_dev, void* change4_out, int evals_before,
+                              void* emit_gas_or_null, void* emit_B_or_null, void* ws, void* stream) {
   int rc = check_common(d, B0, bvk2);
   if (rc) return rc;
   if (!ws || !dt_dev || !gas0 || !change4_out) return fail(AMX_EINVAL, "null pointer");
@@ -1282,9 +1283,18 @@ int amx_magnetic_pair_guarded(const amx_desc* d, const void* B0, const void* gas
   const View vB0 = E.user_internal(B0), vg = E.user_internal(gas0), vk2 = E.user_internal(bvk2);
   View vk;
   if (bvk_or_null) vk = E.user_internal(bvk_or_null);
-  if (!E.pair_supported(E.mag_args(vB0, vg, bvk_or_null ? &vk : nullptr, vk2, dt_dev, evals_before, true)))
+  if ((emit_gas_or_null == nullptr) != (emit_B_or_null == nullptr))
+    return fail(AMX_EINVAL, "emit_gas and emit_B go together");
+  View eg, eb;
+  MagIterArgs probe = E.mag_args(vB0, vg, bvk_or_null ? &vk : nullptr, vk2, dt_dev, evals_before, true);
+  if (emit_gas_or_null) {
+    eg = E.user_internal(emit_gas_or_null); eb = E.user_internal(emit_B_or_null);
+    probe.emit = 1; probe.emit_gas = eg; probe.emit_B = eb;
+  }
+  if (!E.pair_supported(probe))
     return fail(AMX_EUNSUPPORTED, "pair launches need 3-D fp32 with periodic y / z and halo or periodic x");
-  CK(E.mag_pair(vB0, vg, bvk_or_null ? &vk : nullptr, vk2, dt_dev, evals_before));
+  CK(E.mag_pair(vB0, vg, bvk_or_null ? &vk : nullptr, vk2, dt_dev, evals_before, emit_gas_or_null ? &eg : nullptr,
+                emit_gas_or_null ? &eb : nullptr));
   const size_t esz = E.L.esz;
   CK(E.finalize_change(change4_out, false));
   CK(E.finalize_change2(static_cast<char*>(change4_out) + 2 * esz));
@@ -1292,15 +1302,15 @@ int amx_magnetic_pair_guarded(const amx_desc* d, const void* B0, const void* gas
 }
 
 int amx_magnetic_check_pair(const amx_desc* d, const void* change4_dev, int evals_before, int buffer_index,
-                            void* ws, void* stream) {
+                            int emit, void* ws, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
   if (!ws || !change4_dev || evals_before < 0 || buffer_index < 0 || buffer_index > 1)
     return fail(AMX_EINVAL, "null pointer / bad index");
   if ((rc = amx_device_check())) return rc;
   Engine E(d, ws, stream);
-  if (E.is32) mag_check_pair_slab_kernel<float><<<1, 1, 0, E.st>>>(E.ctl, (const float*)change4_dev, d->fp_tol, evals_before, buffer_index);
-  else mag_check_pair_slab_kernel<double><<<1, 1, 0, E.st>>>(E.ctl, (const double*)change4_dev, d->fp_tol, evals_before, buffer_index);
+  if (E.is32) mag_check_pair_slab_kernel<float><<<1, 1, 0, E.st>>>(E.ctl, (const float*)change4_dev, d->fp_tol, evals_before, buffer_index, emit ? 1 : 0);
+  else mag_check_pair_slab_kernel<double><<<1, 1, 0, E.st>>>(E.ctl, (const double*)change4_dev, d->fp_tol, evals_before, buffer_index, emit ? 1 : 0);
   CK(cudaGetLastError());
   return AMX_OK;
 }

@@ -101,23 +101,26 @@ class AmxBackend:
                                                self._s()))
         self.launches += 1
 
-    def magnetic_final_guarded(self, gas, bv0, bv1, B_out, alpha_out):
-        _lib.check(self.lib.amx_magnetic_final_guarded(C.byref(self.desc), self._p(gas), self._p(bv0), self._p(bv1),
-                                                       self._p(B_out), self._p(alpha_out), self.ws_ptr, self._s()))
+    def magnetic_final_guarded(self, gas, gas_out, bv0, bv1, B_out, alpha_out):
+        _lib.check(self.lib.amx_magnetic_final_guarded(C.byref(self.desc), self._p(gas), self._p(gas_out),
+                                                       self._p(bv0), self._p(bv1), self._p(B_out),
+                                                       self._p(alpha_out), self.ws_ptr, self._s()))
         self.launches += 2 if alpha_out is not None else 1
 
     def pair_supported(self):
         return bool(self.lib.amx_magnetic_pair_supported(C.byref(self.desc)))
 
-    def magnetic_pair_guarded(self, B0, gas0, bvk, bvk2, dt, change4_out, evals_before):
+    def magnetic_pair_guarded(self, B0, gas0, bvk, bvk2, dt, change4_out, evals_before, emit_gas=None,
+                              emit_B=None):
         _lib.check(self.lib.amx_magnetic_pair_guarded(C.byref(self.desc), self._p(B0), self._p(gas0), self._p(bvk),
                                                       self._p(bvk2), self._p(dt), self._p(change4_out),
-                                                      int(evals_before), self.ws_ptr, self._s()))
+                                                      int(evals_before), self._p(emit_gas), self._p(emit_B),
+                                                      self.ws_ptr, self._s()))
         self.launches += 3
 
-    def magnetic_check_pair(self, change4, evals_before, buffer_index):
+    def magnetic_check_pair(self, change4, evals_before, buffer_index, emit=False):
         _lib.check(self.lib.amx_magnetic_check_pair(C.byref(self.desc), self._p(change4), int(evals_before),
-                                                    int(buffer_index), self.ws_ptr, self._s()))
+                                                    int(buffer_index), int(bool(emit)), self.ws_ptr, self._s()))
         self.launches += 1
 
     def magnetic_fix_guarded(self, B0, gas0, bvk, bvk1, dt, evals_before):
@@ -207,6 +210,7 @@ class SlabDriver:
         self.S = [z(self.nv), z(self.nv)]
         self.A, self.G = z(self.ng), z(self.ng)
         self.X = [z(6), z(6)] if self.mhd else None
+        self.Gf = z(self.ng) if self.mhd else None  # gas after the magnetic write-back
         self.alpha = torch.zeros(3, dtype=dtype, device=device)
         self.change = torch.zeros(2, dtype=dtype, device=device)
         self.change4 = torch.zeros(4, dtype=dtype, device=device)
@@ -427,10 +431,14 @@ class SlabDriver:
                 self.exchange(src, flip_rows=(1, 4))
             if pair:
                 # two evaluations, the intermediate iterate stays on chip (amx_pair.cu); if the loop
-                # ends on the first of them, that one is re-run alone into the same buffer
-                b.magnetic_pair_guarded(B0, gas, src, dst, self.dt, self.change4, c)
+                # ends on the first of them, that one is re-run alone into the same buffer.  The
+                # launch expected to end the loop also writes the write-back of its result
+                # (gas -> Gf, B -> B_out), which makes magnetic_final a no-op when it does end there.
+                emit = self.pairs and not self.lf and c + 2 == self.expect_evals
+                b.magnetic_pair_guarded(B0, gas, src, dst, self.dt, self.change4, c,
+                                        self.Gf if emit else None, B_out if emit else None)
                 self._allreduce_max(self.change4)
-                b.magnetic_check_pair(self.change4, c, nl & 1)
+                b.magnetic_check_pair(self.change4, c, nl & 1, emit)
                 b.magnetic_fix_guarded(B0, gas, src, dst, self.dt, c)
                 c += 2
             else:
@@ -451,7 +459,7 @@ class SlabDriver:
                 launch(False)
             active, it = b.magnetic_state()
         self.expect_evals = it + 1
-        b.magnetic_final_guarded(gas, self.X[0], self.X[1], B_out, self.alpha if self.lf else None)
+        b.magnetic_final_guarded(gas, self.Gf, self.X[0], self.X[1], B_out, self.alpha if self.lf else None)
         if self.lf:
             self._allreduce_max(self.alpha)
         return it
@@ -468,7 +476,7 @@ class SlabDriver:
             gin, gout = sin[: self.ng], sout[: self.ng]
             self._hydro(gin, self.G, 0.5, False, self.X[0][: self.ng])
             iters = self._magnetic(sin[self.ng:], self.G, sout[self.ng:])
-            self._hydro(self.G, gout, 0.5, True, self.X[0][: self.ng])
+            self._hydro(self.Gf, gout, 0.5, True, self.X[0][: self.ng])
         self.time.add_(self.dt)
         self.cur ^= 1
         return iters

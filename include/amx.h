@@ -189,24 +189,31 @@ AMX_API int amx_magnetic_iter_guarded(const amx_desc* d, const void* B0, const v
  * desc->dtype) after launch `launch_index`; updates the loop state. */
 AMX_API int amx_magnetic_check(const amx_desc* d, const void* change_dev, int launch_index, void* ws,
                       void* stream);
-/* amx_magnetic_final reading the converged iterate from whichever of bv0 / bv1 the loop ended in */
-AMX_API int amx_magnetic_final_guarded(const amx_desc* d, void* gas_inout, const void* bv0, const void* bv1,
-                      void* B_out, void* alpha_out, void* ws, void* stream);
+/* amx_magnetic_final reading the converged iterate from whichever of bv0 / bv1 the loop ended in and
+ * writing the gas rows to gas_out (may be gas_in itself); a no-op when an emitting pair launch ended
+ * the loop */
+AMX_API int amx_magnetic_final_guarded(const amx_desc* d, const void* gas_in, void* gas_out, const void* bv0,
+                      const void* bv1, void* B_out, void* alpha_out, void* ws, void* stream);
 /* Two evaluations per launch for slab ranks (amx_pair.cu; 3-D fp32, periodic y / z): launch number L
  * reads the iterate in bvk (NULL: R_0, only when evals_before == 0) and writes R_{evals_before+2}
  * into bvk2; change4_out (device, 4 values) receives this rank's norms of both evaluations
  * (|dB|, |dv| of the first, then of the second).  The ghost planes of bvk / B0 / gas0 must hold
- * TWO valid planes per side.  amx_magnetic_pair_supported returns 1 when the descriptor qualifies. */
+ * TWO valid planes per side.  amx_magnetic_pair_supported returns 1 when the descriptor qualifies.
+ * emit_gas / emit_B (nullable, together): the launch is expected to end the loop and also writes the
+ * write-back of its result (rho, v_n, p_2 -> emit_gas [ndim+2 rows]; B_n -> emit_B); pass emit = 1 to
+ * amx_magnetic_check_pair for that launch, and amx_magnetic_final_guarded then does nothing if the
+ * loop did end there. */
 AMX_API int amx_magnetic_pair_supported(const amx_desc* d);
 AMX_API int amx_magnetic_pair_guarded(const amx_desc* d, const void* B0, const void* gas0,
                       const void* bvk_or_null, void* bvk2, const void* dt_dev, void* change4_out,
-                      int evals_before, void* ws, void* stream);
+                      int evals_before, void* emit_gas_or_null, void* emit_B_or_null, void* ws,
+                      void* stream);
 /* while-condition after EACH of the two evaluations, on the all-reduced norms; `buffer_index` is the
  * iterate buffer (0 / 1) the pair wrote.  If the loop ends on the first evaluation, the control
  * block asks for that evaluation alone: amx_magnetic_fix_guarded (same arguments as the pair) runs
  * only then and overwrites bvk2 with R_{evals_before+1}. */
 AMX_API int amx_magnetic_check_pair(const amx_desc* d, const void* change4_dev, int evals_before,
-                      int buffer_index, void* ws, void* stream);
+                      int buffer_index, int emit, void* ws, void* stream);
 AMX_API int amx_magnetic_fix_guarded(const amx_desc* d, const void* B0, const void* gas0,
                       const void* bvk_or_null, void* bvk1, const void* dt_dev, int evals_before,
                       void* ws, void* stream);
