@@ -141,6 +141,26 @@ AMX_DI void block_max_to_slots(T (&v)[NV], unsigned long long* slots) {
   }
 }
 
+template <typename T, int ND>
+AMX_DI Gas<T, ND> load_at(const View& v, const Geom& g, const Idx3& pos);
+
+// hll.py:283-296: g = 1 where div v < -0.05 c / dx (central differences of the ghost-filled state)
+template <typename T, int ND>
+AMX_DI T compression_switch(const View& v, const Geom& g, const Idx3& pos, const Gas<T, ND>& s0, const Consts<T>& c) {
+  T div = T(0);
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    Idx3 m = pos, p = pos;
+    m.i[i] -= 1;
+    p.i[i] += 1;
+    const T d = load_at<T, ND>(v, g, p).q[i + 1] - load_at<T, ND>(v, g, m).q[i + 1];
+    const T term = d / (T(2) * c.dx);
+    div = i == 0 ? term : div + term;
+  }
+  const T cs = sound_speed(s0.q[0], s0.q[ND + 1], c);
+  return div < (T(-0.05) * cs) / c.dx ? T(1) : T(0);
+}
+
 // ---------------------------------------------------------------- unsplit stage
 template <typename T, int ND, int RS, int LIM>
 __global__ void __launch_bounds__(256) hydro_stage_kernel(const StageArgs a) {
@@ -161,14 +181,21 @@ __global__ void __launch_bounds__(256) hydro_stage_kernel(const StageArgs a) {
       const Gas<T, ND> sm1 = load_neighbor<T, ND>(a.in, a.g, cell, ax, -1);
       const Gas<T, ND> sp1 = load_neighbor<T, ND>(a.in, a.g, cell, ax, +1);
       const Gas<T, ND> sp2 = load_neighbor<T, ND>(a.in, a.g, cell, ax, +2);
-      T alpha = T(0);
-      if constexpr (RS == RS_LF) alpha = static_cast<const T*>(a.alpha_lf)[ax];
+      T alpha = T(0), alpha_r = T(0);
+      if constexpr (RS == RS_LF) alpha = alpha_r = static_cast<const T*>(a.alpha_lf)[ax];
+      if constexpr (RS == RS_HYBRID_HLLC || RS == RS_AM_HLLC) {
+        // flux array entry i (interface i-1/2) takes the switch of cell i
+        Idx3 pp = cell;
+        pp.i[ax] += 1;
+        alpha = compression_switch<T, ND>(a.in, a.g, cell, sc, c);
+        alpha_r = compression_switch<T, ND>(a.in, a.g, pp, sp1, c);
+      }
       Gas<T, ND> lo_m, hi_m, lo_c, hi_c, lo_p, hi_p;
       faces_unsplit(sm1, slopes<T, ND, LIM>(sm2, sm1, sc, a.np.lim, c), c, lo_m, hi_m);
       faces_unsplit(sc, slopes<T, ND, LIM>(sm1, sc, sp1, a.np.lim, c), c, lo_c, hi_c);
       faces_unsplit(sp1, slopes<T, ND, LIM>(sc, sp1, sp2, a.np.lim, c), c, lo_p, hi_p);
-      const Gas<T, ND> Fl = riemann<T, ND, RS>(hi_m, lo_c, ax + 1, alpha, c);  // interface i-1/2
-      const Gas<T, ND> Fr = riemann<T, ND, RS>(hi_c, lo_p, ax + 1, alpha, c);  // interface i+1/2
+      const Gas<T, ND> Fl = riemann<T, ND, RS>(hi_m, lo_c, ax + 1, alpha, c);    // interface i-1/2
+      const Gas<T, ND> Fr = riemann<T, ND, RS>(hi_c, lo_p, ax + 1, alpha_r, c);  // interface i+1/2
 #pragma unroll
       for (int k = 0; k < ND + 2; ++k) U.q[k] = U.q[k] + (c.inv_dx * (Fl.q[k] - Fr.q[k])) * dt;
     }
@@ -608,6 +635,14 @@ static cudaError_t launch_hydro_stage_pp_t(const StageArgs& a, cudaStream_t st) 
 
 template <typename T>
 static cudaError_t launch_hydro_stage_t(const StageArgs& a, cudaStream_t st) {
+  if (a.np.rs == RS_HYBRID_HLLC || a.np.rs == RS_AM_HLLC) {  // generic limiter switch only
+    AMX_DISPATCH_ND(a.g.nd, {
+      const unsigned grid = grid_for<ND>(a.g);
+      if (a.np.rs == RS_HYBRID_HLLC) hydro_stage_kernel<T, ND, RS_HYBRID_HLLC, -1><<<grid, 256, 0, st>>>(a);
+      else hydro_stage_kernel<T, ND, RS_AM_HLLC, -1><<<grid, 256, 0, st>>>(a);
+    })
+    return cudaGetLastError();
+  }
   AMX_DISPATCH_ND(a.g.nd, AMX_DISPATCH_RS(a.np.rs, {
     const unsigned grid = grid_for<ND>(a.g);
     if (a.np.lim == LIM_MINMOD) hydro_stage_kernel<T, ND, RS, LIM_MINMOD><<<grid, 256, 0, st>>>(a);

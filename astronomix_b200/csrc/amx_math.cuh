@@ -19,7 +19,7 @@ namespace amx {
 
 enum : int { LIM_MINMOD = 0, LIM_OSHER = 1, LIM_DOUBLE_MINMOD = 2, LIM_SUPERBEE = 3, LIM_VAN_ALBADA = 4,
              LIM_VAN_ALBADA_PP = 5 };
-enum : int { RS_HLL = 0, RS_HLLC = 1, RS_HLLC_LM = 2, RS_LF = 3 };
+enum : int { RS_HLL = 0, RS_HLLC = 1, RS_HLLC_LM = 2, RS_LF = 3, RS_HYBRID_HLLC = 4, RS_AM_HLLC = 5 };
 
 #define AMX_DI __device__ __forceinline__
 
@@ -156,6 +156,15 @@ AMX_DI T absvel_sq(const Gas<T, ND>& s) {
     return a;
 #endif
   }
+}
+
+// get_absolute_velocity itself (|u| in 1-D, sqrt(sum v^2 [+ 1e-20 in 3-D]) otherwise)
+template <typename T, int ND>
+AMX_DI T absvel(const Gas<T, ND>& s) {
+  if constexpr (ND == 1) return rabs(s.q[1]);
+  T a = sq(s.q[1]) + sq(s.q[2]);
+  if constexpr (ND == 3) a = a + sq(s.q[3]) + T(1e-20);
+  return rsqrt_(a);
 }
 
 // _equations.py:253-266: p/(gamma-1) + 0.5*rho*u^2
@@ -383,7 +392,9 @@ AMX_DI Gas<T, ND> hll_flux(const Gas<T, ND>& L, const Gas<T, ND>& R, int ax, con
 
 // _riemann_solver/hll.py:123-261 (HLLC; LM = HLLC-LM low-Mach rescaling of SL, SR in the
 // dissipation term only; the upwind selection tests use the unscaled speeds)
-template <typename T, int ND, bool LM>
+// LMDC: low-Mach dissipation control of AM-HLLC (:230-245): the momentum rows of the dissipation
+// term are scaled by min(1, max(|v_L|/c_L, |v_R|/c_R)).
+template <typename T, int ND, bool LM, bool LMDC = false>
 AMX_DI Gas<T, ND> hllc_flux(const Gas<T, ND>& L, const Gas<T, ND>& R, int ax, const Consts<T>& c) {
   constexpr int P = ND + 1;
   const T rhoL = L.q[0], rhoR = R.q[0], uL = L.q[ax], uR = R.q[ax], pL = L.q[P], pR = R.q[P];
@@ -418,11 +429,17 @@ AMX_DI Gas<T, ND> hllc_flux(const Gas<T, ND>& L, const Gas<T, ND>& R, int ax, co
     SRs = SR * phi;
   }
   const T aS = rabs(Sstar);
+  T fm = T(1);
+  if constexpr (LMDC) {
+    const T aL = absvel(L), aR = absvel(R);
+    fm = rmin(T(1), rmax(rabs(rdiv(aL, cL)), rabs(rdiv(aR, cR))));
+  }
   Gas<T, ND> F;
 #pragma unroll
   for (int k = 0; k < ND + 2; ++k) {
     const T bulk = T(0.5) * (FL.q[k] + FR.q[k]);
-    const T diss = T(0.5) * (SLs * (UsL.q[k] - UL.q[k]) + aS * (UsL.q[k] - UsR.q[k]) + SRs * (UsR.q[k] - UR.q[k]));
+    T diss = T(0.5) * (SLs * (UsL.q[k] - UL.q[k]) + aS * (UsL.q[k] - UsR.q[k]) + SRs * (UsR.q[k] - UR.q[k]));
+    if (LMDC && k >= 1 && k <= ND) diss = fm * diss;
     T f = bulk + diss;
     f = sel_ge0(SL, FL.q[k], f);
     f = sel_le0(SR, FR.q[k], f);
@@ -449,7 +466,18 @@ AMX_DI Gas<T, ND> riemann(const Gas<T, ND>& L, const Gas<T, ND>& R, int ax, T al
   if constexpr (RS == RS_HLL) return hll_flux(L, R, ax, c);
   else if constexpr (RS == RS_HLLC) return hllc_flux<T, ND, false>(L, R, ax, c);
   else if constexpr (RS == RS_HLLC_LM) return hllc_flux<T, ND, true>(L, R, ax, c);
-  else return lf_flux(L, R, ax, alpha, c);
+  else if constexpr (RS == RS_LF) return lf_flux(L, R, ax, alpha, c);
+  else {
+    // hll.py:268-326 HYBRID-HLLC / AM-HLLC: HLLC-LM where the cell on the right of the interface is
+    // being compressed (g = 1, passed in `alpha`), plain HLLC elsewhere
+    constexpr bool AM = RS == RS_AM_HLLC;
+    const Gas<T, ND> Fc = hllc_flux<T, ND, false, AM>(L, R, ax, c);
+    const Gas<T, ND> Fl = hllc_flux<T, ND, true, AM>(L, R, ax, c);
+    Gas<T, ND> F;
+#pragma unroll
+    for (int k = 0; k < ND + 2; ++k) F.q[k] = alpha * Fl.q[k] + (T(1) - alpha) * Fc.q[k];
+    return F;
+  }
 }
 
 // ---------------------------------------------------------------- reconstruction

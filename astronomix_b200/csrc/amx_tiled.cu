@@ -798,6 +798,7 @@ cudaError_t launch_mag(const MagIterArgs& a, cudaStream_t st) {
 // wide; everything else (1-D, tiny grids) stays on the generic kernel.
 bool tiled_stage_supported(const StageArgs& a) {
   if (a.np.lim == LIM_VAN_ALBADA_PP) return false;  // multi-axis limiter: generic kernel (amx_kernels.cu)
+  if (a.np.rs > RS_LF) return false;                 // HYBRID / AM-HLLC need the compression switch of the cell
   if (a.g.nd == 3)
     return a.in.s[2] == 1 && a.out.s[2] == 1 && a.g.n[2] >= tiled::Tile<3>::TZ && a.g.n[1] >= tiled::Tile<3>::TY + 2 &&
            a.g.n[0] >= 4 && (!a.in0.p || a.in0.s[2] == 1);

@@ -42,7 +42,7 @@ extern "C" {
 enum { AMX_F32 = 0, AMX_F64 = 1 };
 enum { AMX_MINMOD = 0, AMX_OSHER = 1, AMX_DOUBLE_MINMOD = 2, AMX_SUPERBEE = 3, AMX_VAN_ALBADA = 4 };
 enum { AMX_UNSPLIT = 0, AMX_SPLIT = 1 };
-enum { AMX_HLL = 0, AMX_HLLC = 1, AMX_HLLC_LM = 2, AMX_LAX_FRIEDRICHS = 3 };
+enum { AMX_HLL = 0, AMX_HLLC = 1, AMX_HLLC_LM = 2, AMX_LAX_FRIEDRICHS = 3, AMX_HYBRID_HLLC = 4, AMX_AM_HLLC = 5 };
 enum { AMX_RK2_SSP = 0, AMX_MUSCL = 1 };
 /* AMX_BC_HALO: the ghost planes on that side exist in memory and were filled by the caller
  * (neighbour rank's cells in a slab decomposition); only valid on axis 0. */

@@ -460,3 +460,24 @@ def test_van_albada_pp_reduces_to_van_albada_on_smooth_data(cuda):
         s = pr.smooth_random(2, 32, seed=3, dtype=np.float64)
         outs.append(ti.integrate_steps(s, config, params, rv, 4, arithmetic=_lib.AMX_ARITH_STRICT))
     assert np.array_equal(outs[0], outs[1])
+
+
+# ---- HYBRID_HLLC / AM_HLLC: HLLC blended with HLLC-LM on a compression sensor ----
+@pytest.mark.parametrize("arith", ["fast", "strict"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("dim,n,rs,bnd,mhd", [
+    (1, 128, oc.HYBRID_HLLC, "open", False), (2, 48, oc.HYBRID_HLLC, "periodic", False),
+    (2, 32, oc.AM_HLLC, "reflective", False), (3, 16, oc.AM_HLLC, "periodic", False),
+    (3, 16, oc.HYBRID_HLLC, "periodic", True)])
+def test_hybrid_and_am_hllc_vs_oracle(cuda, dim, n, rs, bnd, mhd, dtype, arith):
+    """hll.py:268-326: the KH notebook's default solver.  The state has strong compressions (the sensor
+    g = [div v < -0.05 c/dx] is 1 in a sizeable fraction of the cells) and low-Mach regions (AM-HLLC's
+    dissipation control < 1)."""
+    config, params, rv = pr.make(dim, n, mhd=mhd, dtype=dtype, riemann_solver=rs, boundaries=bnd)
+    if dim == 1:
+        s = pr.sod(n, dtype)
+        s[1] = 0.3 * np.sin(2 * np.pi * pr.centers(n)).astype(dtype)
+    else:
+        s = pr.smooth_random(dim, n, mhd=mhd, seed=71 + dim, dtype=dtype, amp=0.6)
+    tol = None if dtype == np.float64 else (2e-5 if arith == "fast" else 2e-6)
+    check(s, config, params, rv, 5, arith, tol=tol)
