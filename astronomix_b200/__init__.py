@@ -8,10 +8,11 @@ from .option_classes import (  # noqa: F401
     HLL, HLLC, HLLC_LM, LAX_FRIEDRICHS, HYBRID_HLLC, AM_HLLC,
     OPEN_BOUNDARY, REFLECTIVE_BOUNDARY, PERIODIC_BOUNDARY, CARTESIAN, CYLINDRICAL, SPHERICAL,
     UNSPLIT, SPLIT, RK2_SSP, MUSCL, GHOST_CELLS, PERIODIC_ROLL, IMPLICIT_MIDPOINT, IMPLICIT_EULER,
-    SINGLE_PRECISION, DOUBLE_PRECISION, FINITE_VOLUME, FINITE_DIFFERENCE, WindParams,
+    SINGLE_PRECISION, DOUBLE_PRECISION, FINITE_VOLUME, FINITE_DIFFERENCE, WindParams, SnapshotSettings,
 )
 from .registered_variables import RegisteredVariables, get_registered_variables  # noqa: F401
 from .helpers import get_helper_data, construct_primitive_state, HelperData  # noqa: F401
 
 
-from .stepping import time_integration  # noqa: F401,E402
+from .stepping import time_integration, StateStruct  # noqa: F401,E402
+from .snapshots import SnapshotData  # noqa: F401,E402

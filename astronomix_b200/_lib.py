@@ -88,6 +88,8 @@ PROTOTYPES = {
     "amx_cfl": (C.c_int, [_D, _P, _P, _P, _P]),
     "amx_step": (C.c_int, [_D, _P, _P, _P, _P, _P, C.POINTER(AmxStats)]),
     "amx_integrate": (C.c_int, [_D, _P, _P, C.c_double, C.c_int64, _P, _P, C.POINTER(AmxStats)]),
+    "amx_integrate_from": (C.c_int, [_D, _P, _P, C.c_double, C.c_double, C.c_double, C.c_int64, _P, _P,
+                                     C.POINTER(AmxStats)]),
     "amx_alpha": (C.c_int, [_D, _P, _P, _P, _P]),
     "amx_dt_from_alpha": (C.c_int, [_D, _P, _P, C.c_double, _P, _P]),
     "amx_hydro_stage": (C.c_int, [_D, _P, _P, _P, _P, C.c_double, _P, _P, _P, _P]),

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <cmath>
 #include <vector>
 
 #include "../../include/amx.h"
@@ -255,6 +256,7 @@ __global__ void finalize_slots_kernel(unsigned long long* slots, double* dst_d, 
 struct DtPar {
   int nd, split, use_max, exact_end;
   double C_cfl, dx, dt_max, t_end;
+  double t_stop;  // the loop also ends once time >= t_stop (no dt clipping against it); +inf: off
 };
 
 // _timestep_estimator.py:118-128 (unsplit) / :131-218 (split), time_integration.py:677-678
@@ -283,7 +285,7 @@ template <typename T>
 __global__ void step_begin_kernel(Ctl* ctl, DtPar p, long long max_steps) {
   if (ctl->done) return;
   const T time = (T)ctl->time_d;
-  if (!(time < (T)p.t_end) || (max_steps >= 0 && ctl->steps >= max_steps)) {
+  if (!(time < (T)p.t_end) || !(time < (T)p.t_stop) || (max_steps >= 0 && ctl->steps >= max_steps)) {
     ctl->done = 1;
     return;
   }
@@ -294,6 +296,13 @@ __global__ void step_begin_kernel(Ctl* ctl, DtPar p, long long max_steps) {
   ctl->mag_iter = 0;
   ctl->mag_fix = 0;
   ctl->final_emitted = 0;
+}
+
+template <typename T>
+__global__ void set_time_kernel(Ctl* ctl, double t0) {
+  const T t = (T)t0;
+  ctl->time_d = (double)t;
+  ctl->time_f = (float)t;
 }
 
 template <typename T>
@@ -618,6 +627,7 @@ struct Engine {
     p.dx = d->dx;
     p.dt_max = is32 ? (double)(float)d->dt_max : d->dt_max;
     p.t_end = is32 ? (double)(float)t_end : t_end;
+    p.t_stop = HUGE_VAL;
     return p;
   }
 
@@ -1053,6 +1063,12 @@ int amx_step(const amx_desc* d, const void* seam_in, void* seam_out, const void*
 
 int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpadded_out, double t_end,
                   int64_t max_steps, void* ws, void* stream, amx_stats* stats) {
+  return amx_integrate_from(d, unpadded_in, unpadded_out, 0.0, HUGE_VAL, t_end, max_steps, ws, stream, stats);
+}
+
+int amx_integrate_from(const amx_desc* d, const void* unpadded_in, void* unpadded_out, double t_start,
+                       double t_stop, double t_end, int64_t max_steps, void* ws, void* stream,
+                       amx_stats* stats) {
   int rc = check_common(d, unpadded_in, unpadded_out);
   if (rc) return rc;
   if (!ws) return fail(AMX_EINVAL, "ws is null");
@@ -1066,7 +1082,13 @@ int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpadded_out
   const View S[2] = {E.internal(L.off_S[0]), E.internal(L.off_S[1])};
   // wave bounds of the initial state (time_integration.py:643-653 on the first pass)
   CK(E.alpha_of(vin, nullptr, false));
-  const DtPar p = E.dtpar(t_end);
+  DtPar p = E.dtpar(t_end);
+  p.t_stop = E.is32 ? (double)(float)t_stop : t_stop;
+  if (t_start != 0.0) {
+    if (E.is32) set_time_kernel<float><<<1, 1, 0, E.st>>>(E.ctl, t_start);
+    else set_time_kernel<double><<<1, 1, 0, E.st>>>(E.ctl, t_start);
+    CK(cudaGetLastError());
+  }
   int kspec = d->dtype == AMX_F32 ? 4 : 8;  // first guess of the evaluations per step
   long long issued = 0;
   const int lookahead = d->mhd ? 1 : 8;  // hydro steps enqueued between host looks at the loop state
@@ -1085,7 +1107,8 @@ int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpadded_out
       CK(cudaGetLastError());
     }
     if ((rc = read_ctl(E, &m))) return rc;
-    if (m->done || !(m->time_d < p.t_end) || (max_steps >= 0 && m->steps >= max_steps)) break;
+    if (m->done || !(m->time_d < p.t_end) || !(m->time_d < p.t_stop) || (max_steps >= 0 && m->steps >= max_steps))
+      break;
   }
   // a step that found the loop finished wrote nothing: the state lives where step `steps` put it
   const long long steps = m->steps;

@@ -54,8 +54,6 @@ def _reject_unsupported(config, registered_variables=None):
         raise NotImplementedError("only CARTESIAN geometry is built (spherical 1-D is out of scope)")
     off = {
         "self_gravity": config.self_gravity,
-        "return_snapshots": config.return_snapshots,
-        "activate_snapshot_callback": config.activate_snapshot_callback,
         "fixed_timestep": config.fixed_timestep,
         "source_term_aware_timestep": config.source_term_aware_timestep,
         "runtime_debugging": config.runtime_debugging,
@@ -133,8 +131,8 @@ def time_integration(primitive_state, config, params, registered_variables: Regi
     global last_info
     _lib.require_device()
     _reject_unsupported(config, registered_variables)
-    if snapshot_callable is not None:
-        raise NotImplementedError("snapshot_callable is not built (SURVEY.md f3)")
+    if config.activate_snapshot_callback and snapshot_callable is None:
+        raise ValueError("activate_snapshot_callback needs a snapshot_callable")
     if sharding is not None:
         raise NotImplementedError(
             "jax shardings do not exist here; multi-GPU runs use astronomix_b200.slab.SlabDriver"
@@ -143,6 +141,16 @@ def time_integration(primitive_state, config, params, registered_variables: Regi
     state = primitive_state.primitive_state if struct else primitive_state
     t, kind = _to_device(state)
     _check_state(t, registered_variables.num_vars, config.dimensionality)
+    if config.return_snapshots or config.activate_snapshot_callback:
+        # snapshots / diagnostics / callback at the reference's snapshot times
+        from .snapshots import integrate_with_snapshots
+        final, data, (steps, time, mag_iters, launches) = integrate_with_snapshots(
+            t, kind, config, params, registered_variables, snapshot_callable, _from_device)
+        last_info = IntegrationInfo(steps, time, 0.0, mag_iters, launches)
+        if data is not None:
+            return data
+        res = _from_device(final, kind)
+        return StateStruct(primitive_state=res) if struct else res
     desc = _lib.make_desc(config, params, t.shape[1:], _TORCH_DTYPES[t.dtype])
     ws, ws_ptr = _workspace(desc, t.device)
     out = torch.empty_like(t)

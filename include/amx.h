@@ -142,6 +142,14 @@ AMX_API int amx_step(const amx_desc* d, const void* seam_in, void* seam_out, con
 AMX_API int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpadded_out, double t_end,
                   int64_t max_steps, void* ws, void* stream, amx_stats* stats_or_null);
 
+/* The same loop resumed at simulation time t_start and also ending (without clipping dt) as soon as
+ * time >= t_stop: the segments between two snapshots of time_integration.py:397-570, whose
+ * snapshot condition `time >= checkpoint * t_end / num_snapshots` is tested at the start of a step.
+ * stats->time is the absolute time reached. */
+AMX_API int amx_integrate_from(const amx_desc* d, const void* unpadded_in, void* unpadded_out, double t_start,
+                  double t_stop, double t_end, int64_t max_steps, void* ws, void* stream,
+                  amx_stats* stats_or_null);
+
 /* ---- slab-decomposed building blocks (multi-GPU driver, astronomix_b200/slab.py) --------
  * The local slab is [rows][n[0] + 2*num_ghost][n[1]][n[2]] with desc->bc[0] = {HALO, HALO};
  * the caller exchanges the x ghost planes (NCCL send/recv) before each call that reads them. */

@@ -749,6 +749,60 @@ def time_integration(s0, o, max_steps=None, return_info=False, checkpoint_at=Non
     return out
 
 
+# ------------------------------------------------------------------ snapshots and totals (row f3)
+def total_quantities(s, o, box_size, gamma, centers=None):
+    """_fluid_equations/total_quantities.py:31-176 on an unpadded state (Cartesian; gas energy only;
+    total mass in 2-D / 3-D is sum(rho) * box_size**dim, as the reference writes it)."""
+    t = s.dtype.type
+    dim, dx = o.dim, o.grid_spacing
+    u = get_absolute_velocity(s, o)
+    rho, p = s[o.rho_i], s[o.p_i]
+    vol = (dx * np.ones_like(rho)) if dim == 1 else dx ** dim
+    q = {"total_mass": np.sum(rho * vol) if dim == 1 else np.sum(rho) * box_size ** dim,
+         "internal_energy": np.sum(p / (gamma - 1) * vol),
+         "kinetic_energy": np.sum(t(0.5) * rho * u ** 2 * vol),
+         "total_energy": np.sum(total_energy_from_primitives(rho, u, p, gamma) * vol)}
+    if centers is not None:
+        d = centers - box_size / 2
+        r_hat = d / np.linalg.norm(d, axis=-1, keepdims=True)
+        uu = s[1] if dim == 1 else s[1:1 + dim]
+        u_radial = np.sum(np.moveaxis(uu, 0, -1) * r_hat, axis=-1)
+        q["radial_momentum"] = np.sum(rho * u_radial * vol)
+    if o.mhd and dim == 3:
+        q["magnetic_divergence"] = np.max(np.abs(divergence(s[-3:], dx, 3)))
+    return {k: t(v) for k, v in q.items()}
+
+
+def time_integration_snapshots(s0, o, num_snapshots, box_size=1.0, centers=None):
+    """time_integration.py:397-570, :628-737: the adaptive loop with a snapshot at the START of every
+    step whose time has reached ``current_checkpoint * t_end / num_snapshots`` (one per step at most).
+    Returns (final unpadded state, dict of time_points / states / totals, number of steps)."""
+    t_ = s0.dtype.type
+    gamma, C_cfl, dt_max, t_end = t_(o.gamma), t_(o.C_cfl), t_(o.dt_max), t_(o.t_end)
+    s = prepare_state(s0, o)
+    time, cp, steps = t_(0.0), 0, 0
+    rec = {"time_points": np.zeros(num_snapshots, dtype=s0.dtype), "states": np.zeros((num_snapshots,) + s0.shape,
+                                                                                    dtype=s0.dtype)}
+    while time < t_end:
+        if time >= t_(t_(cp) * t_end) / t_(num_snapshots):
+            if cp < num_snapshots:
+                u = unpad(s, o) if o.boundary_handling == GHOST_CELLS else s
+                rec["time_points"][cp] = time
+                rec["states"][cp] = u
+                for k, v in total_quantities(u, o, box_size, gamma, centers).items():
+                    rec.setdefault(k, np.zeros(num_snapshots, dtype=s0.dtype))[cp] = v
+            cp += 1
+        dt = t_(cfl_time_step(s, o, gamma, C_cfl, dt_max))
+        if o.exact_end_time:
+            dt = min(dt, t_end - time)
+        s = evolve_state_fv(s, dt, gamma, o)
+        time = t_(time + dt)
+        steps += 1
+    out = unpad(s, o) if o.boundary_handling == GHOST_CELLS else s
+    rec["current_checkpoint"] = cp
+    return out, rec, steps
+
+
 def resume_padded(s_padded, time, o, max_steps=None):
     """Continue the loop of ``time_integration`` from a recorded padded state and time."""
     t_ = s_padded.dtype.type

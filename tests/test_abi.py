@@ -52,7 +52,9 @@ def test_workspace_query_and_validation():
     assert lib.amx_workspace_bytes(C.byref(d), C.byref(n)) == 2
     assert b"num_ghost" in lib.amx_last_error()
     d = _desc()
-    d.riemann = oc.HYBRID_HLLC
+    d.riemann = oc.HYBRID_HLLC  # built for the unsplit scheme only
+    assert lib.amx_workspace_bytes(C.byref(d), C.byref(n)) == 0
+    d.split, d.time_integrator = oc.SPLIT, oc.MUSCL
     assert lib.amx_workspace_bytes(C.byref(d), C.byref(n)) == 2
     d = _desc()
     d.abi_version = 99

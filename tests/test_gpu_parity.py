@@ -481,3 +481,57 @@ def test_hybrid_and_am_hllc_vs_oracle(cuda, dim, n, rs, bnd, mhd, dtype, arith):
         s = pr.smooth_random(dim, n, mhd=mhd, seed=71 + dim, dtype=dtype, amp=0.6)
     tol = None if dtype == np.float64 else (2e-5 if arith == "fast" else 2e-6)
     check(s, config, params, rv, 5, arith, tol=tol)
+
+
+# ---- snapshots / diagnostics / callback ----
+@pytest.mark.parametrize("dim,n,mhd,dtype,t_end,ns", [
+    (2, 32, True, np.float64, 0.05, 5), (3, 16, True, np.float32, 0.03, 4), (1, 101, False, np.float64, 0.2, 7),
+    (2, 32, False, np.float32, 0.04, 40)])
+def test_snapshots_and_totals_vs_oracle(cuda, dim, n, mhd, dtype, t_end, ns):
+    """time_integration(return_snapshots=True): snapshot times (taken at the start of the first step
+    past k * t_end / num_snapshots, one per step: with 40 snapshots several are never taken), states,
+    totals and the final state against the oracle's restatement."""
+    st = ax.SnapshotSettings(return_states=True, return_final_state=True, return_total_mass=True,
+                             return_total_energy=True, return_internal_energy=True, return_kinetic_energy=True,
+                             return_radial_momentum=dim > 1, return_magnetic_divergence=mhd and dim == 3)
+    bnd = "open" if dim == 1 else "periodic"
+    config, params, rv = pr.make(dim, n, mhd=mhd, dtype=dtype, boundaries=bnd, return_snapshots=True,
+                                 num_snapshots=ns, snapshot_settings=st)
+    params = params._replace(t_end=t_end)
+    s = pr.sod(n, dtype) if dim == 1 else pr.smooth_random(dim, n, mhd=mhd, seed=5, dtype=dtype)
+    data = ax.time_integration(s, config, params, rv)
+    assert isinstance(data, ax.SnapshotData)
+    o = fo.Opts.from_config(config, params)
+    centers = ax.get_helper_data(config, dtype=dtype).geometric_centers if dim > 1 else None
+    ref, rec, steps = fo.time_integration_snapshots(s, o, ns, box_size=config.box_size, centers=centers)
+    tol = 1e-11 if dtype == np.float64 else 2e-5
+    assert data.num_iterations == steps and data.current_checkpoint == rec["current_checkpoint"]
+    np.testing.assert_allclose(data.time_points, rec["time_points"], rtol=tol, atol=0)
+    assert pr.rel_l1(data.final_state, ref, dim, mhd) <= tol
+    for k in range(ns):
+        if rec["time_points"][k] > 0 or k == 0:
+            assert pr.rel_l1(data.states[k], rec["states"][k], dim, mhd) <= tol
+    for name in ("total_mass", "total_energy", "internal_energy", "kinetic_energy"):
+        np.testing.assert_allclose(getattr(data, name), rec[name], rtol=max(tol, 1e-5 if dtype == np.float32 else 0))
+    if dim > 1:
+        scale = np.abs(rec["kinetic_energy"]).max()
+        np.testing.assert_allclose(data.radial_momentum, rec["radial_momentum"], atol=1e-4 * scale, rtol=1e-4)
+    if mhd and dim == 3:
+        np.testing.assert_allclose(data.magnetic_divergence, rec["magnetic_divergence"],
+                                   rtol=1e-3, atol=1e-5 * np.abs(s[-3:]).max() * n)
+
+
+def test_snapshot_callback(cuda):
+    """activate_snapshot_callback: the callable is invoked at the snapshot times with the device state."""
+    seen = []
+    config, params, rv = pr.make(2, 32, dtype=np.float64, activate_snapshot_callback=True, num_snapshots=3)
+    params = params._replace(t_end=0.03)
+    s = pr.smooth_random(2, 32, seed=6, dtype=np.float64)
+    out = ax.time_integration(s, config, params, rv,
+                              snapshot_callable=lambda t, state, r: seen.append((t, float(state[0].sum()))))
+    o = fo.Opts.from_config(config, params)
+    ref, rec, steps = fo.time_integration_snapshots(s, o, 3)
+    assert pr.rel_l1(out, ref, 2, False) <= 1e-12
+    taken = [t for t in rec["time_points"][: rec["current_checkpoint"]]]
+    assert len(seen) == rec["current_checkpoint"]
+    np.testing.assert_allclose([t for t, _ in seen], taken, rtol=1e-12)

@@ -159,3 +159,25 @@ def test_van_albada_pp_keeps_interface_states_positive():
         b = fo.time_integration(smooth, fo.Opts.from_config(
             *pr.make(dim, n, dtype=np.float64, riemann_solver=oc.LAX_FRIEDRICHS, limiter=oc.VAN_ALBADA)[:2]), max_steps=2)
         assert np.array_equal(a, b)
+
+
+def test_snapshot_schedule_of_the_oracle():
+    """time_integration.py:397-570: one snapshot per step at most, taken at the start of the first step
+    whose time has reached k * t_end / N; checkpoints the loop never reaches stay zero."""
+    import numpy as np
+    from astronomix_b200 import problems as pr
+    from oracle import fv_oracle as fo
+    c, p, _ = pr.make(2, 16, mhd=True, dtype=np.float64)
+    p = p._replace(t_end=0.02)
+    o = fo.Opts.from_config(c, p)
+    s = pr.smooth_random(2, 16, mhd=True, seed=1, dtype=np.float64)
+    out, rec, steps = fo.time_integration_snapshots(s, o, 4)
+    assert np.array_equal(out, fo.time_integration(s, o))           # snapshots do not change the run
+    assert steps == 3 and rec["current_checkpoint"] == 3            # 3 steps -> at most 3 snapshots
+    tp = rec["time_points"]
+    assert tp[0] == 0 and tp[3] == 0 and np.all(np.diff(tp[:3]) > 0)
+    for k in range(1, 3):
+        assert tp[k] >= k * 0.02 / 4
+    assert np.allclose(rec["total_mass"][:3], rec["total_mass"][0], rtol=1e-13)  # periodic: mass conserved
+    out2, rec2, steps2 = fo.time_integration_snapshots(s, o, 40)     # more snapshots than steps
+    assert steps2 == 3 and rec2["current_checkpoint"] == 3 and np.count_nonzero(rec2["time_points"]) == 2
