@@ -1,0 +1,168 @@
+"""Turbulent driving: solenoidal random forcing added to the velocity once per step.
+
+Reference: _physics_modules/_turbulent_forcing/_turbulent_forcing.py:15-125 and its call site
+time_stepping/time_integration.py:699-711 (after dt is known, before the finite-volume step; 3-D,
+PERIODIC_ROLL layout, cubic box).  Per step: complex Gaussian noise with power spectrum
+``k^6 exp(-8 k / k_peak)``, ``k_peak = 4 pi / L``, the DC mode and the compressive part projected
+out, three inverse FFTs (cuFFT through torch.fft: library plumbing, the finite-volume step stays in
+libamx), and an amplitude that injects ``energy_injection_rate * dt`` of kinetic energy (the root of
+a quadratic in two global sums).
+
+The random stream is torch's (``torch.Generator`` seeded with 42, the number the reference seeds
+``jax.random.key`` with): the fields have the reference's statistics, not its bits -- jax is not
+installable here, so its Threefry / erfinv stream cannot be pinned.  The arithmetic after the noise
+is restated in ``oracle/fv_oracle.py`` (``forcing_field``, ``apply_forcing``) and compared on
+identical noise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import option_classes as oc
+
+
+class ForcingNoise:
+    """(3, n, n, n) complex standard-normal noise per step: real and imaginary part drawn separately"""
+
+    def __init__(self, n, dtype, device, seed=42):
+        self.shape, self.dtype, self.device = (3, n, n, n), dtype, device
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed)
+
+    def __call__(self, step):
+        re = torch.randn(self.shape, dtype=self.dtype, device=self.device, generator=self.gen)
+        im = torch.randn(self.shape, dtype=self.dtype, device=self.device, generator=self.gen)
+        return torch.complex(re, im)
+
+
+class Forcing:
+    def __init__(self, config, params, registered_variables, dtype, device):
+        if config.dimensionality != 3:
+            raise ValueError("turbulent forcing needs a 3-D grid")
+        if config.boundary_handling != oc.PERIODIC_ROLL:
+            raise ValueError("turbulent forcing needs boundary_handling=PERIODIC_ROLL (unpadded state)")
+        n, L = config.num_cells, config.box_size
+        self.rv = registered_variables
+        self.edot = float(params.turbulent_forcing_params.energy_injection_rate)
+        self.dV = config.grid_spacing ** 3
+        k1 = (2.0 * math.pi * torch.fft.fftfreq(n, d=L / n, dtype=dtype, device=device))
+        self.kx, self.ky, self.kz = k1.reshape(n, 1, 1), k1.reshape(1, n, 1), k1.reshape(1, 1, n)
+        self.k2 = self.kx ** 2 + self.ky ** 2 + self.kz ** 2
+        kk = torch.sqrt(self.k2)
+        kpk = 4.0 * math.pi / L
+        self.sqrtP = torch.sqrt(kk ** 6 * torch.exp(-8.0 * kk / kpk))
+        self.k2_safe = torch.where(self.k2 == 0.0, torch.ones_like(self.k2), self.k2)
+
+    def field(self, noise):
+        """_create_forcing_field: real solenoidal field (3, n, n, n) from the complex noise"""
+        cw = [self.sqrtP * noise[i] for i in range(3)]
+        for c in cw:
+            c[0, 0, 0] = 0.0
+        div_k = (self.kx * cw[0] + self.ky * cw[1] + self.kz * cw[2]) / self.k2_safe
+        div_k[0, 0, 0] = 0.0
+        cw = [cw[0] - self.kx * div_k, cw[1] - self.ky * div_k, cw[2] - self.kz * div_k]
+        return [torch.fft.ifftn(c).real for c in cw]
+
+    def apply(self, state, dt, noise):
+        """_apply_forcing: state (device, unpadded) gets amp * w added to its velocity rows; dt is a
+        0-d device tensor.  No host synchronisation."""
+        w = self.field(noise)
+        rv = self.rv
+        rho = state[rv.density_index]
+        v = [state[rv.velocity_index.x], state[rv.velocity_index.y], state[rv.velocity_index.z]]
+        tempa = 0.5 * torch.sum(rho * (w[0] ** 2 + w[1] ** 2 + w[2] ** 2))
+        tempb = torch.sum(rho * v[0] * w[0] + rho * v[1] * w[1] + rho * v[2] * w[2])
+        tempc = -self.edot * dt / self.dV
+        disc = tempb ** 2 - 4.0 * tempa * tempc
+        ok = (disc >= 0) & (tempa.abs() > 1e-10)
+        amp = torch.where(ok, (-tempb + torch.sqrt(torch.clamp(disc, min=0))) / (2.0 * tempa), torch.zeros_like(tempa))
+        for i in range(3):
+            v[i].add_(amp * w[i])
+        return state
+
+
+def integrate_per_step(t, kind, config, params, registered_variables, snapshot_callable, from_device,
+                       noise_fn=None):
+    """The reference's loop body one step at a time (time_integration.py:397-737) for runs that touch
+    the state between dt and the step: [snapshot / callback] -> dt = CFL, clipped to t_end -> forcing
+    -> finite-volume step -> t += dt.  dt and t stay on the device; the host reads t once per step
+    for the loop condition."""
+    from .snapshots import Diagnostics, SnapshotData
+    if config.use_specific_snapshot_timepoints:
+        raise NotImplementedError("use_specific_snapshot_timepoints is not built")
+    lib = _lib.load()
+    tdt = t.dtype
+    npdt = np.float32 if tdt == torch.float32 else np.float64
+    code = _lib.AMX_F32 if tdt == torch.float32 else _lib.AMX_F64
+    desc = _lib.make_desc(config, params, t.shape[1:], code)
+    nbytes = C.c_size_t()
+    _lib.check(lib.amx_workspace_bytes(C.byref(desc), C.byref(nbytes)))
+    ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=t.device)
+    ws_ptr = C.c_void_p((ws.data_ptr() + 255) & ~255)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    forced = config.turbulent_forcing_config.turbulent_forcing
+    forcing = Forcing(config, params, registered_variables, tdt, t.device) if forced else None
+    if forcing is not None and noise_fn is None:
+        noise_fn = ForcingNoise(config.num_cells, tdt, t.device)
+    snaps, cb = config.return_snapshots, config.activate_snapshot_callback
+    st, N = config.snapshot_settings, int(config.num_snapshots)
+    diag = Diagnostics(config, params, registered_variables, tdt, t.device) if snaps else None
+    want = {}
+    if snaps:
+        want = {"total_mass": st.return_total_mass, "total_energy": st.return_total_energy,
+                "internal_energy": st.return_internal_energy, "kinetic_energy": st.return_kinetic_energy,
+                "radial_momentum": st.return_radial_momentum,
+                "magnetic_divergence": st.return_magnetic_divergence and config.mhd}
+    series = {k: torch.zeros(N, dtype=tdt, device=t.device) for k, v in want.items() if v}
+    time_points = np.zeros(N, dtype=npdt)
+    states = torch.zeros((N,) + tuple(t.shape), dtype=tdt, device=t.device) if snaps and st.return_states else None
+    cur, nxt = t.clone(), torch.empty_like(t)
+    dt = torch.zeros((), dtype=tdt, device=t.device)
+    time_dev = torch.zeros((), dtype=tdt, device=t.device)
+    t_end_dev = torch.tensor(params.t_end, dtype=tdt, device=t.device)
+    t_end = npdt(params.t_end)
+    time, cp, steps, launches, mag_iters = npdt(0.0), 0, 0, 0, 0
+    stats = _lib.AmxStats()
+    while time < t_end:
+        if (snaps or cb) and time >= npdt(npdt(cp) * t_end) / npdt(N):
+            if snaps and cp < N:
+                time_points[cp] = time
+                if states is not None:
+                    states[cp].copy_(cur)
+                for k in series:
+                    series[k][cp] = getattr(diag, k)(cur)
+            elif cb:
+                snapshot_callable(float(time), cur, registered_variables)
+            cp += 1
+        with torch.cuda.device(t.device):
+            _lib.check(lib.amx_cfl(C.byref(desc), C.c_void_p(cur.data_ptr()), C.c_void_p(dt.data_ptr()), ws_ptr, stream))
+            if config.exact_end_time:
+                torch.minimum(dt, t_end_dev - time_dev, out=dt)
+            if forcing is not None:
+                forcing.apply(cur, dt, noise_fn(steps))
+            _lib.check(lib.amx_step(C.byref(desc), C.c_void_p(cur.data_ptr()), C.c_void_p(nxt.data_ptr()),
+                                    C.c_void_p(dt.data_ptr()), ws_ptr, stream, C.byref(stats)))
+        time_dev.add_(dt)
+        cur, nxt = nxt, cur
+        time = npdt(time_dev.item())
+        steps += 1
+        launches += stats.kernel_launches + 3
+        mag_iters += stats.magnetic_iterations
+    info = (steps, float(time), mag_iters, launches)
+    if not snaps:
+        return cur, None, info
+    out = {k: v.cpu().numpy() for k, v in series.items()}
+    data = SnapshotData(
+        time_points=time_points, states=None if states is None else from_device(states, kind),
+        final_state=from_device(cur, kind) if st.return_final_state else None,
+        total_mass=out.get("total_mass"), total_energy=out.get("total_energy"),
+        internal_energy=out.get("internal_energy"), kinetic_energy=out.get("kinetic_energy"),
+        gravitational_energy=None, radial_momentum=out.get("radial_momentum"),
+        magnetic_divergence=out.get("magnetic_divergence"), runtime=0.0, num_iterations=steps,
+        current_checkpoint=cp)
+    return cur, data, info

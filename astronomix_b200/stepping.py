@@ -57,7 +57,6 @@ def _reject_unsupported(config, registered_variables=None):
         "fixed_timestep": config.fixed_timestep,
         "source_term_aware_timestep": config.source_term_aware_timestep,
         "runtime_debugging": config.runtime_debugging,
-        "turbulent_forcing": config.turbulent_forcing_config.turbulent_forcing,
         "stellar_wind": config.wind_config.stellar_wind,
         "cosmic_rays": config.cosmic_ray_config.cosmic_rays,
         "cooling": config.cooling_config.cooling,
@@ -141,10 +140,16 @@ def time_integration(primitive_state, config, params, registered_variables: Regi
     state = primitive_state.primitive_state if struct else primitive_state
     t, kind = _to_device(state)
     _check_state(t, registered_variables.num_vars, config.dimensionality)
-    if config.return_snapshots or config.activate_snapshot_callback:
-        # snapshots / diagnostics / callback at the reference's snapshot times
-        from .snapshots import integrate_with_snapshots
-        final, data, (steps, time, mag_iters, launches) = integrate_with_snapshots(
+    forced = config.turbulent_forcing_config.turbulent_forcing
+    if forced or config.return_snapshots or config.activate_snapshot_callback:
+        # snapshots / diagnostics / callback at the reference's snapshot times: segments of
+        # the device-resident loop; with turbulent driving (f1) the state is touched between dt and the
+        # step, so the loop body runs one step at a time
+        if forced:
+            from .forcing import integrate_per_step as run
+        else:
+            from .snapshots import integrate_with_snapshots as run
+        final, data, (steps, time, mag_iters, launches) = run(
             t, kind, config, params, registered_variables, snapshot_callable, _from_device)
         last_info = IntegrationInfo(steps, time, 0.0, mag_iters, launches)
         if data is not None:

@@ -803,6 +803,63 @@ def time_integration_snapshots(s0, o, num_snapshots, box_size=1.0, centers=None)
     return out, rec, steps
 
 
+# ------------------------------------------------------------------ turbulent driving (row f1)
+def forcing_field(noise, n, box_size):
+    """_turbulent_forcing.py:15-82 from the complex noise (3, n, n, n): spectrum k^6 exp(-8 k / k_peak),
+    DC mode removed, compressive part projected out, real part of the inverse FFT."""
+    k1 = 2.0 * np.pi * np.fft.fftfreq(n, d=box_size / n).astype(noise.real.dtype)
+    kx, ky, kz = k1.reshape(n, 1, 1), k1.reshape(1, n, 1), k1.reshape(1, 1, n)
+    k2 = kx ** 2 + ky ** 2 + kz ** 2
+    kk = np.sqrt(k2)
+    kpk = 4.0 * np.pi / box_size
+    sqrtP = np.sqrt(kk ** 6 * np.exp(-8.0 * kk / kpk))
+    cw = [sqrtP * noise[i] for i in range(3)]
+    for c in cw:
+        c[0, 0, 0] = 0.0
+    k2_safe = np.where(k2 == 0.0, 1.0, k2)
+    div_k = (kx * cw[0] + ky * cw[1] + kz * cw[2]) / k2_safe
+    div_k[0, 0, 0] = 0.0
+    cw = [cw[0] - kx * div_k, cw[1] - ky * div_k, cw[2] - kz * div_k]
+    return [np.real(np.fft.ifftn(c)).astype(noise.real.dtype) for c in cw]
+
+
+def apply_forcing(s, dt, noise, energy_injection_rate, o, box_size):
+    """_turbulent_forcing.py:84-125: amp from a*amp^2 + b*amp + c = 0 with c = -Edot dt / dV."""
+    t = s.dtype.type
+    n = s.shape[-1]
+    w = forcing_field(noise, n, box_size)
+    dV = o.grid_spacing ** 3
+    rho, v = s[o.rho_i], s[1:4]
+    tempa = t(0.5) * np.sum(rho * (w[0] ** 2 + w[1] ** 2 + w[2] ** 2))
+    tempb = np.sum(rho * v[0] * w[0] + rho * v[1] * w[1] + rho * v[2] * w[2])
+    tempc = t(-energy_injection_rate * dt / dV)
+    disc = tempb ** 2 - t(4.0) * tempa * tempc
+    amp = (-tempb + np.sqrt(disc)) / (t(2.0) * tempa) if (disc >= 0 and abs(tempa) > 1e-10) else t(0.0)
+    out = s.copy()
+    for i in range(3):
+        out[1 + i] = s[1 + i] + t(amp) * w[i]
+    return out
+
+
+def time_integration_forced(s0, o, noises, energy_injection_rate, box_size=1.0):
+    """time_integration.py:628-737 with turbulent_forcing: dt from the unforced state (clipped to
+    t_end), forcing with that dt, finite-volume step.  ``noises[k]`` is the noise of step k; the
+    loop stops when they run out.  PERIODIC_ROLL only (the reference's shapes require it)."""
+    assert o.boundary_handling == PERIODIC_ROLL and o.dim == 3
+    t_ = s0.dtype.type
+    gamma, C_cfl, dt_max, t_end = t_(o.gamma), t_(o.C_cfl), t_(o.dt_max), t_(o.t_end)
+    s, time, steps = np.ascontiguousarray(s0), t_(0.0), 0
+    while time < t_end and steps < len(noises):
+        dt = t_(cfl_time_step(s, o, gamma, C_cfl, dt_max))
+        if o.exact_end_time:
+            dt = min(dt, t_end - time)
+        s = apply_forcing(s, dt, noises[steps], energy_injection_rate, o, box_size)
+        s = evolve_state_fv(s, dt, gamma, o)
+        time = t_(time + dt)
+        steps += 1
+    return s, steps, float(time)
+
+
 def resume_padded(s_padded, time, o, max_steps=None):
     """Continue the loop of ``time_integration`` from a recorded padded state and time."""
     t_ = s_padded.dtype.type

@@ -1,0 +1,64 @@
+"""Turbulent driving: the torch implementation against the NumPy restatement on
+identical noise, and the two properties the construction promises (solenoidal field, prescribed
+kinetic-energy injection).  CPU tensors here; the GPU loop is in test_gpu_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+import astronomix_b200 as ax
+from astronomix_b200 import option_classes as oc, problems as pr
+from astronomix_b200.forcing import Forcing, ForcingNoise
+from oracle import fv_oracle as fo
+
+
+def _setup(n=16, dtype=np.float64, mhd=True):
+    config, params, rv = pr.make(3, n, mhd=mhd, dtype=dtype, boundary_handling=oc.PERIODIC_ROLL,
+                                 turbulent_forcing_config=oc.TurbulentForcingConfig(turbulent_forcing=True))
+    s = pr.smooth_random(3, n, mhd=mhd, seed=9, dtype=dtype)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    return config, params, rv, s, tdt
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-5)])
+def test_forcing_matches_oracle_on_identical_noise(dtype, tol):
+    config, params, rv, s, tdt = _setup(dtype=dtype)
+    f = Forcing(config, params, rv, tdt, torch.device("cpu"))
+    noise = ForcingNoise(16, tdt, torch.device("cpu"))(0)
+    w = f.field(noise.clone())
+    w_ref = fo.forcing_field(noise.numpy().copy(), 16, config.box_size)
+    scale = max(np.abs(x).max() for x in w_ref)
+    for a, b in zip(w, w_ref):
+        assert np.abs(a.numpy() - b).max() <= tol * scale
+    dt = 1.0e-3
+    forced = f.apply(torch.from_numpy(s.copy()), torch.tensor(dt, dtype=tdt), noise.clone()).numpy()
+    o = fo.Opts.from_config(config, params)
+    ref = fo.apply_forcing(s, dtype(dt), noise.numpy().copy(), params.turbulent_forcing_params.energy_injection_rate,
+                           o, config.box_size)
+    assert pr.rel_l1(forced, ref, 3, True) <= tol
+    assert np.array_equal(forced[0], s[0]) and np.array_equal(forced[4:], s[4:])  # only the velocity rows change
+
+
+def test_forcing_field_is_solenoidal_and_injects_the_prescribed_energy():
+    config, params, rv, s, tdt = _setup(n=24)
+    f = Forcing(config, params, rv, tdt, torch.device("cpu"))
+    noise = ForcingNoise(24, tdt, torch.device("cpu"), seed=3)(0)
+    w = f.field(noise.clone())
+    div = sum(k * torch.fft.fftn(c) for k, c in zip((f.kx, f.ky, f.kz), w))
+    spec = sum(torch.fft.fftn(c).abs().max() for c in w)
+    # exact up to the Nyquist planes (taking the real part pairs k with -k, and fftfreq has only -k_Ny),
+    # where the spectrum k^6 exp(-8 k / k_peak) is ~1e-8 of its peak
+    assert div.abs().max() <= 1e-6 * spec * f.kx.abs().max()
+    assert all(abs(float(c.mean())) < 1e-12 * float(c.abs().max()) for c in w)          # no DC mode
+    dt = 2.0e-3
+    st = torch.from_numpy(s.copy())
+    ek0 = 0.5 * (st[0] * (st[1] ** 2 + st[2] ** 2 + st[3] ** 2)).sum() * f.dV
+    forced = f.apply(st, torch.tensor(dt, dtype=tdt), noise.clone())
+    ek1 = 0.5 * (forced[0] * (forced[1] ** 2 + forced[2] ** 2 + forced[3] ** 2)).sum() * f.dV
+    edot = params.turbulent_forcing_params.energy_injection_rate
+    assert abs(float(ek1 - ek0) - edot * dt) <= 1e-10 * edot * dt + 1e-14
+
+
+def test_forcing_needs_periodic_roll_3d():
+    config, params, rv = pr.make(3, 16, mhd=True, dtype=np.float64)   # GHOST_CELLS
+    with pytest.raises(ValueError):
+        Forcing(config, params, rv, torch.float64, torch.device("cpu"))

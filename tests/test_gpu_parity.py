@@ -535,3 +535,50 @@ def test_snapshot_callback(cuda):
     taken = [t for t in rec["time_points"][: rec["current_checkpoint"]]]
     assert len(seen) == rec["current_checkpoint"]
     np.testing.assert_allclose([t for t, _ in seen], taken, rtol=1e-12)
+
+
+# ---- turbulent driving ----
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 2e-5)])
+def test_driven_turbulence_loop_vs_oracle(cuda, dtype, tol):
+    """dt from the unforced state -> forcing with that dt -> MHD step, 4 steps on identical noise
+    (the noise is drawn on the device and handed to the oracle)."""
+    import torch
+    from astronomix_b200 import forcing as fm
+    n = 16
+    tf = oc.TurbulentForcingConfig(turbulent_forcing=True)
+    config, params, rv = pr.make(3, n, mhd=True, dtype=dtype, boundary_handling=oc.PERIODIC_ROLL,
+                                 turbulent_forcing_config=tf)
+    params = params._replace(t_end=1.0e9)
+    s = pr.smooth_random(3, n, mhd=True, seed=12, dtype=dtype)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    gen = fm.ForcingNoise(n, tdt, cuda, seed=42)
+    noises = [gen(k) for k in range(4)]
+
+    def noise_fn(step):
+        return noises[step].clone()
+
+    # the oracle runs as many steps as there are noise fields; the device loop is then given the time
+    # the oracle reached as t_end (its last dt is clipped to the same value to within an ulp)
+    ref, steps, time = fo.time_integration_forced(s, fo.Opts.from_config(config, params),
+                                                  [x.cpu().numpy() for x in noises],
+                                                  params.turbulent_forcing_params.energy_injection_rate,
+                                                  config.box_size)
+    assert steps == 4
+    params_end = params._replace(t_end=time)
+    final, _, info = fm.integrate_per_step(torch.from_numpy(s).to(cuda), "torch_cuda", config, params_end, rv, None,
+                                           ti._from_device, noise_fn=noise_fn)
+    assert info[0] == 4
+    assert pr.rel_l1(final.cpu().numpy(), ref, 3, True) <= tol
+
+
+def test_driven_turbulence_through_time_integration(cuda):
+    """The public call with turbulent_forcing on: runs, stays finite, injects kinetic energy."""
+    tf = oc.TurbulentForcingConfig(turbulent_forcing=True)
+    config, params, rv = pr.make(3, 32, mhd=True, boundary_handling=oc.PERIODIC_ROLL, turbulent_forcing_config=tf)
+    params = params._replace(t_end=0.02)
+    s = np.zeros((8, 32, 32, 32), dtype=np.float32)
+    s[0], s[4], s[5] = 0.5, 0.1, 0.05
+    out = ax.time_integration(s, config, params, rv)
+    assert np.isfinite(out).all() and ti.last_info.steps > 1
+    ek = 0.5 * (out[0] * (out[1:4] ** 2).sum(axis=0)).sum() * config.grid_spacing ** 3
+    assert 0.2 * 2.0 * 0.02 < ek <= 2.0 * 0.02 * 1.001     # at most Edot * t, part of it already thermalised
