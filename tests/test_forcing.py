@@ -62,3 +62,26 @@ def test_forcing_needs_periodic_roll_3d():
     config, params, rv = pr.make(3, 16, mhd=True, dtype=np.float64)   # GHOST_CELLS
     with pytest.raises(ValueError):
         Forcing(config, params, rv, torch.float64, torch.device("cpu"))
+
+
+@pytest.mark.parametrize("dim,n,mhd", [(1, 64, False), (2, 24, True), (3, 12, True)])
+def test_snapshot_totals_match_oracle(dim, n, mhd):
+    """snapshots.Diagnostics (torch reductions, here on CPU tensors) against the oracle's
+    total_quantities (total_quantities.py:31-176, incl. the box_size**dim factor of the total mass)."""
+    from astronomix_b200.snapshots import Diagnostics
+    bnd = "open" if dim == 1 else "periodic"
+    config, params, rv = pr.make(dim, n, mhd=mhd, dtype=np.float64, boundaries=bnd, box=1.5, return_snapshots=True)
+    s = pr.sod(n, np.float64) if dim == 1 else pr.smooth_random(dim, n, mhd=mhd, seed=4, dtype=np.float64)
+    d = Diagnostics(config, params, rv, torch.float64, torch.device("cpu"))
+    centers = ax.get_helper_data(config, dtype=np.float64).geometric_centers
+    ref = fo.total_quantities(s, fo.Opts.from_config(config, params), config.box_size, np.float64(params.gamma),
+                              centers if dim > 1 else None)
+    st = torch.from_numpy(s)
+    for name in ("total_mass", "total_energy", "internal_energy", "kinetic_energy"):
+        assert abs(float(getattr(d, name)(st)) - ref[name]) <= 1e-12 * abs(ref[name])
+    if dim > 1:
+        assert abs(float(d.radial_momentum(st)) - ref["radial_momentum"]) <= 1e-12 * ref["kinetic_energy"]
+    if mhd and dim == 3:
+        assert abs(float(d.magnetic_divergence(st)) - ref["magnetic_divergence"]) <= 1e-12 * abs(ref["magnetic_divergence"])
+    if dim > 1:
+        assert abs(ref["total_mass"] - s[0].sum() * 1.5 ** dim) <= 1e-12 * ref["total_mass"]
