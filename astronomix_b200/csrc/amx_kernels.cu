@@ -17,6 +17,8 @@
 #include "amx_internal.h"
 #include "amx_math.cuh"
 
+#include <algorithm>
+
 #if AMX_STRICT
 #define AMX_NS amx_strict
 #else
@@ -84,8 +86,8 @@ AMX_DI Gas<T, ND> load_neighbor(const View& v, const Geom& g, const Idx3& c, int
 }
 
 template <int ND>
-AMX_DI bool decode_cell(const Geom& g, Idx3& c) {
-  const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+AMX_DI bool decode_cell(const Geom& g, Idx3& c, long long lin = -1) {
+  if (lin < 0) lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = g.n[0];
   if constexpr (ND > 1) total *= g.n[1];
   if constexpr (ND > 2) total *= g.n[2];
@@ -555,17 +557,22 @@ __global__ void __launch_bounds__(256) mag_iter_kernel(const MagIterArgs a) {
 // _magnetic_field_update.py:208-240 (gamma hard-coded 5/3, Q4; 2-D drops v_z, Q5)
 template <typename T, int ND>
 __global__ void __launch_bounds__(256) mag_final_kernel(const MagFinalArgs a) {
+  // grid-stride: a launch that finds its work pre-empted (final_emitted) must cost a few blocks, not 65536
   if (a.ctl_ro && (a.ctl_ro->done || (a.skip_if_emitted && a.ctl_ro->final_emitted))) return;
   if (a.final_runs && blockIdx.x == 0 && threadIdx.x == 0) *a.final_runs += 1;
   const Consts<T> c = make_consts<T>(a.np);
-  Idx3 cell;
-  const bool active = decode_cell<ND>(a.g, cell);
   T wb[ND];
 #pragma unroll
   for (int k = 0; k < ND; ++k) wb[k] = T(0);
-  if (active) {
-    const int fin = a.fixed_final >= 0 ? a.fixed_final : a.ctl_ro->mag_final;
-    const View& X = a.X[fin];
+  long long total = a.g.n[0];
+  if constexpr (ND > 1) total *= a.g.n[1];
+  if constexpr (ND > 2) total *= a.g.n[2];
+  const int fin = a.fixed_final >= 0 ? a.fixed_final : a.ctl_ro->mag_final;
+  const View& X = a.X[fin];
+  for (long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x; lin < total;
+       lin += (long long)gridDim.x * blockDim.x) {
+    Idx3 cell;
+    decode_cell<ND>(a.g, cell, lin);
     const long long ox = offset_of<ND>(X, cell), og = offset_of<ND>(a.gas, cell), ob = offset_of<ND>(a.B_out, cell);
     const long long oo = offset_of<ND>(a.gas_out, cell);
     const T* px = static_cast<const T*>(X.p) + ox;
@@ -589,7 +596,7 @@ __global__ void __launch_bounds__(256) mag_final_kernel(const MagFinalArgs a) {
     po[(ND + 1) * a.gas_out.vs] = p2;
     if (a.alpha_slots) {
 #pragma unroll
-      for (int k = 0; k < ND; ++k) wb[k] = wave_bound(s, k + 1, c);
+      for (int k = 0; k < ND; ++k) wb[k] = rmax(wb[k], wave_bound(s, k + 1, c));
     }
   }
   if (a.alpha_slots) block_max_to_slots<T, ND>(wb, a.alpha_slots);
@@ -684,8 +691,10 @@ cudaError_t launch_mag_iter(const MagIterArgs& a, cudaStream_t st) {
 
 template <typename T>
 static cudaError_t launch_mag_final_t(const MagFinalArgs& a, cudaStream_t st) {
-  if (a.g.nd == 2) mag_final_kernel<T, 2><<<grid_for<2>(a.g), 256, 0, st>>>(a);
-  else if (a.g.nd == 3) mag_final_kernel<T, 3><<<grid_for<3>(a.g), 256, 0, st>>>(a);
+  // at most 148 SMs x 8 resident blocks; the kernel strides over the cells
+  const unsigned cap = 148u * 8u;
+  if (a.g.nd == 2) mag_final_kernel<T, 2><<<std::min(grid_for<2>(a.g), cap), 256, 0, st>>>(a);
+  else if (a.g.nd == 3) mag_final_kernel<T, 3><<<std::min(grid_for<3>(a.g), cap), 256, 0, st>>>(a);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
