@@ -143,6 +143,28 @@ struct CopyArgs {  // strided row copy (pad / unpad / concatenate)
   int edge_pad;  // >0: dst is padded by this many cells, fill them edge-mode (np.pad 'edge')
 };
 
+// Opt a kernel into more than 48 KB of dynamic shared memory once per DEVICE: the attribute belongs
+// to the device's context, and one process may drive several devices (JAX runs all local GPUs from
+// one process and calls the FFI handlers per device).  `done` is a per-launcher static.
+struct SmemOptIn {
+  bool done[64] = {};
+  template <typename K>
+  cudaError_t ensure(K kern, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return cudaSuccess;
+  }
+  bool first_time() const {  // true until the current device has been configured
+    int dev = 0;
+    return cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !done[dev];
+  }
+};
+
 #define AMX_DECLARE_LAUNCHERS                                                             \
   cudaError_t launch_hydro_stage(const amx::StageArgs&, cudaStream_t);                    \
   cudaError_t launch_split_sweep(const amx::SweepArgs&, cudaStream_t);                    \

@@ -403,11 +403,10 @@ template <bool FIRST, bool MID, int TY, bool EMIT>
 cudaError_t launch_pair_e(const MagIterArgs& a, cudaStream_t st) {
   using G = PG<TY>;
   auto kern = mag_pair_vec<FIRST, MID, TY, EMIT>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
+  static SmemOptIn opt;
+  {
+    cudaError_t e = opt.ensure(kern, G::smem_bytes);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid;
   grid.x = (a.g.n[2] + 63) / 64;

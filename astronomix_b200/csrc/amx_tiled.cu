@@ -472,11 +472,10 @@ cudaError_t launch_stage(const StageArgs& a, cudaStream_t st) {
   constexpr int TY = Tile<ND>::TY, TZ = Tile<ND>::TZ;
   const size_t smem = hydro_smem_bytes<T, ND>();
   auto kern = hydro_stage_tiled<T, ND, RS, LIM>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn opt;
+  {
+    cudaError_t e = opt.ensure(kern, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid;
   const int LA = ND - 1;
@@ -773,12 +772,11 @@ cudaError_t launch_mag(const MagIterArgs& a, cudaStream_t st) {
   constexpr int TY = Tile<ND>::TY, TZ = Tile<ND>::TZ;
   const size_t smem = mag_smem_bytes<T, ND>();
   auto kern = mag_iter_tiled<T, ND>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn opt;
+  if (opt.first_time()) {
+    cudaError_t e = opt.ensure(kern, smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
   }
   dim3 grid;
   const int LA = ND - 1;

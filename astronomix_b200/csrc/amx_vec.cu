@@ -421,16 +421,15 @@ cudaError_t launch_mag(const MagIterArgs& a, cudaStream_t st) {
   constexpr int TY = VT<ND, CW>::TY, TZ = 2 * VT<ND, CW>::TQ, kThreads = 32 * CW + 32;
   const size_t smem = mag_vec_smem_bytes<ND, CW>();
   auto kern = mag_iter_vec<ND, MODE, LD, CW>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn opt;
+  if (opt.first_time()) {
+    cudaError_t e = opt.ensure(kern, smem);
     if (e != cudaSuccess) return e;
     // Leave the carveout to the driver (just enough shared memory for two blocks): the remaining L1
     // tracks the loads in flight, and starving it costs ~45 % (measured: 0.47 ms with
     // cudaSharedmemCarveoutMaxShared, 0.32 ms without).
     static const int carve = [] { const char* e = getenv("AMX_VEC_CARVE"); return e ? atoi(e) : -1; }();
     if (carve >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    configured = true;
   }
   dim3 grid;
   const int LA = ND - 1;
@@ -939,11 +938,10 @@ template <int ND, int RS, int LIM, bool COMBINE>
 cudaError_t launch_stage_vec(const StageArgs& a, cudaStream_t st) {
   using G = HG<ND>;
   auto kern = hydro_stage_vec<ND, RS, LIM, COMBINE>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
+  static SmemOptIn opt;
+  {
+    cudaError_t e = opt.ensure(kern, G::smem_bytes);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid;
   const int LA = ND - 1;

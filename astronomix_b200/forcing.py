@@ -11,8 +11,7 @@ a quadratic in two global sums).
 The random stream is torch's (``torch.Generator`` seeded with 42, the number the reference seeds
 ``jax.random.key`` with): the fields have the reference's statistics, not its bits -- jax is not
 installable here, so its Threefry / erfinv stream cannot be pinned.  The arithmetic after the noise
-is restated in ``oracle/fv_oracle.py`` (``forcing_field``, ``apply_forcing``) and compared on
-identical noise.
+is restated in the test oracle (``forcing_field``, ``apply_forcing``) and compared on identical noise.
 """
 from __future__ import annotations
 
