@@ -86,7 +86,38 @@ struct Layout {
   size_t row_bytes;        // cells * esz rounded up to 256
   // byte offsets into ws
   size_t off_ctl, off_S[2], off_A, off_G, off_Gf, off_X[2], total;
+  size_t off_shell;        // ghost shell of the gas state (padded gas rows), shell mode only
 };
+
+// Unsplit MHD with ghost cells and a reflective side: the reference's ghost gas cells are not images
+// of interior cells (Q3 + Q11 + Q12, see ShellArgs) and take part in the CFL reduction.
+// Written in front of the shell once it holds valid data: a resumed segment (t_start != 0) trusts the
+// shell only if the stamp matches its own problem, otherwise it starts from images of the interior.
+struct ShellStamp {
+  unsigned long long magic;
+  int nd, n[3], dtype, bc[3][2];
+  bool operator==(const ShellStamp& o) const {
+    bool same = magic == o.magic && nd == o.nd && dtype == o.dtype;
+    for (int a = 0; a < 3; ++a) same = same && n[a] == o.n[a] && bc[a][0] == o.bc[a][0] && bc[a][1] == o.bc[a][1];
+    return same;
+  }
+};
+ShellStamp stamp_of(const amx_desc* d) {
+  ShellStamp s{};
+  s.magic = 0x414d585348454c4cull;  // "AMXSHELL"
+  s.nd = d->ndim;
+  s.dtype = d->dtype;
+  for (int a = 0; a < 3; ++a) { s.n[a] = d->n[a]; s.bc[a][0] = d->bc[a][0]; s.bc[a][1] = d->bc[a][1]; }
+  return s;
+}
+
+bool shell_mode(const amx_desc* d) {
+  if (!d->mhd || d->split != AMX_UNSPLIT || d->boundary_handling != AMX_GHOST_CELLS) return false;
+  if (d->bc[0][0] == AMX_BC_HALO || d->bc[0][1] == AMX_BC_HALO) return false;
+  for (int a = 0; a < d->ndim; ++a)
+    if (d->bc[a][0] == AMX_BC_REFLECTIVE || d->bc[a][1] == AMX_BC_REFLECTIVE) return true;
+  return false;
+}
 
 size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -153,6 +184,12 @@ Layout make_layout(const amx_desc* d) {
   L.off_G = off; off += L.row_bytes * L.ng;
   L.off_Gf = off; off += d->mhd ? L.row_bytes * L.ng : 0;  // gas after the magnetic write-back
   for (int k = 0; k < 2; ++k) { L.off_X[k] = off; off += d->mhd ? L.row_bytes * 6 : 0; }
+  L.off_shell = off;
+  if (shell_mode(d)) {
+    size_t padded = 1;
+    for (int a = 0; a < d->ndim; ++a) padded *= (size_t)(d->n[a] + 2 * d->num_ghost);
+    off += 256 + align256(padded * L.esz * L.ng);  // 256-byte stamp (ShellStamp), then the padded gas rows
+  }
   L.total = off;
   return L;
 }
@@ -587,6 +624,9 @@ struct Engine {
   cudaStream_t st;
   long long launches = 0;
   bool strict, is32, lf;  // lf: every stage needs the wave bounds of its input (Lax-Friedrichs alpha, PP limiter C)
+  // ghost shell (ShellArgs): where the shell is read / written by the next update; off unless set
+  bool shell_on = false;
+  View shell_src, shell_dst;
 
   Engine(const amx_desc* d_, void* ws_, void* stream)
       : d(d_), L(make_layout(d_)), g(geom_of(d_)), np(numpar_of(d_)), ws(static_cast<char*>(ws_)),
@@ -654,18 +694,36 @@ struct Engine {
     return cudaGetLastError();
   }
 
-  cudaError_t alpha_of(const View& gas, void* alpha_t_out, bool guarded) {
+  // padded_gas: also reduce over the ghost cells of this padded array (view at its first active cell)
+  cudaError_t alpha_of(const View& gas, void* alpha_t_out, bool guarded, const View* padded_gas = nullptr) {
     AlphaArgs a{g, np, gas, guarded ? ctl : nullptr, aslots()};
     ++launches;
     {
       ProfScope ps(PC_ALPHA, st);
       CKE(strict ? amx_strict::launch_alpha(a, st) : amx_fast::launch_alpha(a, st));
     }
+    if (padded_gas) CKE(shell(2, *padded_gas, *padded_gas, nullptr, nullptr, nullptr, true, guarded));
     return finalize_alpha(alpha_t_out, guarded);
   }
 
+  // one update of the ghost shell (ShellArgs); with_alpha: its wave bounds join the slots
+  cudaError_t shell(int mode, const View& src, const View& dst, const View* u0, const View* u1, const View* X,
+                    bool with_alpha, bool guarded) {
+    ShellArgs a;
+    a.g = g; a.np = np; a.mode = mode; a.ng = d->num_ghost;
+    a.shell_in = src; a.shell_out = dst;
+    a.u0 = u0 ? *u0 : src; a.u1 = u1 ? *u1 : src;
+    a.X[0] = X ? X[0] : src; a.X[1] = X ? X[1] : src;
+    a.ctl_ro = (guarded || mode == 1) ? ctl : nullptr;
+    a.fixed_final = -1;
+    a.alpha_slots = with_alpha ? aslots() : nullptr;
+    ++launches;
+    return strict ? amx_strict::launch_shell(a, st) : amx_fast::launch_shell(a, st);
+  }
+
   cudaError_t stage(const View& in, const View* in0, const View& out, const void* dt, double dt_scale,
-                    const void* alpha_lf, bool want_alpha, void* alpha_t_out, bool guarded) {
+                    const void* alpha_lf, bool want_alpha, void* alpha_t_out, bool guarded,
+                    bool defer_finalize = false) {
     StageArgs a;
     a.g = g; a.np = np; a.in = in; a.out = out;
     a.in0 = in0 ? *in0 : in;
@@ -682,7 +740,7 @@ struct Engine {
       else if (tiled) CKE(strict ? amx_strict::launch_hydro_stage_tiled(a, st) : amx_fast::launch_hydro_stage_tiled(a, st));
       else CKE(strict ? amx_strict::launch_hydro_stage(a, st) : amx_fast::launch_hydro_stage(a, st));
     }
-    return want_alpha ? finalize_alpha(alpha_t_out, guarded) : cudaSuccess;
+    return (want_alpha && !defer_finalize) ? finalize_alpha(alpha_t_out, guarded) : cudaSuccess;
   }
 
   cudaError_t sweep(const View& in, const View& out, int axis, const void* dt, double dt_scale,
@@ -706,7 +764,13 @@ struct Engine {
                     double scale, bool final_alpha) {
     if (d->split == AMX_UNSPLIT) {
       CKE(stage(gas_in, nullptr, tmpA, dt_ptr(), scale, alpha_ptr(), lf, nullptr, true));
-      return stage(tmpA, &gas_in, gas_out, dt_ptr(), scale, alpha_ptr(), final_alpha || lf, nullptr, true);
+      if (!shell_on) return stage(tmpA, &gas_in, gas_out, dt_ptr(), scale, alpha_ptr(), final_alpha || lf, nullptr, true);
+      // shell mode: the ghost shell follows the half step, and the wave bounds the NEXT CFL reads
+      // (final_alpha) are those of the padded array
+      CKE(stage(tmpA, &gas_in, gas_out, dt_ptr(), scale, alpha_ptr(), final_alpha || lf, nullptr, true, true));
+      CKE(shell(0, shell_src, shell_dst, &gas_in, &gas_out, nullptr, final_alpha, true));
+      shell_src = shell_dst;
+      return (final_alpha || lf) ? finalize_alpha(nullptr, true) : cudaSuccess;
     }
     // Strang sequences of evolve_state.py:168-325
     int axes[5];
@@ -842,7 +906,7 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
   // the expectation holds; Lax-Friedrichs / PP need the wave bounds of the written-back gas and
   // keep mag_final.  AMX_NO_EMIT=1 switches it off.
   static const bool no_emit = [] { const char* e = getenv("AMX_NO_EMIT"); return e && e[0] == '1'; }();
-  bool emit_ok = pairs && !E.lf && !no_emit;
+  bool emit_ok = pairs && !E.lf && !no_emit && !E.shell_on;
   if (emit_ok) {
     MagIterArgs probe = E.mag_args(Bin, G, nullptr, X[0], E.dt_ptr(), 0, true);
     probe.emit = 1; probe.emit_gas = Gf; probe.emit_B = Bout;
@@ -876,6 +940,7 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
   static const bool nosync = [] { const char* e = getenv("AMX_NOSYNC"); return e && e[0] == '1'; }();
   if (nosync) {
     CK(E.mag_final(G, Gf, Bout, X, -1, E.lf, nullptr, true));
+    if (E.shell_on) CK(E.shell(1, E.shell_src, E.shell_dst, &G, nullptr, X, false, true));
     CK(E.hydro(Gf, sout, A, X[0], 0.5, true));
     return AMX_OK;
   }
@@ -890,6 +955,7 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
   }
   if (!m->done) *kspec = m->mag_iter + 1;
   CK(E.mag_final(G, Gf, Bout, X, -1, E.lf, nullptr, true));
+  if (E.shell_on) CK(E.shell(1, E.shell_src, E.shell_dst, &G, nullptr, X, false, true));
   // X buffers are free again: reuse X[0] rows as sweep scratch
   CK(E.hydro(Gf, sout, A, X[0], 0.5, true));
   return AMX_OK;
@@ -1005,7 +1071,11 @@ int amx_cfl(const amx_desc* d, const void* seam_state, void* dt_out, void* ws, v
   if ((rc = amx_device_check())) return rc;
   Engine E(d, ws, stream);
   CK(cudaMemsetAsync(E.ctl, 0, sizeof(Ctl), E.st));
-  CK(E.alpha_of(E.user_seam(seam_state), nullptr, false));
+  // _timestep_estimator.py:118-128 reduces over the array it is given: in GHOST_CELLS mode that is
+  // the padded one, ghost cells included (Q3)
+  const View seam = E.user_seam(seam_state);
+  const bool padded = d->boundary_handling == AMX_GHOST_CELLS && d->bc[0][0] != AMX_BC_HALO && d->bc[0][1] != AMX_BC_HALO;
+  CK(E.alpha_of(seam, nullptr, false, padded ? &seam : nullptr));
   DtPar p = E.dtpar(0.0);
   if (E.is32) dt_only_kernel<float><<<1, 1, 0, E.st>>>(E.ctl->alpha_f, nullptr, p, (float*)dt_out);
   else dt_only_kernel<double><<<1, 1, 0, E.st>>>(E.ctl->alpha, nullptr, p, (double*)dt_out);
@@ -1029,11 +1099,17 @@ int amx_step(const amx_desc* d, const void* seam_in, void* seam_out, const void*
   CK(cudaGetLastError());
   const View sin = E.user_seam(seam_in), sout = E.user_seam(seam_out);
   if (E.lf) CK(E.alpha_of(sin, nullptr, false));
+  if (shell_mode(d)) {  // ghost gas cells: read from seam_in, carried through the step in seam_out's ghost cells
+    E.shell_on = true;
+    E.shell_src = sin;
+    E.shell_dst = sout;
+  }
   int kspec = d->dtype == AMX_F32 ? 4 : 8;  // first guess of the evaluations per step
   if ((rc = run_step(E, sin, sout, &kspec))) return rc;
   if (d->boundary_handling == AMX_GHOST_CELLS) {
-    // ghosts of the result: what the reference's trailing _boundary_handler calls leave behind
-    if ((rc = amx_boundary_fill(d, seam_out, E.L.ng, 0, stream))) return rc;
+    // ghosts of the result: what the reference's trailing _boundary_handler calls leave behind (shell
+    // mode: the gas ghosts are the shell and are already in place)
+    if (!E.shell_on && (rc = amx_boundary_fill(d, seam_out, E.L.ng, 0, stream))) return rc;
     if (d->mhd) {
       int pad[3];
       seam_pad(d, pad);
@@ -1080,8 +1156,33 @@ int amx_integrate_from(const amx_desc* d, const void* unpadded_in, void* unpadde
   CK(cudaMemsetAsync(E.ctl, 0, sizeof(Ctl), E.st));
   const View vin = E.user_unpadded(unpadded_in);
   const View S[2] = {E.internal(L.off_S[0]), E.internal(L.off_S[1])};
+  if (shell_mode(d)) {
+    int pad[3];
+    seam_pad(d, pad);
+    const View sh = make_view(E.ws + L.off_shell + 256, d, pad, 0, 0);
+    const ShellStamp mine = stamp_of(d);
+    bool keep = false;
+    if (t_start != 0.0) {  // resumed segment on the same ws: keep the shell the previous segment left
+      ShellStamp found{};
+      CK(cudaMemcpyAsync(&found, E.ws + L.off_shell, sizeof(found), cudaMemcpyDeviceToHost, E.st));
+      CK(cudaStreamSynchronize(E.st));
+      keep = found == mine;
+    }
+    if (!keep) {
+      // time_integration.py:274-286: pad + ghost fill of the gas rows = images of the interior cells
+      CK(cudaMemcpyAsync(E.ws + L.off_shell, &mine, sizeof(mine), cudaMemcpyHostToDevice, E.st));
+      long long tot = 1;
+      for (int a = 0; a < d->ndim; ++a) tot *= d->n[a] + 2 * d->num_ghost;
+      if (E.is32) pad_kernel<float><<<blocks_for(tot), 256, 0, E.st>>>(E.g, d->num_ghost, L.ng, L.ng, vin, sh);
+      else pad_kernel<double><<<blocks_for(tot), 256, 0, E.st>>>(E.g, d->num_ghost, L.ng, L.ng, vin, sh);
+      CK(cudaGetLastError());
+    }
+    E.shell_on = true;
+    E.shell_src = sh;
+    E.shell_dst = sh;
+  }
   // wave bounds of the initial state (time_integration.py:643-653 on the first pass)
-  CK(E.alpha_of(vin, nullptr, false));
+  CK(E.alpha_of(vin, nullptr, false, E.shell_on ? &E.shell_src : nullptr));
   DtPar p = E.dtpar(t_end);
   p.t_stop = E.is32 ? (double)(float)t_stop : t_stop;
   if (t_start != 0.0) {
@@ -1100,6 +1201,9 @@ int amx_integrate_from(const amx_desc* d, const void* unpadded_in, void* unpadde
       else step_begin_kernel<double><<<1, 1, 0, E.st>>>(E.ctl, p, (long long)max_steps);
       CK(cudaGetLastError());
       const View& sin = issued == 0 ? vin : S[(issued - 1) & 1];
+      // shell mode: ctl->alpha now holds the bounds of the padded array (what dt needed); the
+      // Lax-Friedrichs / PP stages want those of the ghost-FILLED state, i.e. of the interior
+      if (E.shell_on && E.lf && issued > 0) CK(E.alpha_of(sin, nullptr, true));
       if ((rc = run_step(E, sin, S[issued & 1], &kspec))) return rc;
       ++E.launches;
       if (E.is32) step_end_kernel<float><<<1, 1, 0, E.st>>>(E.ctl);

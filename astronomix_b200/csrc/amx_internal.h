@@ -126,6 +126,26 @@ struct AlphaArgs {
   unsigned long long* alpha_slots;
 };
 
+// Ghost shell of the gas state (amx_kernels.cu shell_kernel): the reference reduces the CFL bound
+// over the PADDED array (Q3), leaves the ghost cells of the RK2 combine un-refilled (Q11) and fills
+// the ghost velocities in magnetic_update with the 3-vector flip rule (Q12).  With a reflective
+// side in an unsplit MHD run the ghost gas cells follow their own recurrence and can set dt; the
+// kernels work on unpadded arrays, so the shell is carried beside them.
+struct ShellArgs {
+  Geom g;
+  NumPar np;
+  int mode;        // 0 hydro half step, 1 magnetic write-back, 2 wave bounds of the shell as it is
+  int ng;          // ghost cells per side (2)
+  View shell_in;   // ND+2 gas rows of a padded array, p at the first ACTIVE cell
+  View shell_out;  // updated shell (may be the same array)
+  View u0;         // mode 0: interior gas entering the half step; mode 1: interior gas before the write-back
+  View u1;         // mode 0: interior gas leaving the half step
+  View X[2];       // mode 1: fixed-point iterate buffers (rows 3..5 = v_n)
+  const Ctl* ctl_ro;
+  int fixed_final;  // >= 0: iterate buffer index; < 0: ctl_ro->mag_final
+  unsigned long long* alpha_slots;  // nullable: add the wave bounds of the (updated) shell cells
+};
+
 struct FillArgs {  // ghost fill of a padded array (GHOST_CELLS seam arrays)
   Geom g;
   int dtype;
@@ -171,6 +191,7 @@ struct SmemOptIn {
   cudaError_t launch_mag_iter(const amx::MagIterArgs&, cudaStream_t);                     \
   cudaError_t launch_mag_final(const amx::MagFinalArgs&, cudaStream_t);                   \
   cudaError_t launch_alpha(const amx::AlphaArgs&, cudaStream_t);                          \
+  cudaError_t launch_shell(const amx::ShellArgs&, cudaStream_t);                          \
   bool tiled_stage_supported(const amx::StageArgs&);                                      \
   cudaError_t launch_hydro_stage_tiled(const amx::StageArgs&, cudaStream_t);             \
   bool tiled_mag_supported(const amx::MagIterArgs&);                                      \

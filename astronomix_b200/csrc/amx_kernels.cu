@@ -602,6 +602,96 @@ __global__ void __launch_bounds__(256) mag_final_kernel(const MagFinalArgs a) {
   if (a.alpha_slots) block_max_to_slots<T, ND>(wb, a.alpha_slots);
 }
 
+// ---------------------------------------------------------------- ghost shell of the gas state
+// One thread per cell of the PADDED array; interior cells only take part in the block maximum.
+// A ghost cell g has the interior source cell src(g) (index mapping per axis, the composition of
+// the reference's axis-by-axis fills) and, per reflective axis it lies beyond, one sign flip.
+//   mode 0  evolve_state.py:456-469 at a ghost cell: prim(0.5*(cons(G) + cons(fill(S2)))) with
+//           cons(S2) = 2 cons(U1) - cons(U) at src(g) (U -> U1 is the interior RK2 combine) and the
+//           gas rule: momentum `axis` changes sign
+//   mode 1  _magnetic_field_update.py:208-240 at a ghost cell: rho, p of the shell; |v_0|, |v_n| of
+//           the source cell; velocity rows <- v_n with the 3-vector rule (component index `axis`,
+//           1-based, changes sign if it exists: Q12)
+//   mode 2  nothing changes; wave bounds only
+// then |v_axis| + c of the shell cell joins the wave-bound maximum (_timestep_estimator.py:118-128
+// runs over the padded array).
+template <typename T, int ND>
+__global__ void __launch_bounds__(256) shell_kernel(const ShellArgs a) {
+  if (a.ctl_ro && a.ctl_ro->done) return;
+  const Consts<T> c = make_consts<T>(a.np);
+  T wb[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) wb[k] = T(0);
+  long long e[3], tot = 1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { e[k] = k < ND ? a.g.n[k] + 2 * a.ng : 1; tot *= e[k]; }
+  const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool ghost = false;
+  if (lin < tot) {
+    long long r = lin;
+    Idx3 gi, si;
+    gi.i[2] = (int)(r % e[2]); r /= e[2];
+    gi.i[1] = (int)(r % e[1]); r /= e[1];
+    gi.i[0] = (int)r;
+    bool flip[3] = {false, false, false};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < ND) {
+        gi.i[k] -= a.ng;
+        si.i[k] = map_index<ND>(gi.i[k], a.g.n[k], a.g.bc[k][0], a.g.bc[k][1], flip[k]);
+        ghost = ghost || gi.i[k] < 0 || gi.i[k] >= a.g.n[k];
+      } else {
+        gi.i[k] = 0;
+        si.i[k] = 0;
+      }
+    }
+    if (ghost) {
+      Gas<T, ND> G = load_gas<T, ND>(a.shell_in, offset_of<ND>(a.shell_in, gi));
+      if (a.mode == 0) {
+        const Gas<T, ND> U0 = cons_from_prim(load_gas<T, ND>(a.u0, offset_of<ND>(a.u0, si)), c);
+        const Gas<T, ND> U1 = cons_from_prim(load_gas<T, ND>(a.u1, offset_of<ND>(a.u1, si)), c);
+        const Gas<T, ND> UG = cons_from_prim(G, c);
+        Gas<T, ND> Um;
+#pragma unroll
+        for (int k = 0; k < ND + 2; ++k) {
+          T s2 = T(2) * U1.q[k] - U0.q[k];
+          if (k >= 1 && k <= ND && flip[k - 1]) s2 = -s2;
+          Um.q[k] = T(0.5) * (UG.q[k] + s2);
+        }
+        G = prim_from_cons(Um, c);
+      } else if (a.mode == 1) {
+        const int fin = a.fixed_final >= 0 ? a.fixed_final : a.ctl_ro->mag_final;
+        const View& X = a.X[fin];
+        const T* px = static_cast<const T*>(X.p) + offset_of<ND>(X, si);
+        const Gas<T, ND> s0 = load_gas<T, ND>(a.u0, offset_of<ND>(a.u0, si));
+        T n0 = T(0), nn = T(0), vn[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          vn[k] = __ldg(px + (3 + k) * X.vs);
+          const T v0k = (k < ND) ? s0.q[k + 1] : T(0);
+          n0 = n0 + sq(rabs(v0k));
+          nn = nn + sq(rabs(vn[k]));
+        }
+        const T p2 = magnetic_writeback_pressure(G.q[0], G.q[ND + 1], n0, nn);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+          T v = vn[k];
+          // the fill of axis k2 flips 3-vector component k2 + 1
+          if (k >= 1 && flip[k - 1]) v = -v;
+          G.q[k + 1] = v;
+        }
+        G.q[ND + 1] = p2;
+      }
+      if (a.mode != 2 || a.shell_out.p != a.shell_in.p) store_gas<T, ND>(a.shell_out, offset_of<ND>(a.shell_out, gi), G);
+      if (a.alpha_slots) {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) wb[k] = wave_bound(G, k + 1, c);
+      }
+    }
+  }
+  if (a.alpha_slots) block_max_to_slots<T, ND>(wb, a.alpha_slots);
+}
+
 // ---------------------------------------------------------------- launchers
 template <int ND>
 static inline unsigned grid_for(const Geom& g) {
@@ -709,6 +799,18 @@ static cudaError_t launch_alpha_t(const AlphaArgs& a, cudaStream_t st) {
 }
 cudaError_t launch_alpha(const AlphaArgs& a, cudaStream_t st) {
   return a.np.dtype == 0 ? launch_alpha_t<float>(a, st) : launch_alpha_t<double>(a, st);
+}
+
+template <typename T>
+static cudaError_t launch_shell_t(const ShellArgs& a, cudaStream_t st) {
+  long long tot = 1;
+  for (int k = 0; k < a.g.nd; ++k) tot *= a.g.n[k] + 2 * a.ng;
+  const unsigned grid = (unsigned)((tot + 255) / 256);
+  AMX_DISPATCH_ND(a.g.nd, { shell_kernel<T, ND><<<grid, 256, 0, st>>>(a); })
+  return cudaGetLastError();
+}
+cudaError_t launch_shell(const ShellArgs& a, cudaStream_t st) {
+  return a.np.dtype == 0 ? launch_shell_t<float>(a, st) : launch_shell_t<double>(a, st);
 }
 
 }  // namespace AMX_NS

@@ -106,6 +106,24 @@ def all_cases():
             if dim > 1:
                 cs.append(case(f"mhd{dim}d_{bn}", dim, mhd=True, init=("smooth_random", 73 + b), bnd=b,
                                numerical_precision=DOUBLE))
+    # reflective sides in unsplit MHD: the ghost gas cells are not images of interior cells (Q3 + Q11 + Q12)
+    # and take part in the CFL reduction -- longer runs, both precisions, the solvers that need wave bounds
+    cs.append(case("mhd3d_reflective_long", 3, mhd=True, init=("smooth_random", 110), bnd=REFLECTIVE, steps=12,
+                   numerical_precision=DOUBLE))
+    cs.append(case("mhd2d_reflective_long", 2, mhd=True, init=("smooth_random", 111), bnd=REFLECTIVE, steps=12,
+                   numerical_precision=DOUBLE))
+    cs.append(case("mhd3d_reflective_f32", 3, mhd=True, init=("smooth_random", 112), bnd=REFLECTIVE, dtype="f32"))
+    cs.append(case("mhd2d_reflective_f32", 2, mhd=True, init=("smooth_random", 113), bnd=REFLECTIVE, dtype="f32"))
+    cs.append(case("mhd3d_reflective_lf", 3, mhd=True, init=("smooth_random", 114), bnd=REFLECTIVE,
+                   riemann_solver=LAX_FRIEDRICHS, numerical_precision=DOUBLE))
+    cs.append(case("mhd2d_reflective_lf_valbadapp", 2, mhd=True, init=("smooth_random", 115), bnd=REFLECTIVE,
+                   riemann_solver=LAX_FRIEDRICHS, limiter=VAN_ALBADA_PP, numerical_precision=DOUBLE))
+    cs.append(case("mhd3d_reflective_hllc_euler", 3, mhd=True, init=("smooth_random", 116), bnd=REFLECTIVE,
+                   riemann_solver=HLLC, fv_magnetic_integrator=IMPLICIT_EULER, numerical_precision=DOUBLE))
+    cs.append(case("mhd2d_mixed_bnd", 2, mhd=True, init=("smooth_random", 117),
+                   bnd=[[REFLECTIVE, OPEN], [OPEN, REFLECTIVE]], steps=8, numerical_precision=DOUBLE))
+    cs.append(case("mhd3d_reflective_split_muscl", 3, mhd=True, init=("smooth_random", 118), bnd=REFLECTIVE,
+                   split=SPLIT, time_integrator=MUSCL, params={"dt_max": 1.0}, numerical_precision=DOUBLE))
     cs.append(case("hydro2d_mixed_bnd", 2, init=("smooth_random", 76), bnd=[[PERIODIC, PERIODIC], [REFLECTIVE, OPEN]]))
     cs.append(case("mhd3d_mixed_bnd", 3, mhd=True, init=("smooth_random", 77),
                    bnd=[[OPEN, REFLECTIVE], [PERIODIC, PERIODIC], [REFLECTIVE, OPEN]], numerical_precision=DOUBLE))
@@ -235,10 +253,14 @@ def main():
                             spec=np.array(json.dumps(spec)))
         index.append(c["name"])
         print(f"{c['name']:40s} t_end={t_end:.6g} shape={out.shape} {time.time() - t0:.1f}s", flush=True)
-    if not args.only:
-        with open(os.path.join(OUT, "INDEX.json"), "w") as f:
-            json.dump({"generator": "oracle/gen_reference_vectors.py", "reference": "leo1200/astronomix v0.5.1 sources "
-                       "executed over oracle/jaxshim (NumPy backend)", "cases": index}, f, indent=1)
+    path = os.path.join(OUT, "INDEX.json")
+    if args.only and os.path.exists(path):  # partial run: keep the recorded cases, add the new ones
+        with open(path) as f:
+            known = json.load(f)["cases"]
+        index = known + [n for n in index if n not in known]
+    with open(path, "w") as f:
+        json.dump({"generator": "oracle/gen_reference_vectors.py", "reference": "leo1200/astronomix v0.5.1 sources "
+                   "executed over oracle/jaxshim (NumPy backend)", "cases": index}, f, indent=1)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,178 @@
+"""The ghost-shell recurrence of the CUDA path (amx_shell.cu), restated in NumPy and checked
+against the oracle's padded arrays.
+
+Why it exists (SURVEY.md Q3 + Q11 + Q12): the reference's CFL reduction runs over the PADDED
+array, the RK2 combine leaves the ghost cells un-refilled, and ``magnetic_update`` fills the
+ghost velocities with the 3-vector flip rule, which is not the gas rule.  With a reflective side
+in an UNSPLIT MHD run the ghost gas cells therefore stop being images of interior cells; they
+follow their own recurrence and can hold the largest |v| + c of the padded array, i.e. they set
+dt.  The CUDA kernels work on unpadded arrays, so the library carries the ghost shell separately:
+
+    hydro half step   G <- prim(0.5 * (cons(G) + image_gas(2 cons(U1) - cons(U))))
+    magnetic update   G <- (G.rho, image_Q12(v_n)[:dim], p2(G.rho, G.p, |image(v_0)|, |image(v_n)|))
+    CFL               alpha_axis = max(interior, max over the shell of |G.v_axis| + c(G))
+
+where U -> U1 are the interior states around the half step (cons(S2) = 2 cons(U1) - cons(U) is
+the second RK stage, exact up to one rounding).  This test runs the oracle (which works on padded
+arrays like the reference does) and checks that the recurrence reproduces its ghost cells and its
+time steps without ever reading them.
+"""
+import numpy as np
+import pytest
+
+from astronomix_b200 import option_classes as oc
+from astronomix_b200 import problems as pr
+from oracle import fv_oracle as fo
+
+
+def axis_maps(o, n):
+    """padded index -> (interior source index, flipped?) per axis; same rule as map_index in the kernels."""
+    maps = []
+    for ax in range(o.dim):
+        bl, br = o.boundaries[ax]
+        src, flip = np.zeros(n + 4, dtype=np.int64), np.zeros(n + 4, dtype=bool)
+        for j in range(n + 4):
+            i = j - 2
+            if i < 0:
+                src[j] = {fo.OPEN_BOUNDARY: 0, fo.REFLECTIVE_BOUNDARY: -1 - i, fo.PERIODIC_BOUNDARY: i + n}[bl]
+                flip[j] = bl == fo.REFLECTIVE_BOUNDARY
+            elif i >= n:
+                src[j] = {fo.OPEN_BOUNDARY: n - 1, fo.REFLECTIVE_BOUNDARY: 2 * n - 1 - i, fo.PERIODIC_BOUNDARY: i - n}[br]
+                flip[j] = br == fo.REFLECTIVE_BOUNDARY
+            else:
+                src[j] = i
+        maps.append((src, flip))
+    return maps
+
+
+def image(a, maps, rows_flipped):
+    """Interior array [rows, n..] -> padded array of images; rows_flipped[ax] = row that changes sign
+    on a reflective side of axis ax (None: no row)."""
+    out = a[(slice(None),) + np.ix_(*[m[0] for m in maps])].copy()
+    for ax, (src, flip) in enumerate(maps):
+        r = rows_flipped[ax]
+        if r is None:
+            continue
+        shape = [1] * (a.ndim - 1)
+        shape[ax] = -1
+        sign = np.where(flip, -1.0, 1.0).astype(a.dtype).reshape(shape)
+        out[r] = out[r] * sign
+    return out
+
+
+def run_with_shell(s0, o, steps):
+    """The oracle's loop; beside it the shell recurrence fed with interior values only."""
+    t_ = s0.dtype.type
+    dim, n = o.dim, s0.shape[1]
+    gamma, C_cfl, dt_max, t_end = t_(o.gamma), t_(o.C_cfl), t_(o.dt_max), t_(o.t_end)
+    maps = axis_maps(o, n)
+    inner = (slice(None),) + (slice(2, -2),) * dim
+    ghost = np.ones((n + 4,) * dim, dtype=bool)
+    ghost[(slice(2, -2),) * dim] = False
+    gas_rows = [ax + 1 for ax in range(dim)]                       # gas rule: v_axis
+    q12_rows = [ax + 1 if ax + 1 < 3 else None for ax in range(dim)]  # 3-vector rule (Q12)
+    ng = dim + 2
+
+    s = fo.prepare_state(s0, o)
+    G = image(s0[:ng], maps, gas_rows)  # time_integration.py:281-284: initial fill of the gas rows
+    worst = {"ghost": 0.0, "dt": 0.0}
+
+    def compare(G, padded_gas):
+        d = np.abs(G - padded_gas)[:, ghost].max() / np.abs(padded_gas).max()
+        worst["ghost"] = max(worst["ghost"], float(d))
+
+    def hydro_shell(G, U, U1):
+        cS2 = t_(2) * fo.conserved_state_from_primitive(U1, gamma, o_gas) - fo.conserved_state_from_primitive(U, gamma, o_gas)
+        cG = fo.conserved_state_from_primitive(G, gamma, o_gas)
+        return fo.primitive_state_from_conserved(t_(0.5) * (cG + image(cS2, maps, gas_rows)), gamma, o_gas)
+
+    o_gas = o  # cons/prim read only dim and the row indices of the gas rows
+    time = t_(0.0)
+    for _ in range(steps):
+        # CFL over interior + shell
+        Gs = np.where(ghost, G, s[:ng])  # interior from the interior, shell from the recurrence
+        full = np.concatenate((Gs, s[ng:]), axis=0)
+        dt_model = t_(fo.cfl_time_step(full, o, gamma, C_cfl, dt_max))
+        dt = t_(fo.cfl_time_step(s, o, gamma, C_cfl, dt_max))
+        worst["dt"] = max(worst["dt"], abs(float(dt_model) - float(dt)) / float(dt))
+        dt = min(dt, t_end - time)
+        # the oracle's step, sub-step by sub-step (evolve_state.py:497-600)
+        gas, B = s[:-3], s[-3:]
+        gas1 = fo.evolve_gas(gas, dt / 2, gamma, o)
+        G = hydro_shell(G, gas[inner], gas1[inner])
+        compare(G, gas1)
+        B2, gas2 = fo.magnetic_update(B, gas1, dt, o)
+        # magnetic write-back on the shell: rho and p of the shell, images of v_0 and v_n (3 components)
+        v0 = np.zeros((3,) + gas1[inner].shape[1:], dtype=s.dtype)
+        v0[:dim] = gas1[inner][1:1 + dim]
+        vn = v0.copy()
+        vn[:dim] = gas2[inner][1:1 + dim]
+        if dim == 2:  # the dropped v_z increment (Q5) still enters |v_n|: recompute it like the iterate buffer holds it
+            vn[2] = _vz_increment(B, gas1, B2, dt, o)[(slice(2, -2),) * dim]
+        v0g, vng = image(v0, maps, q12_rows), image(vn, maps, q12_rows)
+        g53 = 5 / 3
+        E = fo.total_energy_from_primitives(G[0], fo._norm0(v0g), G[ng - 1], g53)
+        E2 = E - t_(0.5) * G[0] * fo._norm0(v0g) ** 2 + t_(0.5) * G[0] * fo._norm0(vng) ** 2
+        G = G.copy()
+        G[ng - 1] = fo.pressure_from_energy(E2, G[0], fo._norm0(vng), g53)
+        G[1:1 + dim] = vng[:dim]
+        compare(G, gas2)
+        gas3 = fo.evolve_gas(gas2, dt / 2, gamma, o)
+        G = hydro_shell(G, gas2[inner], gas3[inner])
+        compare(G, gas3)
+        s = np.concatenate((gas3, B2), axis=0)
+        time = t_(time + dt)
+    return worst
+
+
+def _vz_increment(B, gas1, B2, dt, o):
+    """v_z of the converged iterate in 2-D (padded array); the oracle drops it after the pressure update,
+    so it is recomputed here from the converged B the same way the last evaluation did."""
+    t = B.dtype.type
+    v = np.zeros((3,) + gas1.shape[1:], dtype=B.dtype)
+    v[0:2] = gas1[1:3]
+    Bf = fo._bc(B, o, fo.MAGNETIC_FIELD_ONLY)
+    v = fo._bc(v, o, fo.VELOCITY_ONLY)
+    # last evaluation used the argument (B_k + B_0)/2 with B_k the iterate before B_n; at convergence
+    # B_k = B_n to the fixed-point tolerance, which is far below what this test resolves in |v_n|
+    aB = (B2 + Bf) / 2 if o.fv_magnetic_integrator == fo.IMPLICIT_MIDPOINT else B2
+    phiB = fo.cross(aB, fo.curl2D(aB, o.grid_spacing)) / gas1[o.rho_i]
+    return (v - dt * phiB)[2]
+
+
+CASES = [
+    (3, 12, "reflective", np.float64, 1e-13),
+    (3, 12, "mixed", np.float64, 1e-13),
+    (2, 24, "reflective", np.float64, 1e-8),   # 2-D: |v_n| needs the dropped v_z, known here to the fixed-point tolerance only
+    (3, 12, "reflective", np.float32, 1e-5),
+    (3, 12, "open", np.float64, 1e-13),
+]
+
+
+@pytest.mark.parametrize("dim,n,bnd,dtype,tol", CASES)
+def test_shell_recurrence_reproduces_the_oracles_ghost_cells(dim, n, bnd, dtype, tol):
+    if bnd == "mixed":
+        b = oc.BoundarySettings1D
+        bs = oc.BoundarySettings(b(oc.OPEN_BOUNDARY, oc.REFLECTIVE_BOUNDARY), b(oc.PERIODIC_BOUNDARY, oc.PERIODIC_BOUNDARY),
+                                 b(oc.REFLECTIVE_BOUNDARY, oc.OPEN_BOUNDARY))
+    else:
+        bs = bnd
+    s0 = pr.smooth_random(dim, n, mhd=True, seed=74, dtype=dtype)
+    config, params, rv = pr.make(dim, n, mhd=True, boundaries=bs, dtype=dtype, numerical_precision=oc.DOUBLE_PRECISION)
+    o = fo.Opts.from_config(config, params)
+    worst = run_with_shell(s0, o, 4)
+    assert worst["ghost"] <= tol, worst
+    assert worst["dt"] <= tol, worst
+
+
+def test_padded_cfl_differs_from_interior_cfl_with_reflective_mhd():
+    """The effect is real: ignoring the shell changes dt at the 1e-3 level in this run."""
+    s0 = pr.smooth_random(3, 12, mhd=True, seed=74, dtype=np.float64)
+    config, params, rv = pr.make(3, 12, mhd=True, boundaries="reflective", dtype=np.float64)
+    o = fo.Opts.from_config(config, params)
+    _, info = fo.time_integration(s0, o, max_steps=3, return_info=True)
+    s = info["padded"]
+    g = s.dtype.type
+    dt_padded = fo.cfl_time_step(s, o, g(o.gamma), g(o.C_cfl), g(o.dt_max))
+    dt_inner = fo.cfl_time_step(np.ascontiguousarray(fo.unpad(s, o)), o, g(o.gamma), g(o.C_cfl), g(o.dt_max))
+    assert dt_padded < dt_inner * (1 - 1e-5)
