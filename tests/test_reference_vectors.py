@@ -69,3 +69,113 @@ def test_cuda_reproduces_reference_vector(cuda, name):
     assert out.dtype == ref.dtype and out.shape == ref.shape and np.isfinite(out).all()
     err = pr.rel_l1(out, ref, spec["dim"], spec["mhd"])
     assert err <= (1e-12 if spec["dtype"] == "f64" else 1e-5), f"{name}: rel-L1 {err:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------
+# Rows next to the step, recorded by oracle/gen_reference_aux_vectors.py from
+# the reference's own time_integration: SnapshotData of return_snapshots runs, and driven-turbulence
+# runs together with the noise the reference drew (the stand-in's random stream is not JAX's, so the
+# noise is an input here, not something to reproduce).
+AUX_DIR = os.path.join(HERE, "golden", "reference_vectors_aux")
+SNAP_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(AUX_DIR, "snap_*.npz")))
+FORCED_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(AUX_DIR, "forced_*.npz")))
+SERIES = ("total_mass", "total_energy", "internal_energy", "kinetic_energy")
+
+
+def load_aux(name):
+    z = np.load(os.path.join(AUX_DIR, name + ".npz"))
+    return z, json.loads(str(z["spec"]))
+
+
+def build_snap(spec):
+    dim, mhd = spec["dim"], spec["mhd"]
+    dtype = np.float64 if spec["dtype"] == "f64" else np.float32
+    st = ax.SnapshotSettings(return_states=True, return_final_state=True, return_total_mass=True,
+                             return_total_energy=True, return_internal_energy=True, return_kinetic_energy=True,
+                             return_radial_momentum=dim > 1, return_magnetic_divergence=mhd and dim == 3)
+    bnd = {0: "open", 1: "reflective", 2: "periodic"}[spec["boundary"]]
+    config, params, rv = pr.make(dim, spec["n"], mhd=mhd, dtype=dtype, boundaries=bnd, return_snapshots=True,
+                                 num_snapshots=spec["num_snapshots"], snapshot_settings=st,
+                                 numerical_precision=oc.SINGLE_PRECISION)  # the reference's default
+    return config, params._replace(t_end=spec["t_end"]), rv, dtype
+
+
+def test_aux_vectors_present():
+    assert len(SNAP_NAMES) >= 6 and len(FORCED_NAMES) >= 2
+
+
+@pytest.mark.parametrize("name", SNAP_NAMES)
+def test_oracle_reproduces_reference_snapshots(name):
+    z, spec = load_aux(name)
+    config, params, rv, dtype = build_snap(spec)
+    dim, mhd, ns = spec["dim"], spec["mhd"], spec["num_snapshots"]
+    centers = ax.get_helper_data(config, dtype=dtype).geometric_centers if dim > 1 else None
+    ref, rec, steps = fo.time_integration_snapshots(z["initial_state"], fo.Opts.from_config(config, params), ns,
+                                                    box_size=config.box_size, centers=centers)
+    tol = 1e-13 if dtype == np.float64 else 2e-6
+    assert steps == int(z["num_iterations"]) and rec["current_checkpoint"] == int(z["current_checkpoint"])
+    np.testing.assert_allclose(rec["time_points"], z["time_points"], rtol=tol, atol=0)
+    assert pr.rel_l1(ref, z["final_state"], dim, mhd) <= tol
+    for k in range(min(ns, int(z["current_checkpoint"]))):
+        assert pr.rel_l1(rec["states"][k], z["states"][k], dim, mhd) <= tol
+    for f in SERIES + (("radial_momentum",) if dim > 1 else ()) + (("magnetic_divergence",) if mhd and dim == 3 else ()):
+        scale = max(np.abs(z[f]).max(), np.abs(z["kinetic_energy"]).max())
+        np.testing.assert_allclose(rec[f], z[f], rtol=tol * 10, atol=tol * 10 * scale)
+
+
+@pytest.mark.parametrize("name", FORCED_NAMES)
+def test_oracle_reproduces_reference_driven_turbulence(name):
+    z, spec = load_aux(name)
+    dtype = np.float64 if spec["dtype"] == "f64" else np.float32
+    tf = oc.TurbulentForcingConfig(turbulent_forcing=True)
+    config, params, rv = pr.make(3, spec["n"], mhd=True, dtype=dtype, boundary_handling=oc.PERIODIC_ROLL,
+                                 turbulent_forcing_config=tf, numerical_precision=oc.SINGLE_PRECISION)
+    params = params._replace(t_end=spec["t_end"])
+    assert params.turbulent_forcing_params.energy_injection_rate == spec["energy_injection_rate"]
+    out, steps, time = fo.time_integration_forced(z["initial_state"], fo.Opts.from_config(config, params),
+                                                  list(z["noise"]), spec["energy_injection_rate"], config.box_size)
+    assert steps == spec["steps"]
+    assert pr.rel_l1(out, z["final_state"], 3, True) <= (1e-13 if dtype == np.float64 else 2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SNAP_NAMES)
+def test_cuda_reproduces_reference_snapshots(cuda, name):
+    z, spec = load_aux(name)
+    config, params, rv, dtype = build_snap(spec)
+    dim, mhd, ns = spec["dim"], spec["mhd"], spec["num_snapshots"]
+    data = ax.time_integration(z["initial_state"], config, params, rv)
+    assert isinstance(data, ax.SnapshotData)
+    tol = 1e-11 if dtype == np.float64 else 2e-5
+    assert data.num_iterations == int(z["num_iterations"]) and data.current_checkpoint == int(z["current_checkpoint"])
+    np.testing.assert_allclose(data.time_points, z["time_points"], rtol=tol, atol=0)
+    assert pr.rel_l1(data.final_state, z["final_state"], dim, mhd) <= tol
+    for k in range(min(ns, int(z["current_checkpoint"]))):
+        assert pr.rel_l1(data.states[k], z["states"][k], dim, mhd) <= tol
+    for f in SERIES:
+        np.testing.assert_allclose(getattr(data, f), z[f], rtol=max(tol, 1e-5 if dtype == np.float32 else 0))
+    if dim > 1:
+        scale = np.abs(z["kinetic_energy"]).max()
+        np.testing.assert_allclose(data.radial_momentum, z["radial_momentum"], atol=1e-4 * scale, rtol=1e-4)
+    if mhd and dim == 3:
+        np.testing.assert_allclose(data.magnetic_divergence, z["magnetic_divergence"], rtol=1e-3,
+                                   atol=1e-5 * np.abs(z["initial_state"][-3:]).max() * spec["n"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FORCED_NAMES)
+def test_cuda_reproduces_reference_driven_turbulence(cuda, name):
+    import torch
+    from astronomix_b200 import forcing as fm
+    from astronomix_b200 import stepping as ti
+    z, spec = load_aux(name)
+    dtype = np.float64 if spec["dtype"] == "f64" else np.float32
+    tf = oc.TurbulentForcingConfig(turbulent_forcing=True)
+    config, params, rv = pr.make(3, spec["n"], mhd=True, dtype=dtype, boundary_handling=oc.PERIODIC_ROLL,
+                                 turbulent_forcing_config=tf, numerical_precision=oc.SINGLE_PRECISION)
+    params = params._replace(t_end=spec["t_end"])
+    noises = [torch.from_numpy(x).to(cuda) for x in z["noise"]]
+    final, _, info = fm.integrate_per_step(torch.from_numpy(z["initial_state"]).to(cuda), "torch_cuda", config, params,
+                                           rv, None, ti._from_device, noise_fn=lambda step: noises[step].clone())
+    assert info[0] == spec["steps"]
+    assert pr.rel_l1(final.cpu().numpy(), z["final_state"], 3, True) <= (1e-11 if dtype == np.float64 else 2e-5)
