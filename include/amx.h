@@ -124,13 +124,21 @@ AMX_API int amx_unpad(const amx_desc* d, const void* seam_in, void* unpadded_out
 AMX_API int amx_boundary_fill(const amx_desc* d, void* seam_inout, int nrows, int type_handled, void* stream);
 
 /* _finite_volume/_timestep_estimation/_timestep_estimator.py:95-218 _cfl_time_step:
- * seam state -> dt (device scalar of desc->dtype at dt_out). */
+ * seam state -> dt (device scalar of desc->dtype at dt_out).  Like the reference, the reduction runs
+ * over the array it is given: with AMX_GHOST_CELLS the ghost cells of the seam array take part
+ * (SURVEY.md Q3), whatever they hold. */
 AMX_API int amx_cfl(const amx_desc* d, const void* seam_state, void* dt_out, void* ws, void* stream);
 
 /* _finite_volume/_state_evolution/evolve_state.py:497-600 _evolve_state_fv: one hydro step
  * (RK2-SSP unsplit :419-488 over :339-414, or Strang-split MUSCL sweeps :168-325 over
  * :53-163) or, for desc->mhd, hydro(dt/2) . magnetic_update(dt) . hydro(dt/2)
- * (_magnetic_update/_magnetic_field_update.py:37-242).  dt is read from device memory. */
+ * (_magnetic_update/_magnetic_field_update.py:37-242).  dt is read from device memory.
+ * Ghost cells of seam_out: the fills the reference's trailing _boundary_handler calls leave.
+ * One configuration differs, as it does in the reference: unsplit MHD with a reflective side.  There
+ * the RK2 combine (evolve_state.py:456-469, no refill) mixes the INPUT's ghost gas cells with those of
+ * the second stage, and magnetic_update fills ghost velocities with the 3-vector flip rule (Q12), so the
+ * ghost gas cells of seam_out are a function of the ghost gas cells of seam_in ("ghost shell",
+ * DESIGN.md 3.6) and the next amx_cfl on seam_out sees them. */
 AMX_API int amx_step(const amx_desc* d, const void* seam_in, void* seam_out, const void* dt_dev,
              void* ws, void* stream, amx_stats* stats_or_null);
 
@@ -145,7 +153,10 @@ AMX_API int amx_integrate(const amx_desc* d, const void* unpadded_in, void* unpa
 /* The same loop resumed at simulation time t_start and also ending (without clipping dt) as soon as
  * time >= t_stop: the segments between two snapshots of time_integration.py:397-570, whose
  * snapshot condition `time >= checkpoint * t_end / num_snapshots` is tested at the start of a step.
- * stats->time is the absolute time reached. */
+ * stats->time is the absolute time reached.
+ * Unsplit MHD with a reflective side keeps its ghost shell (see amx_step) in `ws`: a segment with
+ * t_start != 0 continues from the shell the previous segment on the SAME ws left (checked by a stamp
+ * of the problem shape; without one the shell restarts from images of the interior cells). */
 AMX_API int amx_integrate_from(const amx_desc* d, const void* unpadded_in, void* unpadded_out, double t_start,
                   double t_stop, double t_end, int64_t max_steps, void* ws, void* stream,
                   amx_stats* stats_or_null);

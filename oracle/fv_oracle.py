@@ -6,19 +6,20 @@ SURVEY.md §8.  It exists to *check* the CUDA path: only ``tests/``,
 legs may import it.  Nothing under ``astronomix_b200/`` imports it and the product path
 raises when the CUDA library is missing; there is no CPU fallback.
 
-How it is pinned: the reference cannot be imported here (needs jax,
-equinox, astropy; none installed, no network), and it ships exactly one numerical
-fixture for this path, ``tests/mhd_tests/final_state_orszag_tang.npz``.  Run in that
-fixture's configuration (SPLIT + MUSCL-Hancock, HLL, minmod, periodic ghost cells,
-implicit midpoint at tol 1e-10, fp64, 3001 steps) this restatement reproduces the file
-to ~1e-13 relative L1 (``oracle/pin_orszag_tang.py`` -> ``tests/golden/pin_orszag_tang.json``,
-re-checked from a late checkpoint by ``tests/test_oracle_pin.py``).  That pins every
-cell-level function shared by all configurations (limited slopes, HLL, Euler flux,
-cons<->prim, periodic ghost fill, pad/unpad, split CFL, Strang MHD ordering, the
-magnetic fixed point, curl2D, cross, end-time logic).  NOT pinned by any reference
-artefact -- "parity unpinned" for these, they are restated line by line and guarded by
-invariants instead: the UNSPLIT/RK2 driver, unsplit CFL, HLLC / HLLC-LM / hybrid / LF
-fluxes, the other limiters, every 3-D path (curl3D), fp32 behaviour.
+How it is pinned.  (1) Against outputs of the reference itself run here: the
+unmodified sources under /root/reference/astronomix are executed on NumPy through
+``oracle/ref_on_numpy.py`` + ``oracle/jaxshim`` (jax, equinox and astropy cannot be installed),
+``oracle/gen_reference_vectors.py`` / ``gen_reference_aux_vectors.py`` record 121 input/output
+vectors of the reference's public ``time_integration`` (every solver, limiter, dimension,
+boundary kind, both schemes, both precisions, MHD options, snapshots, driven turbulence), and
+``tests/test_reference_vectors.py`` requires this restatement to reproduce each of them
+(bit for bit in practice; bound 1e-13 fp64 / 2e-6 fp32).  (2) Against the one numerical fixture
+the reference ships for this path, ``tests/mhd_tests/final_state_orszag_tang.npz``: run in that
+file's configuration (SPLIT + MUSCL-Hancock, HLL, minmod, periodic ghost cells, implicit midpoint
+at tol 1e-10, fp64, 3001 steps) it reproduces the file to ~1e-13 relative L1
+(``oracle/pin_orszag_tang.py`` -> ``tests/golden/pin_orszag_tang.json``, re-checked from a late
+checkpoint by ``tests/test_oracle_pin.py``).  Not certified by either: XLA's own instruction
+selection (FMA contraction), a round-off-level effect the parity tolerances allow for.
 
 Conventions.  Arrays are ``[var, x(, y(, z))]``.  ``roll(a, k, ax)[i] = a[i-k]``.
 Scalar typing follows the reference under ``jax.jit``: SimulationParams
