@@ -483,8 +483,7 @@ __global__ void pad_kernel(Geom g, int ng, int rows, int gas_rows, View src, Vie
   i[1] = (int)(r % e[1]); r /= e[1];
   i[0] = (int)r;
   long long od = 0, os_gas = 0, os_edge = 0;
-  int flip_row = -1;  // at most the last reflective axis flips; several flips handled below
-  unsigned flipmask = 0;
+  unsigned flipmask = 0;  // bit k: gas row k changes sign (one reflective axis each)
   for (int a = 0; a < g.nd; ++a) {
     const int ia = i[a] - ng;
     od += (long long)ia * dst.s[a];
@@ -502,7 +501,6 @@ __global__ void pad_kernel(Geom g, int ng, int rows, int gas_rows, View src, Vie
     }
     os_gas += (long long)ig * src.s[a];
   }
-  (void)flip_row;
   const T* ps = static_cast<const T*>(src.p);
   T* pd = static_cast<T*>(dst.p);
   for (int k = 0; k < rows; ++k) {

@@ -204,9 +204,7 @@ def _cfl_time_step(primitive_state, grid_spacing, dt_max, gamma, config, registe
     params = oc.SimulationParams(C_cfl=float(C_CFL), gamma=float(gamma), dt_max=float(dt_max))
     cfg = config._replace(grid_spacing=float(grid_spacing))
     desc = _lib.make_desc(cfg, params, _active_shape(cfg, t.shape[1:]), _TORCH_DTYPES[t.dtype])
-    if t.shape[0] != registered_variables.num_vars:
-        # the MHD step calls the estimator with the full state; only the gas rows are read
-        pass
+    # (the MHD loop calls the estimator with the full state; only the gas rows are read)
     ws, ws_ptr = _workspace(desc, t.device)
     dt = torch.empty((), dtype=t.dtype, device=t.device)
     with torch.cuda.device(t.device):

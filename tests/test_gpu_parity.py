@@ -45,7 +45,7 @@ def check(s, config, params, rv, steps, arith, tol=None):
 def test_sod_101(cuda, rs, dtype, arith):
     """BASELINE config 0: 1-D Sod, 101 cells, open boundaries, to t_end = 0.2."""
     config, params, rv = pr.make(1, 101, boundaries="open", dtype=dtype, riemann_solver=rs)
-    check(pr.sod(101, dtype), config, params, rv, -1 if False else 10 ** 6, arith)
+    check(pr.sod(101, dtype), config, params, rv, 10 ** 6, arith)  # step cap far above what t_end needs
 
 
 @pytest.mark.parametrize("arith", ["fast", "strict"])
