@@ -111,9 +111,16 @@ ShellStamp stamp_of(const amx_desc* d) {
   return s;
 }
 
+bool has_jet(const amx_desc* d) { return d->ndim == 2 && d->bc[1][0] == 3; }
+
+// Also with the MHD jet inflow (any scheme, hydro or MHD): its ghost cells hold constants that are not
+// images of interior cells (|v_x| + c = 801 bounds dt from the first step on) and, in the unsplit
+// scheme, drift from them by the rounding of prim(cons(.)).
 bool shell_mode(const amx_desc* d) {
-  if (!d->mhd || d->split != AMX_UNSPLIT || d->boundary_handling != AMX_GHOST_CELLS) return false;
+  if (d->boundary_handling != AMX_GHOST_CELLS) return false;
   if (d->bc[0][0] == AMX_BC_HALO || d->bc[0][1] == AMX_BC_HALO) return false;
+  if (has_jet(d)) return true;
+  if (!d->mhd || d->split != AMX_UNSPLIT) return false;
   for (int a = 0; a < d->ndim; ++a)
     if (d->bc[a][0] == AMX_BC_REFLECTIVE || d->bc[a][1] == AMX_BC_REFLECTIVE) return true;
   return false;
@@ -152,8 +159,12 @@ int validate(const amx_desc* d) {
   for (int a = 0; a < d->ndim; ++a) {
     for (int s = 0; s < 2; ++s) {
       const int b = d->bc[a][s];
-      if (b != AMX_BC_OPEN && b != AMX_BC_REFLECTIVE && b != AMX_BC_PERIODIC && b != AMX_BC_HALO)
-        return fail(b == 3 ? AMX_EUNSUPPORTED : AMX_EINVAL, "boundary code not supported (MHD jet boundary: SURVEY.md f4)");
+      // _geometry/boundaries.py:180-188: the MHD jet inflow only exists as the LEFT y side of a 2-D run
+      // (set anywhere else the reference's handler has no branch for it and the ghost cells go stale)
+      const bool jet_ok = b == 3 && d->ndim == 2 && a == 1 && s == 0 && d->boundary_handling == AMX_GHOST_CELLS;
+      if (b != AMX_BC_OPEN && b != AMX_BC_REFLECTIVE && b != AMX_BC_PERIODIC && b != AMX_BC_HALO && !jet_ok)
+        return fail(b == 3 ? AMX_EUNSUPPORTED : AMX_EINVAL,
+                    "boundary code not supported (the MHD jet boundary is the left y side of a 2-D ghost-cell run only)");
       if (b == AMX_BC_HALO && a != 0) return fail(AMX_EINVAL, "AMX_BC_HALO is only valid on axis 0");
     }
     if ((d->bc[a][0] == AMX_BC_PERIODIC) != (d->bc[a][1] == AMX_BC_PERIODIC))
@@ -161,6 +172,9 @@ int validate(const amx_desc* d) {
     if (d->boundary_handling == AMX_PERIODIC_ROLL && d->bc[a][0] != AMX_BC_PERIODIC && d->bc[a][0] != AMX_BC_HALO)
       return fail(AMX_EINVAL, "PERIODIC_ROLL implies periodic boundaries");
   }
+  if (d->ndim == 2 && d->bc[1][0] == 3 && (d->riemann == AMX_LAX_FRIEDRICHS || (d->limiter == 5 && d->split == AMX_UNSPLIT)))
+    return fail(AMX_EUNSUPPORTED, "MHD jet boundary with LAX_FRIEDRICHS / VAN_ALBADA_PP is not built (their global wave bounds "
+                                  "would have to include the inflow cells)");
   if (!(d->dx > 0) || !(d->gamma > 1) || !(d->C_cfl > 0)) return fail(AMX_EINVAL, "dx, gamma-1, C_cfl must be positive");
   if (d->arithmetic != AMX_ARITH_FAST && d->arithmetic != AMX_ARITH_STRICT) return fail(AMX_EINVAL, "unknown arithmetic mode");
   return AMX_OK;
@@ -201,6 +215,14 @@ Geom geom_of(const amx_desc* d) {
     g.n[a] = d->n[a];
     g.bc[a][0] = d->bc[a][0];
     g.bc[a][1] = d->bc[a][1];
+  }
+  g.jet_lo = g.jet_hi = 0;
+  if (d->ndim == 2 && d->bc[1][0] == 3) {
+    // boundaries.py:412-413,424-428: half_inj_cell_num = int(0.025 / grid_spacing); padded y indices
+    // [num_cells // 2 - h, num_cells // 2 + h) -> unpadded coordinates
+    const int h = (int)(0.025 / d->dx);
+    g.jet_lo = d->n[1] / 2 - h - d->num_ghost;
+    g.jet_hi = d->n[1] / 2 + h - d->num_ghost;
   }
   return g;
 }
@@ -508,6 +530,7 @@ __global__ void pad_kernel(Geom g, int ng, int rows, int gas_rows, View src, Vie
     if (k < gas_rows) {
       v = ps[k * src.vs + os_gas];
       if (flipmask & (1u << k)) v = -v;
+      if (g.nd == 2 && jet_cell(g, i[0] - ng, i[1] - ng)) v = jet_gas_value<T>(k);
     } else {
       v = ps[k * src.vs + os_edge];
     }
@@ -568,12 +591,13 @@ __global__ void ghost_fill_kernel(Geom g, int ng, int rows, int type_handled, Vi
     }
     os += (long long)ig * a.s[ax];
   }
-  if (!ghost || os == od) return;
-  (void)type_handled;
+  const bool jet = g.nd == 2 && jet_cell(g, i[0] - ng, i[1] - ng);
+  if (!ghost || (os == od && !jet)) return;
   T* p = static_cast<T*>(a.p);
   for (int k = 0; k < rows; ++k) {
     T v = p[k * a.vs + os];
     if (flipmask & (1u << k)) v = -v;
+    if (jet) v = type_handled == 0 ? jet_gas_value<T>(k) : jet_vector_value<T>(type_handled, k);
     p[k * a.vs + od] = v;
   }
 }
@@ -742,7 +766,8 @@ struct Engine {
   }
 
   cudaError_t sweep(const View& in, const View& out, int axis, const void* dt, double dt_scale,
-                    const void* alpha_lf, bool want_alpha, void* alpha_t_out, bool guarded) {
+                    const void* alpha_lf, bool want_alpha, void* alpha_t_out, bool guarded,
+                    bool defer_finalize = false) {
     SweepArgs a;
     a.g = g; a.np = np; a.in = in; a.out = out; a.ctl_ro = guarded ? ctl : nullptr;
     a.dt = dt; a.dt_scale = dt_scale; a.axis = axis; a.first_order = d->first_order_fallback;
@@ -752,7 +777,7 @@ struct Engine {
       ProfScope ps(PC_SPLIT_SWEEP, st);
       CKE(strict ? amx_strict::launch_split_sweep(a, st) : amx_fast::launch_split_sweep(a, st));
     }
-    return want_alpha ? finalize_alpha(alpha_t_out, guarded) : cudaSuccess;
+    return (want_alpha && !defer_finalize) ? finalize_alpha(alpha_t_out, guarded) : cudaSuccess;
   }
 
   // evolve_state.py:419-488 / :168-325: gas_in -> gas_out with time step dt*scale.
@@ -782,8 +807,15 @@ struct Engine {
     for (int k = 0; k < ns; ++k) {
       const bool last = k == ns - 1;
       const View* dst = last ? &gas_out : ((k & 1) ? &tmpB : &tmpA);
-      CKE(sweep(*src, *dst, axes[k], dt_ptr(), scale * frac[k], alpha_ptr(), (last && final_alpha) || lf, nullptr, true));
+      const bool want = (last && final_alpha) || lf;
+      const bool defer = last && shell_on;
+      CKE(sweep(*src, *dst, axes[k], dt_ptr(), scale * frac[k], alpha_ptr(), want, nullptr, true, defer));
       src = dst;
+    }
+    if (shell_on) {  // a sweep ends with a ghost fill: the shell is the fill of the result (images / jet constants)
+      CKE(shell(3, shell_src, shell_dst, nullptr, &gas_out, nullptr, final_alpha, true));
+      shell_src = shell_dst;
+      if (final_alpha || lf) return finalize_alpha(nullptr, true);
     }
     return cudaSuccess;
   }
@@ -938,7 +970,7 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
   static const bool nosync = [] { const char* e = getenv("AMX_NOSYNC"); return e && e[0] == '1'; }();
   if (nosync) {
     CK(E.mag_final(G, Gf, Bout, X, -1, E.lf, nullptr, true));
-    if (E.shell_on) CK(E.shell(1, E.shell_src, E.shell_dst, &G, nullptr, X, false, true));
+    if (E.shell_on && d->split == AMX_UNSPLIT) CK(E.shell(1, E.shell_src, E.shell_dst, &G, nullptr, X, false, true));
     CK(E.hydro(Gf, sout, A, X[0], 0.5, true));
     return AMX_OK;
   }
@@ -953,7 +985,7 @@ int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
   }
   if (!m->done) *kspec = m->mag_iter + 1;
   CK(E.mag_final(G, Gf, Bout, X, -1, E.lf, nullptr, true));
-  if (E.shell_on) CK(E.shell(1, E.shell_src, E.shell_dst, &G, nullptr, X, false, true));
+  if (E.shell_on && d->split == AMX_UNSPLIT) CK(E.shell(1, E.shell_src, E.shell_dst, &G, nullptr, X, false, true));
   // X buffers are free again: reuse X[0] rows as sweep scratch
   CK(E.hydro(Gf, sout, A, X[0], 0.5, true));
   return AMX_OK;

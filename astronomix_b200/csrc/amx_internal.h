@@ -10,7 +10,7 @@ namespace amx {
 constexpr int kAlphaSlots = 1024;  // spread of the per-block wave-bound atomics
 
 // boundary codes (include/amx.h)
-enum : int { BC_OPEN = 0, BC_REFLECTIVE = 1, BC_PERIODIC = 2, BC_HALO = 4 };
+enum : int { BC_OPEN = 0, BC_REFLECTIVE = 1, BC_PERIODIC = 2, BC_JET = 3, BC_HALO = 4 };
 
 // Strided view of a [rows][x][y][z] array; p points at row 0, FIRST ACTIVE cell.
 struct View {
@@ -23,7 +23,26 @@ struct Geom {
   int nd;
   int n[3];      // active cells per axis (absent axes: 1)
   int bc[3][2];  // boundary code per axis and side
+  // MHD jet inflow (_geometry/boundaries.py:399-441; 2-D, y-left code BC_JET): the ghost cells of the
+  // x-LEFT side whose y index lies in [jet_lo, jet_hi) (unpadded coordinates) hold constants; the
+  // y-left side itself is an open side.  jet_hi <= jet_lo: no jet.
+  int jet_lo, jet_hi;
 };
+
+// the reference writes state[:, 0:ng, N/2-h : N/2+h] on the padded array, i.e. after every other fill
+__host__ __device__ inline bool jet_cell(const Geom& g, int ix, int iy) {
+  return g.jet_hi > g.jet_lo && ix < 0 && iy >= g.jet_lo && iy < g.jet_hi;
+}
+// boundaries.py:418-421: gas rows (rho, v_x, v_y, p) = (5/3, 800, 0, 1); velocity (800, 0, 0); B (sqrt(200), 0, 0)
+template <typename T>
+__host__ __device__ inline T jet_gas_value(int row) {
+  return row == 0 ? (T)(5.0 / 3.0) : (row == 1 ? (T)800.0 : (row == 3 ? (T)1.0 : (T)0.0));
+}
+template <typename T>
+__host__ __device__ inline T jet_vector_value(int type_handled, int comp) {  // 1 velocity-only, 2 magnetic-only
+  if (comp != 0) return (T)0.0;
+  return type_handled == 1 ? (T)800.0 : (T)14.142135623730951;  // 200 ** 0.5
+}
 
 struct NumPar {
   int dtype;  // 0 f32, 1 f64
@@ -134,7 +153,8 @@ struct AlphaArgs {
 struct ShellArgs {
   Geom g;
   NumPar np;
-  int mode;        // 0 hydro half step, 1 magnetic write-back, 2 wave bounds of the shell as it is
+  int mode;        // 0 hydro half step, 1 magnetic write-back, 2 wave bounds of the shell as it is,
+                   // 3 refill: shell <- ghost fill of u1 (what a split sweep's trailing _boundary_handler leaves)
   int ng;          // ghost cells per side (2)
   View shell_in;   // ND+2 gas rows of a padded array, p at the first ACTIVE cell
   View shell_out;  // updated shell (may be the same array)

@@ -37,7 +37,7 @@ AMX_DI int map_index(int i, int n, int bcl, int bcr, bool& flip) {
   flip = false;
   if (i < 0) {
     if (bcl == BC_PERIODIC) return i + n;
-    if (bcl == BC_OPEN) return 0;
+    if (bcl == BC_OPEN || bcl == BC_JET) return 0;  // boundaries.py:407-410: the jet side itself is an open copy
     if (bcl == BC_REFLECTIVE) { flip = true; return (ND == 1) ? 0 : (-1 - i); }
     return i;  // BC_HALO: ghost planes are resident
   }
@@ -74,11 +74,23 @@ AMX_DI long long offset_of(const View& v, const Idx3& c) {
   return o;
 }
 
+// gas state of an MHD-jet inflow ghost cell (boundaries.py:418: rho, v_x, v_y, p = 5/3, 800, 0, 1)
+template <typename T, int ND>
+AMX_DI Gas<T, ND> jet_gas() {
+  Gas<T, ND> s;
+#pragma unroll
+  for (int k = 0; k < ND + 2; ++k) s.q[k] = jet_gas_value<T>(k);
+  return s;
+}
+
 // gas state of the cell `d` steps from c along axis a (0-based), boundary rules applied
 template <typename T, int ND>
 AMX_DI Gas<T, ND> load_neighbor(const View& v, const Geom& g, const Idx3& c, int a, int d) {
   Idx3 q = c;
   bool flip;
+  if constexpr (ND == 2) {
+    if (a == 0 && jet_cell(g, c.i[0] + d, c.i[1])) return jet_gas<T, ND>();
+  }
   q.i[a] = map_index<ND>(c.i[a] + d, g.n[a], g.bc[a][0], g.bc[a][1], flip);
   Gas<T, ND> s = load_gas<T, ND>(v, offset_of<ND>(v, q));
   if (flip) s.q[a + 1] = -s.q[a + 1];
@@ -232,6 +244,9 @@ template <typename T, int ND>
 AMX_DI Gas<T, ND> load_at(const View& v, const Geom& g, const Idx3& pos) {
   Idx3 q = pos;
   bool flip[ND];
+  if constexpr (ND == 2) {
+    if (jet_cell(g, pos.i[0], pos.i[1])) return jet_gas<T, ND>();
+  }
 #pragma unroll
   for (int k = 0; k < ND; ++k) q.i[k] = map_index<ND>(pos.i[k], g.n[k], g.bc[k][0], g.bc[k][1], flip[k]);
   Gas<T, ND> s = load_gas<T, ND>(v, offset_of<ND>(v, q));
@@ -452,6 +467,14 @@ template <typename T, int ND>
 AMX_DI void load_arg(const MagIterArgs& a, const Idx3& c, int ax, int d, V3<T>& B, V3<T>& v) {
   Idx3 q = c;
   bool flip = false;
+  if constexpr (ND == 2) {
+    // MHD jet inflow cell: every iterate is ghost-filled with the same constants, so is their average
+    if (d != 0 && ax == 0 && jet_cell(a.g, c.i[0] + d, c.i[1])) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { B.x[k] = jet_vector_value<T>(2, k); v.x[k] = jet_vector_value<T>(1, k); }
+      return;
+    }
+  }
   if (d != 0) q.i[ax] = map_index<ND>(c.i[ax] + d, a.g.n[ax], a.g.bc[ax][0], a.g.bc[ax][1], flip);
   const int fc = ax + 1;  // flipped component index
   const long long o0 = offset_of<ND>(a.B0, q), og = offset_of<ND>(a.gas0, q);
@@ -646,19 +669,36 @@ __global__ void __launch_bounds__(256) shell_kernel(const ShellArgs a) {
       }
     }
     if (ghost) {
+      bool jet = false;  // MHD jet inflow cell: its fills are constants, not images
+      if constexpr (ND == 2) jet = jet_cell(a.g, gi.i[0], gi.i[1]);
       Gas<T, ND> G = load_gas<T, ND>(a.shell_in, offset_of<ND>(a.shell_in, gi));
       if (a.mode == 0) {
-        const Gas<T, ND> U0 = cons_from_prim(load_gas<T, ND>(a.u0, offset_of<ND>(a.u0, si)), c);
-        const Gas<T, ND> U1 = cons_from_prim(load_gas<T, ND>(a.u1, offset_of<ND>(a.u1, si)), c);
         const Gas<T, ND> UG = cons_from_prim(G, c);
         Gas<T, ND> Um;
+        if (jet) {
+          const Gas<T, ND> UJ = cons_from_prim(jet_gas<T, ND>(), c);
 #pragma unroll
-        for (int k = 0; k < ND + 2; ++k) {
-          T s2 = T(2) * U1.q[k] - U0.q[k];
-          if (k >= 1 && k <= ND && flip[k - 1]) s2 = -s2;
-          Um.q[k] = T(0.5) * (UG.q[k] + s2);
+          for (int k = 0; k < ND + 2; ++k) Um.q[k] = T(0.5) * (UG.q[k] + UJ.q[k]);
+        } else {
+          const Gas<T, ND> U0 = cons_from_prim(load_gas<T, ND>(a.u0, offset_of<ND>(a.u0, si)), c);
+          const Gas<T, ND> U1 = cons_from_prim(load_gas<T, ND>(a.u1, offset_of<ND>(a.u1, si)), c);
+#pragma unroll
+          for (int k = 0; k < ND + 2; ++k) {
+            T s2 = T(2) * U1.q[k] - U0.q[k];
+            if (k >= 1 && k <= ND && flip[k - 1]) s2 = -s2;
+            Um.q[k] = T(0.5) * (UG.q[k] + s2);
+          }
         }
         G = prim_from_cons(Um, c);
+      } else if (a.mode == 3) {
+        if (jet) {
+          G = jet_gas<T, ND>();
+        } else {
+          G = load_gas<T, ND>(a.u1, offset_of<ND>(a.u1, si));
+#pragma unroll
+          for (int k = 0; k < ND; ++k)
+            if (flip[k]) G.q[k + 1] = -G.q[k + 1];
+        }
       } else if (a.mode == 1) {
         const int fin = a.fixed_final >= 0 ? a.fixed_final : a.ctl_ro->mag_final;
         const View& X = a.X[fin];
@@ -667,8 +707,8 @@ __global__ void __launch_bounds__(256) shell_kernel(const ShellArgs a) {
         T n0 = T(0), nn = T(0), vn[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          vn[k] = __ldg(px + (3 + k) * X.vs);
-          const T v0k = (k < ND) ? s0.q[k + 1] : T(0);
+          vn[k] = jet ? jet_vector_value<T>(1, k) : __ldg(px + (3 + k) * X.vs);
+          const T v0k = jet ? jet_vector_value<T>(1, k) : ((k < ND) ? s0.q[k + 1] : T(0));
           n0 = n0 + sq(rabs(v0k));
           nn = nn + sq(rabs(vn[k]));
         }
@@ -677,7 +717,7 @@ __global__ void __launch_bounds__(256) shell_kernel(const ShellArgs a) {
         for (int k = 0; k < ND; ++k) {
           T v = vn[k];
           // the fill of axis k2 flips 3-vector component k2 + 1
-          if (k >= 1 && flip[k - 1]) v = -v;
+          if (k >= 1 && flip[k - 1] && !jet) v = -v;
           G.q[k + 1] = v;
         }
         G.q[ND + 1] = p2;

@@ -795,6 +795,7 @@ cudaError_t launch_mag(const MagIterArgs& a, cudaStream_t st) {
 // The tiled stage handles 2-D / 3-D grids whose lane axis is contiguous and at least one tile
 // wide; everything else (1-D, tiny grids) stays on the generic kernel.
 bool tiled_stage_supported(const StageArgs& a) {
+  if (a.g.jet_hi > a.g.jet_lo) return false;  // MHD jet inflow cells: generic kernels only
   if (a.np.lim == LIM_VAN_ALBADA_PP) return false;  // multi-axis limiter: generic kernel (amx_kernels.cu)
   if (a.np.rs > RS_LF) return false;                 // HYBRID / AM-HLLC need the compression switch of the cell
   if (a.g.nd == 3)
@@ -819,6 +820,7 @@ static cudaError_t launch_tiled_t(const StageArgs& a, cudaStream_t st) {
 }
 
 bool tiled_mag_supported(const MagIterArgs& a) {
+  if (a.g.jet_hi > a.g.jet_lo) return false;  // MHD jet inflow cells: generic kernels only
   const int la = a.g.nd - 1;
   if (a.g.nd != 2 && a.g.nd != 3) return false;
   const bool unit = a.B0.s[la] == 1 && a.gas0.s[la] == 1 && a.Bk1.s[la] == 1 && a.vk1.s[la] == 1 &&

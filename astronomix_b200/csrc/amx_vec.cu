@@ -961,6 +961,7 @@ cudaError_t launch_stage_vec(const StageArgs& a, cudaStream_t st) {
 
 // fp32, 2-D / 3-D, contiguous 8-byte-aligned rows, even extent along the contiguous axis
 bool vec_mag_supported(const MagIterArgs& a) {
+  if (a.g.jet_hi > a.g.jet_lo) return false;  // MHD jet inflow cells: generic kernels only
   if (a.np.dtype != 0) return false;
   const int nd = a.g.nd;
   if (nd != 2 && nd != 3) return false;
@@ -995,6 +996,7 @@ cudaError_t launch_mag_iter_vec(const MagIterArgs& a, cudaStream_t st) {
 
 // fp32, 2-D / 3-D, in / out / in0 with the same 8-byte-aligned contiguous layout, even lane extent
 bool vec_stage_supported(const StageArgs& a) {
+  if (a.g.jet_hi > a.g.jet_lo) return false;  // MHD jet inflow cells: generic kernels only
   if (a.np.lim == LIM_VAN_ALBADA_PP) return false;  // multi-axis limiter: generic kernel (amx_kernels.cu)
   if (a.np.dtype != 0) return false;
   const int nd = a.g.nd;

@@ -164,6 +164,8 @@ class SlabDriver:
             raise ValueError("slab too thin: need at least 4 planes per rank")
         self.local_n = (self.nxl,) + self.global_n[1:]
         codes = oc.boundary_codes(config)
+        if any(oc.MHD_JET_BOUNDARY in codes[a] for a in range(self.dim)):
+            raise NotImplementedError("slab decomposition with the MHD jet boundary is not built")
         if (config.mhd and config.split == oc.UNSPLIT and config.boundary_handling == oc.GHOST_CELLS
                 and any(oc.REFLECTIVE_BOUNDARY in codes[a] for a in range(self.dim))):
             # the reference's ghost gas cells set dt in this configuration (DESIGN.md "ghost shell");

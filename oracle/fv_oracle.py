@@ -37,7 +37,7 @@ MINMOD, OSHER, DOUBLE_MINMOD, SUPERBEE, VAN_ALBADA, VAN_ALBADA_PP = 0, 1, 2, 3, 
 UNSPLIT, SPLIT = 0, 1
 HLL, HLLC, HLLC_LM, LAX_FRIEDRICHS, HYBRID_HLLC, AM_HLLC = 0, 1, 2, 3, 4, 5
 RK2_SSP, MUSCL = 0, 1
-OPEN_BOUNDARY, REFLECTIVE_BOUNDARY, PERIODIC_BOUNDARY = 0, 1, 2
+OPEN_BOUNDARY, REFLECTIVE_BOUNDARY, PERIODIC_BOUNDARY, MHD_JET_BOUNDARY = 0, 1, 2, 3
 GAS_STATE, VELOCITY_ONLY, MAGNETIC_FIELD_ONLY = 0, 1, 2
 GHOST_CELLS, PERIODIC_ROLL = 0, 1
 IMPLICIT_MIDPOINT, IMPLICIT_EULER = 0, 1
@@ -430,7 +430,24 @@ def boundary_handler(s, o, type_handled=GAS_STATE):
             for i in range(ng):
                 _set_along_axis(s, ax, i, i - 2 * ng)
                 _set_along_axis(s, ax, -i - 1, 2 * ng - i - 1)
+    if o.dim == 2 and o.boundaries[1][0] == MHD_JET_BOUNDARY:
+        _jet_left_boundary(s, o, type_handled)
     return s
+
+
+def _jet_left_boundary(s, o, type_handled):
+    """boundaries.py:180-188, :399-441 (2-D, left y side only): the y ghost rows are an open copy; then the
+    cells [:, 0:ng, N/2-h : N/2+h] of the padded array -- ghost rows of the X-left side, a window of
+    PADDED y indices -- are overwritten with the inflow constants of the array's kind."""
+    ng = o.num_ghost_cells
+    for i in range(ng):
+        _set_along_axis(s, 2, i, ng)
+    n = s.shape[1] - 2 * ng  # config.num_cells
+    h = int(0.025 / o.grid_spacing)
+    B0 = 200 ** 0.5
+    to_set = {GAS_STATE: [5 / 3, 800.0, 0.0, 1.0], VELOCITY_ONLY: [800.0, 0.0, 0.0],
+              MAGNETIC_FIELD_ONLY: [B0, 0.0, 0.0]}[type_handled]
+    s[:, 0:ng, (n // 2 - h):(n // 2 + h)] = np.asarray(to_set, dtype=s.dtype)[:, None, None]
 
 
 def pad(s, o):

@@ -43,7 +43,7 @@ MINMOD, OSHER, DOUBLE_MINMOD, SUPERBEE, VAN_ALBADA, VAN_ALBADA_PP = 0, 1, 2, 3, 
 UNSPLIT, SPLIT = 0, 1
 HLL, HLLC, HLLC_LM, LAX_FRIEDRICHS, HYBRID_HLLC, AM_HLLC = 0, 1, 2, 3, 4, 5
 RK2_SSP, MUSCL = 0, 1
-OPEN, REFLECTIVE, PERIODIC = 0, 1, 2
+OPEN, REFLECTIVE, PERIODIC, MHD_JET = 0, 1, 2, 3
 GHOST_CELLS, PERIODIC_ROLL = 0, 1
 IMPLICIT_MIDPOINT, IMPLICIT_EULER = 0, 1
 SINGLE, DOUBLE = 0, 1
@@ -124,6 +124,18 @@ def all_cases():
                    bnd=[[REFLECTIVE, OPEN], [OPEN, REFLECTIVE]], steps=8, numerical_precision=DOUBLE))
     cs.append(case("mhd3d_reflective_split_muscl", 3, mhd=True, init=("smooth_random", 118), bnd=REFLECTIVE,
                    split=SPLIT, time_integrator=MUSCL, params={"dt_max": 1.0}, numerical_precision=DOUBLE))
+    # MHD jet inflow (tests/mhd_tests/mhd_jet.py): left y side = jet, i.e. constants in a window of the x-left
+    # ghost rows; the CFL reduction sees them (|v_x| + c = 801) from the first step on
+    jet_bnd = [[OPEN, OPEN], [MHD_JET, OPEN]]
+    cs.append(case("mhd2d_jet", 2, mhd=True, n=80, init=("jet",), bnd=jet_bnd, steps=12, numerical_precision=DOUBLE))
+    cs.append(case("mhd2d_jet_f32", 2, mhd=True, n=80, init=("jet",), bnd=jet_bnd, steps=12, dtype="f32"))
+    cs.append(case("mhd2d_jet_hllc_random", 2, mhd=True, n=48, init=("smooth_random", 120), bnd=jet_bnd, steps=8,
+                   riemann_solver=HLLC, numerical_precision=DOUBLE))
+    cs.append(case("mhd2d_jet_split_muscl", 2, mhd=True, n=48, init=("jet",), bnd=jet_bnd, steps=8, split=SPLIT,
+                   time_integrator=MUSCL, numerical_precision=DOUBLE))
+    cs.append(case("hydro2d_jet", 2, n=48, init=("smooth_random", 121), bnd=jet_bnd, steps=8, riemann_solver=HLLC))
+    cs.append(case("mhd2d_jet_reflective_x", 2, mhd=True, n=48, init=("jet",), bnd=[[REFLECTIVE, OPEN], [MHD_JET, REFLECTIVE]],
+                   steps=8, numerical_precision=DOUBLE))
     cs.append(case("hydro2d_mixed_bnd", 2, init=("smooth_random", 76), bnd=[[PERIODIC, PERIODIC], [REFLECTIVE, OPEN]]))
     cs.append(case("mhd3d_mixed_bnd", 3, mhd=True, init=("smooth_random", 77),
                    bnd=[[OPEN, REFLECTIVE], [PERIODIC, PERIODIC], [REFLECTIVE, OPEN]], numerical_precision=DOUBLE))
@@ -164,6 +176,12 @@ def initial_state(c):
         return pr.orszag_tang(n, dtype)
     if kind == "mhd_blast3d":
         return pr.mhd_blast3d(n, dtype)
+    if kind == "jet":  # tests/mhd_tests/mhd_jet.py:68-84
+        s = np.zeros((7 if c["mhd"] else 4, n, n), dtype=dtype)
+        s[0], s[3] = dtype(5 / 3) * dtype(0.1), 1.0
+        if c["mhd"]:
+            s[4] = 200 ** 0.5
+        return s
     if kind == "mhd_blast3d_arena":
         return pr.mhd_blast3d(n, dtype, p_in=100.0, p_out=1.0, B0=10.0, r_inj=0.125)
     raise ValueError(kind)
@@ -210,6 +228,7 @@ def run_reference(c, s0, t_end):
                       ("HLL", HLL), ("HLLC", HLLC), ("HLLC_LM", HLLC_LM), ("LAX_FRIEDRICHS", LAX_FRIEDRICHS),
                       ("HYBRID_HLLC", HYBRID_HLLC), ("AM_HLLC", AM_HLLC), ("RK2_SSP", RK2_SSP), ("MUSCL", MUSCL),
                       ("OPEN_BOUNDARY", OPEN), ("REFLECTIVE_BOUNDARY", REFLECTIVE), ("PERIODIC_BOUNDARY", PERIODIC),
+                      ("MHD_JET_BOUNDARY", MHD_JET),
                       ("GHOST_CELLS", GHOST_CELLS), ("PERIODIC_ROLL", PERIODIC_ROLL),
                       ("IMPLICIT_MIDPOINT", IMPLICIT_MIDPOINT), ("IMPLICIT_EULER", IMPLICIT_EULER),
                       ("SINGLE_PRECISION", SINGLE), ("DOUBLE_PRECISION", DOUBLE)):

@@ -34,7 +34,8 @@ def axis_maps(o, n):
         for j in range(n + 4):
             i = j - 2
             if i < 0:
-                src[j] = {fo.OPEN_BOUNDARY: 0, fo.REFLECTIVE_BOUNDARY: -1 - i, fo.PERIODIC_BOUNDARY: i + n}[bl]
+                src[j] = {fo.OPEN_BOUNDARY: 0, fo.REFLECTIVE_BOUNDARY: -1 - i, fo.PERIODIC_BOUNDARY: i + n,
+                          fo.MHD_JET_BOUNDARY: 0}[bl]  # the jet side itself is an open copy
                 flip[j] = bl == fo.REFLECTIVE_BOUNDARY
             elif i >= n:
                 src[j] = {fo.OPEN_BOUNDARY: n - 1, fo.REFLECTIVE_BOUNDARY: 2 * n - 1 - i, fo.PERIODIC_BOUNDARY: i - n}[br]
@@ -45,9 +46,24 @@ def axis_maps(o, n):
     return maps
 
 
-def image(a, maps, rows_flipped):
+def jet_window(o, n):
+    """padded (x, y) index slices of the MHD jet inflow cells (boundaries.py:424-428), or None"""
+    if o.dim == 2 and o.boundaries[1][0] == fo.MHD_JET_BOUNDARY:
+        h = int(0.025 / o.grid_spacing)
+        return slice(0, 2), slice(n // 2 - h, n // 2 + h)
+    return None
+
+
+def image(a, maps, rows_flipped, jet=None):
     """Interior array [rows, n..] -> padded array of images; rows_flipped[ax] = row that changes sign
-    on a reflective side of axis ax (None: no row)."""
+    on a reflective side of axis ax (None: no row); jet = (window, constants) written last."""
+    out = _image(a, maps, rows_flipped)
+    if jet is not None and jet[0] is not None:
+        out[(slice(None),) + jet[0]] = np.asarray(jet[1], dtype=a.dtype)[:, None, None]
+    return out
+
+
+def _image(a, maps, rows_flipped):
     out = a[(slice(None),) + np.ix_(*[m[0] for m in maps])].copy()
     for ax, (src, flip) in enumerate(maps):
         r = rows_flipped[ax]
@@ -73,8 +89,10 @@ def run_with_shell(s0, o, steps):
     q12_rows = [ax + 1 if ax + 1 < 3 else None for ax in range(dim)]  # 3-vector rule (Q12)
     ng = dim + 2
 
+    win = jet_window(o, n)
+    jet_gas, jet_v = (win, [5 / 3, 800.0, 0.0, 1.0]), (win, [800.0, 0.0, 0.0])
     s = fo.prepare_state(s0, o)
-    G = image(s0[:ng], maps, gas_rows)  # time_integration.py:281-284: initial fill of the gas rows
+    G = image(s0[:ng], maps, gas_rows, jet_gas)  # time_integration.py:281-284: initial fill of the gas rows
     worst = {"ghost": 0.0, "dt": 0.0}
 
     def compare(G, padded_gas):
@@ -84,7 +102,12 @@ def run_with_shell(s0, o, steps):
     def hydro_shell(G, U, U1):
         cS2 = t_(2) * fo.conserved_state_from_primitive(U1, gamma, o_gas) - fo.conserved_state_from_primitive(U, gamma, o_gas)
         cG = fo.conserved_state_from_primitive(G, gamma, o_gas)
-        return fo.primitive_state_from_conserved(t_(0.5) * (cG + image(cS2, maps, gas_rows)), gamma, o_gas)
+        cF = image(cS2, maps, gas_rows)
+        if win is not None:  # the second stage's fill holds the inflow constants there: cons(constants)
+            const = np.broadcast_to(np.asarray(jet_gas[1], dtype=G.dtype)[:, None, None], G.shape)
+            cJ = fo.conserved_state_from_primitive(np.ascontiguousarray(const), gamma, o_gas)
+            cF[(slice(None),) + win] = cJ[(slice(None),) + win]
+        return fo.primitive_state_from_conserved(t_(0.5) * (cG + cF), gamma, o_gas)
 
     o_gas = o  # cons/prim read only dim and the row indices of the gas rows
     time = t_(0.0)
@@ -109,7 +132,7 @@ def run_with_shell(s0, o, steps):
         vn[:dim] = gas2[inner][1:1 + dim]
         if dim == 2:  # the dropped v_z increment (Q5) still enters |v_n|: recompute it like the iterate buffer holds it
             vn[2] = _vz_increment(B, gas1, B2, dt, o)[(slice(2, -2),) * dim]
-        v0g, vng = image(v0, maps, q12_rows), image(vn, maps, q12_rows)
+        v0g, vng = image(v0, maps, q12_rows, jet_v), image(vn, maps, q12_rows, jet_v)
         g53 = 5 / 3
         E = fo.total_energy_from_primitives(G[0], fo._norm0(v0g), G[ng - 1], g53)
         E2 = E - t_(0.5) * G[0] * fo._norm0(v0g) ** 2 + t_(0.5) * G[0] * fo._norm0(vng) ** 2
@@ -146,6 +169,7 @@ CASES = [
     (2, 24, "reflective", np.float64, 1e-8),   # 2-D: |v_n| needs the dropped v_z, known here to the fixed-point tolerance only
     (3, 12, "reflective", np.float32, 1e-5),
     (3, 12, "open", np.float64, 1e-13),
+    (2, 48, "jet", np.float64, 1e-8),
 ]
 
 
@@ -155,6 +179,10 @@ def test_shell_recurrence_reproduces_the_oracles_ghost_cells(dim, n, bnd, dtype,
         b = oc.BoundarySettings1D
         bs = oc.BoundarySettings(b(oc.OPEN_BOUNDARY, oc.REFLECTIVE_BOUNDARY), b(oc.PERIODIC_BOUNDARY, oc.PERIODIC_BOUNDARY),
                                  b(oc.REFLECTIVE_BOUNDARY, oc.OPEN_BOUNDARY))
+    elif bnd == "jet":
+        b = oc.BoundarySettings1D
+        bs = oc.BoundarySettings(b(oc.OPEN_BOUNDARY, oc.OPEN_BOUNDARY), b(oc.MHD_JET_BOUNDARY, oc.OPEN_BOUNDARY),
+                                 b(oc.OPEN_BOUNDARY, oc.OPEN_BOUNDARY))
     else:
         bs = bnd
     s0 = pr.smooth_random(dim, n, mhd=True, seed=74, dtype=dtype)
