@@ -45,8 +45,11 @@ enum { AMX_UNSPLIT = 0, AMX_SPLIT = 1 };
 enum { AMX_HLL = 0, AMX_HLLC = 1, AMX_HLLC_LM = 2, AMX_LAX_FRIEDRICHS = 3, AMX_HYBRID_HLLC = 4, AMX_AM_HLLC = 5 };
 enum { AMX_RK2_SSP = 0, AMX_MUSCL = 1 };
 /* AMX_BC_HALO: the ghost planes on that side exist in memory and were filled by the caller
- * (neighbour rank's cells in a slab decomposition); only valid on axis 0. */
-enum { AMX_BC_OPEN = 0, AMX_BC_REFLECTIVE = 1, AMX_BC_PERIODIC = 2, AMX_BC_HALO = 4 };
+ * (neighbour rank's cells in a slab decomposition); only valid on axis 0.
+ * AMX_BC_MHD_JET (_geometry/boundaries.py:180-188, :399-441): only valid as bc[1][0] of a 2-D
+ * AMX_GHOST_CELLS run -- the y-left side is an open copy and the x-left ghost rows hold the inflow
+ * constants in a window of y; not with LAX_FRIEDRICHS / VAN_ALBADA_PP. */
+enum { AMX_BC_OPEN = 0, AMX_BC_REFLECTIVE = 1, AMX_BC_PERIODIC = 2, AMX_BC_MHD_JET = 3, AMX_BC_HALO = 4 };
 enum { AMX_GHOST_CELLS = 0, AMX_PERIODIC_ROLL = 1 };
 enum { AMX_IMPLICIT_MIDPOINT = 0, AMX_IMPLICIT_EULER = 1 };
 /* arithmetic: FAST = contracted FMAs, reciprocal multiplies, approximate sqrt/div (fp32);
