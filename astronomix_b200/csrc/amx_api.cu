@@ -89,8 +89,6 @@ struct Layout {
   size_t off_shell;        // ghost shell of the gas state (padded gas rows), shell mode only
 };
 
-// Unsplit MHD with ghost cells and a reflective side: the reference's ghost gas cells are not images
-// of interior cells (Q3 + Q11 + Q12, see ShellArgs) and take part in the CFL reduction.
 // Written in front of the shell once it holds valid data: a resumed segment (t_start != 0) trusts the
 // shell only if the stamp matches its own problem, otherwise it starts from images of the interior.
 struct ShellStamp {
@@ -113,6 +111,8 @@ ShellStamp stamp_of(const amx_desc* d) {
 
 bool has_jet(const amx_desc* d) { return d->ndim == 2 && d->bc[1][0] == 3; }
 
+// Unsplit MHD with ghost cells and a reflective side: the reference's ghost gas cells are not images
+// of interior cells (Q3 + Q11 + Q12, see ShellArgs) and take part in the CFL reduction.
 // Also with the MHD jet inflow (any scheme, hydro or MHD): its ghost cells hold constants that are not
 // images of interior cells (|v_x| + c = 801 bounds dt from the first step on) and, in the unsplit
 // scheme, drift from them by the rounding of prim(cons(.)).
@@ -1233,7 +1233,8 @@ int amx_integrate_from(const amx_desc* d, const void* unpadded_in, void* unpadde
       const View& sin = issued == 0 ? vin : S[(issued - 1) & 1];
       // shell mode: ctl->alpha now holds the bounds of the padded array (what dt needed); the
       // Lax-Friedrichs / PP stages want those of the ghost-FILLED state, i.e. of the interior
-      if (E.shell_on && E.lf && issued > 0) CK(E.alpha_of(sin, nullptr, true));
+      // (also on the first step of a resumed segment, whose initial bounds include the carried shell)
+      if (E.shell_on && E.lf) CK(E.alpha_of(sin, nullptr, true));
       if ((rc = run_step(E, sin, S[issued & 1], &kspec))) return rc;
       ++E.launches;
       if (E.is32) step_end_kernel<float><<<1, 1, 0, E.st>>>(E.ctl);
