@@ -104,3 +104,36 @@ def test_config_mirror_defaults():
         assert (rv.num_vars, rv.pressure_index) == (nv, pi)
     with pytest.raises(ValueError):
         ax.finalize_config(oc.SimulationConfig(dimensionality=2), (4, 8, 16))
+
+
+def test_ghost_shell_workspace_and_jet_validation():
+    """Host logic of the ghost shell: only unsplit MHD with a reflective side, and any
+    run with the MHD jet inflow, reserve the padded gas buffer; the jet code is accepted only where the
+    reference's boundary handler has a branch for it."""
+    lib = _lib.load()
+
+    def ws(**kw):
+        n = C.c_size_t()
+        d = _desc(**kw)
+        rc = lib.amx_workspace_bytes(C.byref(d), C.byref(n))
+        return rc, n.value
+
+    shell3 = 256 + 5 * 20 ** 3 * 4  # stamp + 5 gas rows of the padded 16^3 grid, fp32
+    assert ws(mhd=True, boundaries="reflective")[1] - ws(mhd=True, boundaries="open")[1] == shell3
+    assert ws(mhd=True, boundaries="open")[1] == ws(mhd=True)[1]
+    assert ws(boundaries="reflective")[1] == ws()[1]                                    # hydro: ghost cells stay images
+    split = dict(split=oc.SPLIT, time_integrator=oc.MUSCL)
+    assert ws(mhd=True, boundaries="reflective", **split)[1] == ws(mhd=True, **split)[1]  # sweeps end with a fill
+    b = oc.BoundarySettings1D
+    jet = oc.BoundarySettings(b(oc.OPEN_BOUNDARY, oc.OPEN_BOUNDARY), b(oc.MHD_JET_BOUNDARY, oc.OPEN_BOUNDARY),
+                              b(oc.OPEN_BOUNDARY, oc.OPEN_BOUNDARY))
+    for kw in (dict(mhd=True), dict(), dict(mhd=True, **split)):
+        rc, n_jet = ws(dim=2, boundaries=jet, **kw)
+        assert rc == 0
+        assert n_jet - ws(dim=2, boundaries="open", **kw)[1] == 256 + 4 * 20 ** 2 * 4
+    assert ws(dim=2, boundaries=jet, riemann_solver=oc.LAX_FRIEDRICHS)[0] == 2          # AMX_EUNSUPPORTED
+    assert b"jet" in lib.amx_last_error()
+    wrong_side = oc.BoundarySettings(b(oc.MHD_JET_BOUNDARY, oc.OPEN_BOUNDARY), b(oc.OPEN_BOUNDARY, oc.OPEN_BOUNDARY),
+                                     b(oc.OPEN_BOUNDARY, oc.OPEN_BOUNDARY))
+    assert ws(dim=2, boundaries=wrong_side)[0] == 2
+    assert ws(dim=3, boundaries=jet)[0] == 2
