@@ -99,27 +99,27 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU arms
 def _oracle_worker(args):
-    n, steps, seed = args
+    n, steps, warmup = args
     from astronomix_b200 import problems as pr
     from oracle import fv_oracle as fo
     config, params, rv = pr.make(3, n, mhd=True)
     params = params._replace(t_end=1.0e9)
     s = pr.mhd_blast3d(n, np.float32)
     o = fo.Opts.from_config(config, params)
-    fo.time_integration(s, o, max_steps=1)  # warm caches / allocator
+    fo.time_integration(s, o, max_steps=max(1, warmup))  # untimed: caches, allocator, page faults
     t0 = time.perf_counter()
     fo.time_integration(s, o, max_steps=steps)
     return time.perf_counter() - t0
 
 
-def cpu_oracle_rate(n, steps, procs):
+def cpu_oracle_rate(n, steps, procs, warmup=1):
     """cell-updates/s of the NumPy oracle: `procs` independent replicas of the same workload at
-    n^3 (throughput of all replicas over the slowest replica's wall time)."""
+    n^3 (throughput of all replicas over the slowest replica's wall time); `warmup` untimed steps first."""
     if procs == 1:
-        dt = _oracle_worker((n, steps, 0))
+        dt = _oracle_worker((n, steps, warmup))
         return n ** 3 * steps / dt
     with mp.get_context("spawn").Pool(procs) as pool:
-        times = pool.map(_oracle_worker, [(n, steps, k) for k in range(procs)])
+        times = pool.map(_oracle_worker, [(n, steps, warmup)] * procs)
     return procs * n ** 3 * steps / max(times)
 
 
@@ -129,15 +129,17 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n = 48
-    # each "step" of this arm = one oracle time step on every replica; K steps + W warm-up
-    steps = max(1, min(args.steps, 4))
+    # each "step" of this arm = one oracle time step of every replica (a bounded sample of the 256^3
+    # workload: cores x 48^3 cells); W untimed warm-up steps, then exactly K timed steps (K <= 40 keeps
+    # the run within a minute or two at ~0.5 s per step)
+    steps, warmup = max(1, min(args.steps, 40)), max(1, args.warmup)
     t0 = time.perf_counter()
-    rate = cpu_oracle_rate(n, steps, cores)
+    rate = cpu_oracle_rate(n, steps, cores, warmup)
     wall = time.perf_counter() - t0
     sample = (f"NumPy oracle (restatement of the reference; JAX not installable here), {cores} independent "
               f"replicas of the 3D MHD blast at {n}^3 fp32, {steps} time steps each, one process per core")
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": 1, "ms_per_step": 1e3 * cores * n ** 3 / rate, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * cores * n ** 3 / rate, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(), "wall_s": wall,
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -325,7 +327,7 @@ def run_native(args):
     # ---- CPU baseline beside it (bounded sample of the same workload)
     cpu = None
     if not args.no_cpu:
-        nc, sc = 48, 3
+        nc, sc = 64, 16  # about 10 s of single-core work
         t0c = time.perf_counter()
         rate = cpu_oracle_rate(nc, sc, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
