@@ -580,7 +580,9 @@ __global__ void ghost_fill_kernel(Geom g, int ng, int rows, int type_handled, Vi
     if (ia < 0) {
       ghost = true;
       const int b = g.bc[ax][0];
-      ig = b == BC_PERIODIC ? ia + g.n[ax] : (b == BC_REFLECTIVE ? (g.nd == 1 ? 0 : -1 - ia) : (b == BC_OPEN ? 0 : ia));
+      // (the MHD jet side itself is an open copy, boundaries.py:407-410)
+      ig = b == BC_PERIODIC ? ia + g.n[ax]
+                            : (b == BC_REFLECTIVE ? (g.nd == 1 ? 0 : -1 - ia) : ((b == BC_OPEN || b == BC_JET) ? 0 : ia));
       if (b == BC_REFLECTIVE) flipmask |= 1u << (ax + 1);
     } else if (ia >= g.n[ax]) {
       ghost = true;

@@ -231,3 +231,57 @@ def _evolve_state_fv(primitive_state, dt, gamma, gravitational_constant, config,
         _lib.check(_lib.load().amx_step(C.byref(desc), C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()),
                                         C.c_void_p(dt_dev.data_ptr()), ws_ptr, _stream_ptr(), None))
     return _from_device(out, kind)
+
+
+def _seam_desc(config, padded_shape, dtype, all_open=False):
+    """Descriptor of the active grid behind a padded (seam) array; all_open: every side an open copy."""
+    n = _active_shape(config, padded_shape)
+    desc = _lib.make_desc(config, oc.SimulationParams(), n, _TORCH_DTYPES[dtype])
+    if all_open:
+        for a in range(config.dimensionality):
+            desc.bc[a][0] = desc.bc[a][1] = oc.OPEN_BOUNDARY
+    return desc
+
+
+def _pad(state, config):
+    """Edge-pad by two cells per side and axis; mirror of time_stepping/_utils.py:65-75 (Q8).  In
+    PERIODIC_ROLL mode the reference never pads and this returns a copy."""
+    _lib.require_device()
+    t, kind = _to_device(state)
+    ghost = config.boundary_handling == oc.GHOST_CELLS
+    g = config.num_ghost_cells if ghost else 0
+    out = torch.empty((t.shape[0],) + tuple(int(s) + 2 * g for s in t.shape[1:]), dtype=t.dtype, device=t.device)
+    # an open side copies the edge cell into its ghost cells, which is np.pad(mode="edge") row by row
+    desc = _seam_desc(config, out.shape[1:], t.dtype, all_open=ghost)
+    if t.shape[0] != (config.dimensionality + 2 + (3 if config.mhd else 0)):
+        raise ValueError("_pad expects the full state (gas rows, then the three magnetic rows for MHD)")
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().amx_pad(C.byref(desc), C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()), _stream_ptr()))
+    return _from_device(out, kind)
+
+
+def _unpad(state, config):
+    """Slice the ghost cells off; mirror of time_stepping/_utils.py:19-61."""
+    _lib.require_device()
+    t, kind = _to_device(state)
+    desc = _seam_desc(config, t.shape[1:], t.dtype)
+    out = torch.empty((t.shape[0],) + _active_shape(config, t.shape[1:]), dtype=t.dtype, device=t.device)
+    if t.shape[0] != (config.dimensionality + 2 + (3 if config.mhd else 0)):
+        raise ValueError("_unpad expects the full state (gas rows, then the three magnetic rows for MHD)")
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().amx_unpad(C.byref(desc), C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()), _stream_ptr()))
+    return _from_device(out, kind)
+
+
+def _boundary_handler(primitive_state, config, type_handled=0):
+    """Ghost-cell fill of a padded array; mirror of _geometry/boundaries.py:74-441.  type_handled: 0 gas
+    state, 1 velocity-only, 2 magnetic-field-only (3-row arrays; the flip rule of SURVEY.md Q12 and the
+    MHD jet constants depend on it).  Returns the filled array (the input is not modified unless it is a
+    CUDA tensor, which is filled in place like the reference's donated buffer)."""
+    _lib.require_device()
+    t, kind = _to_device(primitive_state)
+    desc = _seam_desc(config, t.shape[1:], t.dtype)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().amx_boundary_fill(C.byref(desc), C.c_void_p(t.data_ptr()), int(t.shape[0]),
+                                                 int(type_handled), _stream_ptr()))
+    return _from_device(t, kind)

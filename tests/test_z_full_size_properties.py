@@ -84,3 +84,69 @@ def test_cuda_properties_full_size(cuda, case, arith, tol_shift):
         return out
 
     check_properties(run, case, CASES[case]["full"], np.float32, 4, tol_shift, 2e-6)
+
+
+# ---- the layout seams: _pad / _unpad / _boundary_handler on the C-ABI ----
+def _boundaries(dim, kind):
+    b = oc.BoundarySettings1D
+    if kind == "mixed":
+        sides = [b(oc.OPEN_BOUNDARY, oc.REFLECTIVE_BOUNDARY), b(oc.PERIODIC_BOUNDARY, oc.PERIODIC_BOUNDARY),
+                 b(oc.REFLECTIVE_BOUNDARY, oc.OPEN_BOUNDARY)]
+    elif kind == "jet":
+        sides = [b(oc.REFLECTIVE_BOUNDARY, oc.OPEN_BOUNDARY), b(oc.MHD_JET_BOUNDARY, oc.OPEN_BOUNDARY),
+                 b(oc.OPEN_BOUNDARY, oc.OPEN_BOUNDARY)]
+    else:
+        return kind
+    return sides[0] if dim == 1 else oc.BoundarySettings(*sides)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,n,mhd,kind", [(1, 33, False, "open"), (1, 33, False, "reflective"), (1, 32, False, "periodic"),
+                                            (2, 20, False, "mixed"), (2, 20, True, "reflective"), (2, 48, True, "jet"),
+                                            (2, 48, False, "jet"), (3, 10, True, "mixed"), (3, 10, True, "reflective"),
+                                            (3, 10, False, "periodic"), (3, 10, True, "open")])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_layout_seams_vs_oracle(cuda, dim, n, mhd, kind, dtype):
+    """Pure data movement (copies, sign flips, constants): identical bits required."""
+    from astronomix_b200 import stepping as ti
+    s = pr.smooth_random(dim, n, mhd=mhd, seed=3, dtype=dtype)
+    config, params, rv = pr.make(dim, n, mhd=mhd, boundaries=_boundaries(dim, kind), dtype=dtype)
+    o = fo.Opts.from_config(config, params)
+    ng = dim + 2
+    padded = ti._pad(s, config)
+    assert np.array_equal(padded, fo.pad(s, o))                       # _utils.py:65-75: edge mode, every row
+    assert np.array_equal(ti._unpad(padded, config), s)               # _utils.py:19-61
+    gas = ti._boundary_handler(np.ascontiguousarray(padded[:ng]), config, 0)
+    assert np.array_equal(gas, fo.boundary_handler(padded[:ng], o, fo.GAS_STATE))
+    assert np.array_equal(fo.prepare_state(s, o)[:ng], gas)           # time_integration.py:274-286
+    if mhd:
+        rng = np.random.default_rng(4)
+        vec = rng.standard_normal((3,) + padded.shape[1:]).astype(dtype)
+        for kind_, code in ((fo.VELOCITY_ONLY, 1), (fo.MAGNETIC_FIELD_ONLY, 2)):
+            assert np.array_equal(ti._boundary_handler(vec, config, code), fo.boundary_handler(vec, o, kind_))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mhd", [True, False])
+def test_seam_loop_with_jet_inflow(cuda, mhd):
+    """_cfl_time_step -> _evolve_state_fv on padded arrays with the MHD jet boundary, each step fed with
+    the previous output: dt (bounded by the inflow cells, |v_x| + c = 801) and the whole padded state
+    -- ghost cells of the gas AND of the magnetic rows -- must follow the oracle."""
+    from astronomix_b200 import stepping as ti
+    dim, n = 2, 48
+    s = pr.smooth_random(dim, n, mhd=mhd, seed=120, dtype=np.float64)
+    config, params, rv = pr.make(dim, n, mhd=mhd, boundaries=_boundaries(dim, "jet"), dtype=np.float64,
+                                 numerical_precision=oc.DOUBLE_PRECISION)
+    o = fo.Opts.from_config(config, params)
+    g, C, dm = np.float64(params.gamma), np.float64(params.C_cfl), np.float64(params.dt_max)
+    sp_ref = fo.prepare_state(s, o)
+    sp = sp_ref.copy()
+    for _ in range(3):
+        dt_ref = fo.cfl_time_step(sp_ref, o, g, C, dm)
+        dt = ti._cfl_time_step(sp, config.grid_spacing, params.dt_max, params.gamma, config, rv, params.C_cfl)
+        assert abs(float(dt) - float(dt_ref)) <= 1e-13 * float(dt_ref)
+        assert float(dt_ref) < 0.4 * config.grid_spacing / 800.0  # the inflow cells bound it
+        sp_ref = fo.evolve_state_fv(sp_ref, dt_ref, g, o)
+        sp = ti._evolve_state_fv(sp, float(dt_ref), params.gamma, 1.0, config, params, None, rv)
+        assert np.abs(sp - sp_ref).max() <= 1e-12 * np.abs(sp_ref).max()  # every row, ghost cells included
+        assert pr.rel_l1(fo.unpad(sp, o), fo.unpad(sp_ref, o), dim, mhd) < 1e-12
