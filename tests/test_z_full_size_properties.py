@@ -15,7 +15,12 @@ sizes the kernels are held to properties that need no second implementation:
 * for Orszag-Tang: B_z stays exactly zero (the reference's fixture has the same property).
 
 The CPU leg runs the same checks on the oracle at small sizes: it pins the test logic and is an
-invariant test of the oracle in its own right."""
+invariant test of the oracle in its own right.
+
+Further down: the layout seams (_pad / _unpad / _boundary_handler on the C-ABI, identical bits against the
+oracle) and the seam loop with the MHD jet inflow.  This file sorts last on purpose: its GPU legs were
+written after the round's GPU minutes were spent and have not been on hardware yet, so under ``-x`` they
+cannot hide a test that has."""
 import numpy as np
 import pytest
 
