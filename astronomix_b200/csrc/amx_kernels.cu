@@ -402,12 +402,20 @@ __global__ void __launch_bounds__(256) split_sweep_kernel(const SweepArgs a) {
     Gas<T, ND> U = cons_from_prim(sc, c);
     const Gas<T, ND> sm1 = load_neighbor<T, ND>(a.in, a.g, cell, AX, -1);
     const Gas<T, ND> sp1 = load_neighbor<T, ND>(a.in, a.g, cell, AX, +1);
-    T alpha = T(0);
-    if constexpr (RS == RS_LF) alpha = static_cast<const T*>(a.alpha_lf)[AX];
+    T alpha = T(0), alpha_r = T(0);
+    if constexpr (RS == RS_LF) alpha = alpha_r = static_cast<const T*>(a.alpha_lf)[AX];
+    if constexpr (RS == RS_HYBRID_HLLC || RS == RS_AM_HLLC) {
+      // _riemann_solver.py:37-87 hands the sweep's (ghost-filled) input state to the hybrid solvers: flux
+      // array entry i (interface i-1/2) takes the compression switch of cell i, as in the unsplit stage
+      Idx3 pp = cell;
+      pp.i[AX] += 1;
+      alpha = compression_switch<T, ND>(a.in, a.g, cell, sc, c);
+      alpha_r = compression_switch<T, ND>(a.in, a.g, pp, sp1, c);
+    }
     Gas<T, ND> Fl, Fr;
     if (a.first_order) {  // evolve_state.py:72-74
       Fl = riemann<T, ND, RS>(sm1, sc, AX + 1, alpha, c);
-      Fr = riemann<T, ND, RS>(sc, sp1, AX + 1, alpha, c);
+      Fr = riemann<T, ND, RS>(sc, sp1, AX + 1, alpha_r, c);
     } else {
       const Gas<T, ND> sm2 = load_neighbor<T, ND>(a.in, a.g, cell, AX, -2);
       const Gas<T, ND> sp2 = load_neighbor<T, ND>(a.in, a.g, cell, AX, +2);
@@ -417,7 +425,7 @@ __global__ void __launch_bounds__(256) split_sweep_kernel(const SweepArgs a) {
       faces_muscl(sc, slopes<T, ND, -1>(sm1, sc, sp1, a.np.lim, c), AX + 1, hdt, c, lo_c, hi_c);
       faces_muscl(sp1, slopes<T, ND, -1>(sc, sp1, sp2, a.np.lim, c), AX + 1, hdt, c, lo_p, hi_p);
       Fl = riemann<T, ND, RS>(hi_m, lo_c, AX + 1, alpha, c);
-      Fr = riemann<T, ND, RS>(hi_c, lo_p, AX + 1, alpha, c);
+      Fr = riemann<T, ND, RS>(hi_c, lo_p, AX + 1, alpha_r, c);
     }
 #pragma unroll
     for (int k = 0; k < ND + 2; ++k) U.q[k] = U.q[k] + (c.inv_dx * (Fl.q[k] - Fr.q[k])) * dt;
@@ -796,6 +804,16 @@ cudaError_t launch_hydro_stage(const StageArgs& a, cudaStream_t st) {
 template <typename T>
 static cudaError_t launch_split_sweep_t(const SweepArgs& a, cudaStream_t st) {
   if (a.axis < 1 || a.axis > a.g.nd) return cudaErrorInvalidValue;
+#define AMX_LAUNCH_SWEEP(RS_)                                                                            \
+  AMX_DISPATCH_ND(a.g.nd, {                                                                              \
+    const unsigned grid = grid_for<ND>(a.g);                                                             \
+    if (a.axis == 1) split_sweep_kernel<T, ND, RS_, 0><<<grid, 256, 0, st>>>(a);                         \
+    if constexpr (ND >= 2) { if (a.axis == 2) split_sweep_kernel<T, ND, RS_, 1><<<grid, 256, 0, st>>>(a); } \
+    if constexpr (ND >= 3) { if (a.axis == 3) split_sweep_kernel<T, ND, RS_, 2><<<grid, 256, 0, st>>>(a); } \
+  })
+  if (a.np.rs == RS_HYBRID_HLLC) { AMX_LAUNCH_SWEEP(RS_HYBRID_HLLC) return cudaGetLastError(); }
+  if (a.np.rs == RS_AM_HLLC) { AMX_LAUNCH_SWEEP(RS_AM_HLLC) return cudaGetLastError(); }
+#undef AMX_LAUNCH_SWEEP
   AMX_DISPATCH_ND(a.g.nd, AMX_DISPATCH_RS(a.np.rs, {
     const unsigned grid = grid_for<ND>(a.g);
     if (a.axis == 1) split_sweep_kernel<T, ND, RS, 0><<<grid, 256, 0, st>>>(a);

@@ -152,6 +152,14 @@ def all_cases():
     cs.append(case("hydro2d_split_hllc_open", 2, init=("smooth_random", 96), split=SPLIT, time_integrator=MUSCL,
                    riemann_solver=HLLC, bnd=OPEN, params={"dt_max": 1.0}))
     cs.append(case("hydro3d_split_dtmax_clipped", 3, init=("smooth_random", 97), split=SPLIT, time_integrator=MUSCL))
+    # HYBRID_HLLC / AM_HLLC inside the split sweeps (the compression switch of the sweep's input state)
+    for dim, mhd, rs in ((1, False, HYBRID_HLLC), (2, False, HYBRID_HLLC), (2, False, AM_HLLC), (3, False, AM_HLLC),
+                         (3, True, HYBRID_HLLC), (2, True, AM_HLLC)):
+        cs.append(case(f"{'mhd' if mhd else 'hydro'}{dim}d_split_{RS_NAMES[rs]}", dim, mhd=mhd,
+                       init=("smooth_random", 130 + dim + rs), split=SPLIT, time_integrator=MUSCL, riemann_solver=rs,
+                       params={"dt_max": 1.0}, numerical_precision=DOUBLE))
+    cs.append(case("hydro2d_split_hybrid_reflective", 2, init=("smooth_random", 139), split=SPLIT, time_integrator=MUSCL,
+                   riemann_solver=HYBRID_HLLC, bnd=REFLECTIVE, params={"dt_max": 1.0}))
     # parameters off their defaults
     cs.append(case("hydro2d_gamma14_cfl08", 2, init=("smooth_random", 98), riemann_solver=HLLC,
                    params={"gamma": 1.4, "C_cfl": 0.8}))
