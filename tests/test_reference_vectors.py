@@ -58,9 +58,18 @@ def test_oracle_reproduces_reference_vector(name):
 
 # HYBRID_HLLC / AM_HLLC / VAN_ALBADA_PP run on the generic kernels only in unsplit mode; everything
 # recorded here is inside the C-ABI's supported set.
+# vectors whose CUDA leg has not been on hardware yet run from tests/test_z_full_size_properties.py (which
+# sorts last), so that under -x they cannot hide a test that has
+NOT_YET_ON_HARDWARE = tuple(n for n in NAMES if "_split_hybrid" in n or "_split_amhllc" in n)
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("name", [n for n in NAMES if n not in NOT_YET_ON_HARDWARE])
 def test_cuda_reproduces_reference_vector(cuda, name):
+    check_cuda_vector(name)
+
+
+def check_cuda_vector(name):
     from astronomix_b200 import stepping as ti
     s0, ref, spec = load(name)
     config, params, rv = build(spec)

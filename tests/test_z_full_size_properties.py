@@ -155,3 +155,13 @@ def test_seam_loop_with_jet_inflow(cuda, mhd):
         sp = ti._evolve_state_fv(sp, float(dt_ref), params.gamma, 1.0, config, params, None, rv)
         assert np.abs(sp - sp_ref).max() <= 1e-12 * np.abs(sp_ref).max()  # every row, ghost cells included
         assert pr.rel_l1(fo.unpad(sp, o), fo.unpad(sp_ref, o), dim, mhd) < 1e-12
+
+
+# ---- reference vectors whose CUDA leg is new (see tests/test_reference_vectors.py) ----
+import test_reference_vectors as _rv  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _rv.NOT_YET_ON_HARDWARE)
+def test_cuda_reproduces_new_reference_vectors(cuda, name):
+    _rv.check_cuda_vector(name)
