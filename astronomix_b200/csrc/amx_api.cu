@@ -139,8 +139,6 @@ int validate(const amx_desc* d) {
   if (d->dtype != AMX_F32 && d->dtype != AMX_F64) return fail(AMX_EINVAL, "dtype must be AMX_F32 or AMX_F64");
   if (d->mhd && d->ndim == 1) return fail(AMX_EUNSUPPORTED, "MHD currently not supported in 1D.");
   if (d->riemann < AMX_HLL || d->riemann > 5) return fail(AMX_EINVAL, "Riemann solver not supported.");
-  if (d->riemann > AMX_LAX_FRIEDRICHS && d->split == AMX_UNSPLIT && d->limiter == 5)
-    return fail(AMX_EUNSUPPORTED, "HYBRID_HLLC / AM_HLLC with the unsplit VAN_ALBADA_PP reconstruction are not built");
   if (d->limiter < 0 || d->limiter > 5) return fail(AMX_EINVAL, "Unknown limiter.");
   if (d->limiter == 5 && d->split == AMX_UNSPLIT && d->ndim == 1)
     return fail(AMX_EUNSUPPORTED, "VAN_ALBADA_PP in 1-D is not built (the reference's 1-D branch sums over the grid)");

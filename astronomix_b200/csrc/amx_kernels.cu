@@ -361,9 +361,13 @@ __global__ void __launch_bounds__(128) hydro_stage_pp_kernel(const StageArgs a) 
         hi_c.q[k] = sc.q[k] + dc.q[k];
         lo_p.q[k] = sp1.q[k] - dp.q[k];
       }
-      const T al = RS == RS_LF ? alpha[ax] : T(0);
+      T al = RS == RS_LF ? alpha[ax] : T(0), ar = al;
+      if constexpr (RS == RS_HYBRID_HLLC || RS == RS_AM_HLLC) {  // compression switch of the cell right of the interface
+        al = compression_switch<T, ND>(a.in, a.g, cell, sc, c);
+        ar = compression_switch<T, ND>(a.in, a.g, pp, sp1, c);
+      }
       const Gas<T, ND> Fl = riemann<T, ND, RS>(hi_m, lo_c, ax + 1, al, c);
-      const Gas<T, ND> Fr = riemann<T, ND, RS>(hi_c, lo_p, ax + 1, al, c);
+      const Gas<T, ND> Fr = riemann<T, ND, RS>(hi_c, lo_p, ax + 1, ar, c);
 #pragma unroll
       for (int k = 0; k < ND + 2; ++k) U.q[k] = U.q[k] + (c.inv_dx * (Fl.q[k] - Fr.q[k])) * dt;
     }
@@ -771,6 +775,16 @@ static cudaError_t launch_hydro_stage_pp_t(const StageArgs& a, cudaStream_t st) 
   if (a.g.nd < 2 || !a.alpha_lf) return cudaErrorInvalidValue;
   long long total = (long long)a.g.n[0] * a.g.n[1] * (a.g.nd == 3 ? a.g.n[2] : 1);
   const unsigned grid = (unsigned)((total + 127) / 128);
+  if (a.np.rs == RS_HYBRID_HLLC || a.np.rs == RS_AM_HLLC) {
+    if (a.g.nd == 2) {
+      if (a.np.rs == RS_HYBRID_HLLC) hydro_stage_pp_kernel<T, 2, RS_HYBRID_HLLC><<<grid, 128, 0, st>>>(a);
+      else hydro_stage_pp_kernel<T, 2, RS_AM_HLLC><<<grid, 128, 0, st>>>(a);
+    } else {
+      if (a.np.rs == RS_HYBRID_HLLC) hydro_stage_pp_kernel<T, 3, RS_HYBRID_HLLC><<<grid, 128, 0, st>>>(a);
+      else hydro_stage_pp_kernel<T, 3, RS_AM_HLLC><<<grid, 128, 0, st>>>(a);
+    }
+    return cudaGetLastError();
+  }
   AMX_DISPATCH_RS(a.np.rs, {
     if (a.g.nd == 2) hydro_stage_pp_kernel<T, 2, RS><<<grid, 128, 0, st>>>(a);
     else hydro_stage_pp_kernel<T, 3, RS><<<grid, 128, 0, st>>>(a);

@@ -9,7 +9,7 @@ raises when the CUDA library is missing; there is no CPU fallback.
 How it is pinned.  (1) Against outputs of the reference itself run here: the
 unmodified sources under /root/reference/astronomix are executed on NumPy through
 ``oracle/ref_on_numpy.py`` + ``oracle/jaxshim`` (jax, equinox and astropy cannot be installed),
-``oracle/gen_reference_vectors.py`` / ``gen_reference_aux_vectors.py`` record 134 input/output
+``oracle/gen_reference_vectors.py`` / ``gen_reference_aux_vectors.py`` record 138 input/output
 vectors of the reference's public ``time_integration`` (every solver, limiter, dimension,
 boundary kind, both schemes, both precisions, MHD options, snapshots, driven turbulence), and
 ``tests/test_reference_vectors.py`` requires this restatement to reproduce each of them

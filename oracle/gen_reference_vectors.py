@@ -160,6 +160,11 @@ def all_cases():
                        params={"dt_max": 1.0}, numerical_precision=DOUBLE))
     cs.append(case("hydro2d_split_hybrid_reflective", 2, init=("smooth_random", 139), split=SPLIT, time_integrator=MUSCL,
                    riemann_solver=HYBRID_HLLC, bnd=REFLECTIVE, params={"dt_max": 1.0}))
+    # HYBRID_HLLC / AM_HLLC fluxes on the positivity-preserving reconstruction
+    for dim, mhd, rs in ((2, False, HYBRID_HLLC), (2, True, AM_HLLC), (3, False, AM_HLLC), (3, True, HYBRID_HLLC)):
+        cs.append(case(f"{'mhd' if mhd else 'hydro'}{dim}d_{RS_NAMES[rs]}_valbadapp", dim, mhd=mhd,
+                       init=("smooth_random", 140 + dim + rs), riemann_solver=rs, limiter=VAN_ALBADA_PP,
+                       numerical_precision=DOUBLE))
     # parameters off their defaults
     cs.append(case("hydro2d_gamma14_cfl08", 2, init=("smooth_random", 98), riemann_solver=HLLC,
                    params={"gamma": 1.4, "C_cfl": 0.8}))

@@ -52,12 +52,14 @@ def test_workspace_query_and_validation():
     assert lib.amx_workspace_bytes(C.byref(d), C.byref(n)) == 2
     assert b"num_ghost" in lib.amx_last_error()
     d = _desc()
-    d.riemann = oc.HYBRID_HLLC  # unsplit and split; not with the unsplit VAN_ALBADA_PP reconstruction
+    d.riemann = oc.HYBRID_HLLC  # unsplit, split sweeps and the unsplit VAN_ALBADA_PP reconstruction
     assert lib.amx_workspace_bytes(C.byref(d), C.byref(n)) == 0
     d.split, d.time_integrator = oc.SPLIT, oc.MUSCL
     assert lib.amx_workspace_bytes(C.byref(d), C.byref(n)) == 0
     d.split, d.time_integrator, d.limiter = oc.UNSPLIT, oc.RK2_SSP, oc.VAN_ALBADA_PP
-    assert lib.amx_workspace_bytes(C.byref(d), C.byref(n)) == 2
+    assert lib.amx_workspace_bytes(C.byref(d), C.byref(n)) == 0
+    d.riemann = 6
+    assert lib.amx_workspace_bytes(C.byref(d), C.byref(n)) == 1
     d = _desc()
     d.abi_version = 99
     assert lib.amx_workspace_bytes(C.byref(d), C.byref(n)) == 1
