@@ -141,7 +141,7 @@ int validate(const amx_desc* d) {
   if (d->riemann < AMX_HLL || d->riemann > 5) return fail(AMX_EINVAL, "Riemann solver not supported.");
   if (d->limiter < 0 || d->limiter > 5) return fail(AMX_EINVAL, "Unknown limiter.");
   if (d->limiter == 5 && d->split == AMX_UNSPLIT && d->ndim == 1)
-    return fail(AMX_EUNSUPPORTED, "VAN_ALBADA_PP in 1-D is not built (the reference's 1-D branch sums over the grid)");
+    return fail(AMX_EUNSUPPORTED, "VAN_ALBADA_PP does not exist in 1-D (the reference raises there too: reconstruction.py reads velocity_index.x of an int)");
   if (d->split == AMX_UNSPLIT) {
     if (d->time_integrator != AMX_RK2_SSP)
       return fail(AMX_EINVAL, "Only the RK2 SSP time integrator is currently supported for the unsplit scheme.");
