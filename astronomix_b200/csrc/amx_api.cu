@@ -1304,6 +1304,9 @@ int amx_hydro_stage(const amx_desc* d, const void* gas_in, const void* gas0_or_n
   if (rc) return rc;
   if (!ws || !dt_dev) return fail(AMX_EINVAL, "ws / dt_dev is null");
   if (d->riemann == AMX_LAX_FRIEDRICHS && !alpha_lf) return fail(AMX_EINVAL, "Lax-Friedrichs needs alpha_lf");
+  // reconstruction.py:186-193: the PP limiter weights C = alpha / sum(alpha) come from the stage's input
+  if (d->limiter == 5 && d->split == AMX_UNSPLIT && !alpha_lf)
+    return fail(AMX_EINVAL, "VAN_ALBADA_PP needs alpha_lf (wave bounds of the stage's input state)");
   if ((rc = amx_device_check())) return rc;
   Engine E(d, ws, stream);
   const View in = E.user_internal(gas_in), out = E.user_internal(gas_out);
@@ -1480,11 +1483,15 @@ int amx_magnetic_fix_guarded(const amx_desc* d, const void* B0, const void* gas0
   if (!ws || !dt_dev || !gas0) return fail(AMX_EINVAL, "null pointer");
   if (evals_before < 0 || (evals_before == 0) != (bvk_or_null == nullptr))
     return fail(AMX_EINVAL, "bvk must be NULL exactly when evals_before == 0");
+  if (!d->mhd) return fail(AMX_EINVAL, "descriptor is not MHD");
   if ((rc = amx_device_check())) return rc;
   Engine E(d, ws, stream);
   const View vB0 = E.user_internal(B0), vg = E.user_internal(gas0), vk1 = E.user_internal(bvk1);
   View vk;
   if (bvk_or_null) vk = E.user_internal(bvk_or_null);
+  // the re-run goes to the vectorised single-evaluation kernel: same layout rules as the pair launch it repairs
+  if (!E.pair_supported(E.mag_args(vB0, vg, bvk_or_null ? &vk : nullptr, vk1, dt_dev, evals_before, true)))
+    return fail(AMX_EUNSUPPORTED, "pair launches (and their re-run) need 3-D fp32 with periodic y / z and halo or periodic x");
   CK(E.mag_fix(vB0, vg, bvk_or_null ? &vk : nullptr, vk1, dt_dev, evals_before));
   return AMX_OK;
 }

@@ -179,7 +179,11 @@ class SlabDriver:
         self.bcx = oc.boundary_codes(config)[0]
         if config.boundary_handling == oc.PERIODIC_ROLL:
             self.bcx = (oc.PERIODIC_BOUNDARY, oc.PERIODIC_BOUNDARY)
-        self.lf = config.riemann_solver == oc.LAX_FRIEDRICHS
+        # kernels that need the global wave bounds of every stage's INPUT state: the Lax-Friedrichs flux
+        # (_lax_friedrichs.py:61-66) and the unsplit VAN_ALBADA_PP reconstruction (reconstruction.py:186-193,
+        # C = alpha / sum(alpha)); amx_api.cu's Engine makes the same choice
+        self.lf = (config.riemann_solver == oc.LAX_FRIEDRICHS
+                   or (config.limiter == oc.VAN_ALBADA_PP and config.split == oc.UNSPLIT))
         self.tol = 1e-5 if config.numerical_precision == oc.SINGLE_PRECISION else 1e-10
         self.backend = backend if backend is not None else AmxBackend(config, params, self.local_n, dtype, device,
                                                                      arithmetic)
@@ -233,7 +237,12 @@ class SlabDriver:
         self.pack_halos = os.environ.get("AMX_SLAB_PACK", "1") != "0"
         # two fixed-point evaluations per launch where the kernel supports the problem (AMX_SLAB_PAIRS=0: off)
         self.pair_greedy = False  # tests: pair launches regardless of the expected count (exercises the re-run)
+        # The pair kernel computes the intermediate iterate on ghost planes -1 / n with the stencil; that is
+        # only what the reference has there when x is periodic (the while-body refills the ghosts of every
+        # iterate with _boundary_handler, _magnetic_field_update.py:124-125,161-163): physical x sides keep
+        # one evaluation per launch.
         self.pairs = (self.mhd and os.environ.get("AMX_SLAB_PAIRS", "1") != "0"
+                      and self.bcx == (oc.PERIODIC_BOUNDARY, oc.PERIODIC_BOUNDARY)
                       and bool(getattr(self.backend, "pair_supported", lambda: False)()))
 
     # ------------------------------------------------------------------ communication
