@@ -354,10 +354,13 @@ AMX_DI Gas<T, ND> hll_flux(const Gas<T, ND>& L, const Gas<T, ND>& R, int ax, con
     F.q[k] = (SR * FL.q[k] - SL * FR.q[k] + SLSR * (UR.q[k] - UL.q[k])) / den;
   return F;
 #else
-  // Same flux, arranged for the issue slots: one reciprocal per density and per interface,
-  // momenta and energies formed once and shared by the flux and the conserved state,
-  // F = a*FL - b*FR + ab*(UR - UL) with a = SR/(SR-SL), b = SL/(SR-SL), ab = a*SL.
-  T m[2][ND], E[2], un[2], cs[2], pr[2], rho[2];
+  // Same flux, arranged for the FMA pipe.  With a = SR/(SR-SL), b = SL/(SR-SL) (so a*SL = b*SR) and
+  // F_side = un*U + P (P = p in the normal-momentum row, p*un in the energy row, 0 elsewhere):
+  //   F = a*FL - b*FR + a*SL*(UR - UL) = [a(unL - SL)]*UL - [b(unR - SR)]*UR + (a*PL - b*PR),
+  // i.e. two multiply-adds per row on the conserved states instead of forming both fluxes and the
+  // difference of the states; the momenta are never formed (AL*rho and BR*rho multiply the velocities).
+  // Supersonic sides stay exact: SL = 0 gives b = 0, a = 1, F = FL.
+  T un[2], cs[2], pr[2], rho[2], E[2];
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const Gas<T, ND>& W = s == 0 ? L : R;
@@ -367,25 +370,24 @@ AMX_DI Gas<T, ND> hll_flux(const Gas<T, ND>& L, const Gas<T, ND>& R, int ax, con
     cs[s] = rsqrt_((c.gamma * pr[s]) * rdiv(T(1), rho[s]));
     T ke = ND == 3 ? T(1e-20) : T(0);
 #pragma unroll
-    for (int k = 0; k < ND; ++k) {
-      m[s][k] = rho[s] * W.q[k + 1];
-      ke = ke + W.q[k + 1] * W.q[k + 1];
-    }
+    for (int k = 0; k < ND; ++k) ke = ke + W.q[k + 1] * W.q[k + 1];
     E[s] = pr[s] * c.inv_gm1 + (T(0.5) * rho[s]) * ke;
   }
   const T SR = rmax(rmax(un[0] + cs[0], un[1] + cs[1]), T(0));
   const T SL = rmin(rmin(un[0] - cs[0], un[1] - cs[1]), T(0));
   const T iden = rdiv(T(1), SR - SL);
-  const T a = SR * iden, b = SL * iden, ab = a * SL;
+  const T a = SR * iden, b = SL * iden;
+  const T AL = a * (un[0] - SL), BR = b * (un[1] - SR);
+  const T ALr = AL * rho[0], BRr = BR * rho[1];
+  const T apL = a * pr[0], bpR = b * pr[1];
+  const Gas<T, ND>& WL = L;
+  const Gas<T, ND>& WR = R;
   Gas<T, ND> F;
-  F.q[0] = a * m[0][ax - 1] - b * m[1][ax - 1] + ab * (rho[1] - rho[0]);
+  F.q[0] = ALr - BRr;
 #pragma unroll
-  for (int k = 0; k < ND; ++k) {
-    T fl = un[0] * m[0][k], fr = un[1] * m[1][k];
-    if (k == ax - 1) { fl = fl + pr[0]; fr = fr + pr[1]; }
-    F.q[k + 1] = a * fl - b * fr + ab * (m[1][k] - m[0][k]);
-  }
-  F.q[P] = a * (un[0] * (E[0] + pr[0])) - b * (un[1] * (E[1] + pr[1])) + ab * (E[1] - E[0]);
+  for (int k = 0; k < ND; ++k) F.q[k + 1] = ALr * WL.q[k + 1] - BRr * WR.q[k + 1];
+  F.q[ax] = F.q[ax] + (apL - bpR);
+  F.q[P] = (AL * E[0] - BR * E[1]) + (apL * un[0] - bpR * un[1]);
   return F;
 #endif
 }

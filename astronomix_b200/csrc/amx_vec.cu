@@ -521,7 +521,15 @@ struct HG {
   static constexpr int PLFY = ND == 3 ? (TY + 1) * TZ : 0;  // y fluxes: lower interfaces of rows 0 .. TY
   static constexpr int PLFZ = TY * (TQ + 1);                // first halves of the lane-axis flux pairs + edge
   static constexpr int FSLOT = NV * (PLFY + PLFZ);
-  static constexpr size_t smem_bytes = (size_t)(3 * WSLOT + 2 * FSLOT) * sizeof(float);
+  // 3-D: every limited slope is evaluated once.  A thread publishes the upper y face state of its pair
+  // (s + d_y, the L state of the interface above) one plane ahead: rows -1 .. TY-1 at row index 0 .. TY;
+  // the upper z face state of the last cell left of a tile row (L state of the row's first interface)
+  // comes from the halo warp.  2-D keeps one row of 7 warps, where a shuffle cannot cross the warps.
+  static constexpr bool SHARE = ND == 3;
+  static constexpr int PLPY = SHARE ? (TY + 1) * TZ : 0;   // floats per variable per plus slot
+  static constexpr int PSLOT = NV * PLPY;
+  static constexpr int ESLOT = SHARE ? NV * 16 : 0;        // left-edge L states: [NV][row]
+  static constexpr size_t smem_bytes = (size_t)(3 * WSLOT + 2 * FSLOT + 2 * PSLOT + 2 * ESLOT) * sizeof(float);
 };
 
 template <int ND, int RS, int LIM, bool COMBINE>
@@ -530,11 +538,15 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
   using G = HG<ND>;
   constexpr int NV = G::NV, TY = G::TY, TQ = G::TQ, TZ = G::TZ, YO = G::YO, RSW = G::RSW, PLW = G::PLW;
   constexpr int WSLOT = G::WSLOT, PLFY = G::PLFY, PLFZ = G::PLFZ, FSLOT = G::FSLOT;
+  constexpr bool SHARE = G::SHARE;
+  constexpr int PLPY = G::PLPY, PSLOT = G::PSLOT, ESLOT = G::ESLOT;
   constexpr int LA = ND - 1;  // lane (contiguous) axis
   constexpr int kCompute = 32 * kHydroCW;
   extern __shared__ __align__(16) float smem[];
   float* const win = smem;                 // [3][NV][WY][RSW]
   float* const flx = smem + 3 * WSLOT;     // [2][NV][PLFY + PLFZ]
+  float* const ply = flx + 2 * FSLOT;      // [2][NV][TY + 1][TZ]  upper y face states, slot = plane parity
+  float* const edl = ply + 2 * PSLOT;      // [2][NV][16]          upper z face state of cell z0-1 per row
 
   const Consts<F2> c = make_consts2(a.np);
   const Geom& g = a.g;
@@ -652,22 +664,36 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
       }
     };
     // fluxes on the upper tile edges of plane x (window slot s complete and visible)
-    auto edge_fluxes = [&](int s, int fs) {
+    auto edge_fluxes = [&](int s, int fs, int par) {
       const float* w = win + s * WSLOT;
       float* f = flx + fs * FSLOT;
       if constexpr (ND == 3) {
         if (l < TQ) {
           if (l < tqa) {  // interface below row ta (pair l)
             const float* wp = w + (ta + 2) * RSW + 4 + 2 * l;
-            F2 m2[NV], m1[NV], s0[NV], p1[NV];
+            Gas<F2, ND> F;
+            if constexpr (SHARE) {
+              // L = upper face state of tile row ta-1 (published by its thread), R = lower face state of halo row ta
+              const float* pl = ply + par * PSLOT + ta * TZ + 2 * l;
+              Gas<F2, ND> L, R;
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-              m2[k] = lds2(wp + k * PLW - 2 * RSW);
-              m1[k] = lds2(wp + k * PLW - RSW);
-              s0[k] = lds2(wp + k * PLW);
-              p1[k] = lds2(wp + k * PLW + RSW);
+              for (int k = 0; k < NV; ++k) {
+                const F2 m1 = lds2(wp + k * PLW - RSW), s0 = lds2(wp + k * PLW), p1 = lds2(wp + k * PLW + RSW);
+                L.q[k] = lds2(pl + k * PLPY);
+                R.q[k] = s0 - half_slope<LIM>(s0 - m1, p1 - s0, lim, c);
+              }
+              F = riemann<F2, ND, RS>(L, R, 2, alpha_lf[1], c);
+            } else {
+              F2 m2[NV], m1[NV], s0[NV], p1[NV];
+#pragma unroll
+              for (int k = 0; k < NV; ++k) {
+                m2[k] = lds2(wp + k * PLW - 2 * RSW);
+                m1[k] = lds2(wp + k * PLW - RSW);
+                s0[k] = lds2(wp + k * PLW);
+                p1[k] = lds2(wp + k * PLW + RSW);
+              }
+              F = edge_flux(m2, m1, s0, p1, 2, alpha_lf[1]);
             }
-            const Gas<F2, ND> F = edge_flux(m2, m1, s0, p1, 2, alpha_lf[1]);
 #pragma unroll
             for (int k = 0; k < NV; ++k) sts2(f + k * (PLFY + PLFZ) + ta * TZ + 2 * l, F.q[k]);
           }
@@ -690,6 +716,34 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
         for (int k = 0; k < NV; ++k) f[k * (PLFY + PLFZ) + PLFY + r * (TQ + 1) + tqa] = F.q[k].x;
       }
     };
+    // SHARE: face states that compute threads cannot get from a neighbour thread, from the complete window
+    // slot s into parity slot q: the upper y face state of halo row y0-1 (pair l) and the upper z face
+    // state of cell z0-1 of tile row r (the L states of the tile's lowest y / first z interfaces)
+    auto halo_plus = [&](int s, int q) {
+      if constexpr (SHARE) {
+        const float* w = win + s * WSLOT;
+        if (l < TQ) {
+          if (l < tqa) {
+            const float* wp = w + RSW + 4 + 2 * l;  // window row 1 = y0-1
+            float* pp = ply + q * PSLOT + 2 * l;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              const F2 m1 = lds2(wp + k * PLW - RSW), s0 = lds2(wp + k * PLW), p1 = lds2(wp + k * PLW + RSW);
+              sts2(pp + k * PLPY, s0 + half_slope<LIM>(s0 - m1, p1 - s0, lim, c));
+            }
+          }
+        } else if (l - TQ < ta) {
+          const int r = l - TQ;
+          const float* wp = w + (r + YO) * RSW + 3;  // cell z0-1
+          float* pe = edl + q * ESLOT + r;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const F2 m1 = F2(wp[k * PLW - 1]), s0 = F2(wp[k * PLW]), p1 = F2(wp[k * PLW + 1]);
+            pe[k * 16] = (s0 + half_slope<LIM>(s0 - m1, p1 - s0, lim, c)).x;
+          }
+        }
+      }
+    };
     issue(xs, 1);
     issue(xs + 1, 2);
     issue(xs + 2, 0);
@@ -697,9 +751,14 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
     fixup(xs, 1);
     fixup(xs + 1, 2);
     __syncthreads();
+    if constexpr (SHARE) {
+      halo_plus(1, 0);
+      __syncthreads();
+    }
     int sC = 1, sN = 2, sF = 0, fs = 0;
     for (int x = xs; x < xe; ++x) {
-      edge_fluxes(sC, fs);
+      edge_fluxes(sC, fs, fs);
+      halo_plus(sN, fs ^ 1);
       cp_async_wait<0>();
       fixup(x + 2, sF);
       __syncthreads();
@@ -781,23 +840,53 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
       for (int k = 0; k < NV; ++k) F0[k] = F.q[k];
     }
     __syncthreads();
+    // SHARE: lower / upper y face states of the own pair in plane p from the complete window slot s; the
+    // upper one is published for the row above (plus ring, parity slot q), the lower one stays here
+    auto y_faces = [&](int s, int q, const F2 (&sv)[NV], F2 (&lower)[NV]) {
+      const float* wn = win + s * WSLOT + smW;
+      float* pp = ply + q * PSLOT + (ty + 1) * TZ + 2 * tq;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const F2 m1 = lds2(wn + k * PLW - RSW), p1 = lds2(wn + k * PLW + RSW);
+        const F2 dy = half_slope<LIM>(sv[k] - m1, p1 - sv[k], lim, c);
+        if (active) sts2(pp + k * PLPY, sv[k] + dy);
+        lower[k] = sv[k] - dy;
+      }
+    };
+    F2 mY0[NV], mY1[NV];
+    if constexpr (SHARE) {
+      F2 sv[NV];
+      read_own(1, sv);
+      y_faces(1, 0, sv, mY0);
+      __syncthreads();
+    }
 
     int sCs = 1, sNs = 2, sFs = 0, fs = 0;
-    // one plane: (dC, FxL) in, (dP, FxR) out
-    auto step = [&](int x, const F2 (&dC)[NV], const F2 (&FxL)[NV], F2 (&dP)[NV], F2 (&FxR)[NV]) {
+    // one plane: (dC, FxL, mYc) in, (dP, FxR, mYn) out
+    auto step = [&](int x, const F2 (&dC)[NV], const F2 (&FxL)[NV], const F2 (&mYc)[NV], F2 (&dP)[NV],
+                    F2 (&FxR)[NV], F2 (&mYn)[NV]) {
       const float* w = win + sCs * WSLOT + smW;
       float* f = flx + fs * FSLOT;
       F2 sC[NV];
       read_own(sCs, sC);
-      // ---- phase 1a: flux at the lower y interface (rows y-2, y-1, y, y+1 of the window)
+      // ---- phase 1a: flux at the lower y interface
       if constexpr (ND == 3) {
         Gas<F2, ND> L, R;
+        if constexpr (SHARE) {  // L: upper face state of the row below (plus ring), R: own lower face state
+          const float* pl = ply + fs * PSLOT + ty * TZ + 2 * tq;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          const F2 m2 = lds2(w + k * PLW - 2 * RSW), m1 = lds2(w + k * PLW - RSW), p1 = lds2(w + k * PLW + RSW);
-          const F2 dd = sC[k] - m1;
-          L.q[k] = m1 + half_slope<LIM>(m1 - m2, dd, lim, c);
-          R.q[k] = sC[k] - half_slope<LIM>(dd, p1 - sC[k], lim, c);
+          for (int k = 0; k < NV; ++k) {
+            L.q[k] = lds2(pl + k * PLPY);
+            R.q[k] = mYc[k];
+          }
+        } else {  // rows y-2, y-1, y, y+1 of the window
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const F2 m2 = lds2(w + k * PLW - 2 * RSW), m1 = lds2(w + k * PLW - RSW), p1 = lds2(w + k * PLW + RSW);
+            const F2 dd = sC[k] - m1;
+            L.q[k] = m1 + half_slope<LIM>(m1 - m2, dd, lim, c);
+            R.q[k] = sC[k] - half_slope<LIM>(dd, p1 - sC[k], lim, c);
+          }
         }
         const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, 2, alpha_lf[1], c);
         if (active) {
@@ -810,14 +899,31 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
       F2 Fz[NV];
       {
         Gas<F2, ND> L, R;
+        if constexpr (SHARE) {
+          // (d_a, d_b) once; l1 + d_l1 is the .y half of the left neighbour's upper face pair (shuffle
+          // inside the 16 pairs of a tile row; for the first pair it comes from the halo warp)
+          const float* pe = edl + fs * ESLOT + ty;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          const F2 lp = lds2(w + k * PLW - 2);
-          const float r1 = w[k * PLW + 2];
-          const F2 la = mk2(lp.y, sC[k].x);
-          const F2 D1 = la - lp, D2 = sC[k] - la, D3 = mk2(sC[k].y, r1) - sC[k];
-          L.q[k] = la + half_slope<LIM>(D1, D2, lim, c);
-          R.q[k] = sC[k] - half_slope<LIM>(D2, D3, lim, c);
+          for (int k = 0; k < NV; ++k) {
+            const float l1 = w[k * PLW - 1], r1 = w[k * PLW + 2];
+            const F2 D2 = sC[k] - mk2(l1, sC[k].x), D3 = mk2(sC[k].y, r1) - sC[k];
+            const F2 d = half_slope<LIM>(D2, D3, lim, c);
+            const F2 pz = sC[k] + d;
+            R.q[k] = sC[k] - d;
+            float nb = __shfl_up_sync(0xffffffffu, pz.y, 1, 16);
+            if (tq == 0) nb = pe[k * 16];
+            L.q[k] = mk2(nb, pz.x);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const F2 lp = lds2(w + k * PLW - 2);
+            const float r1 = w[k * PLW + 2];
+            const F2 la = mk2(lp.y, sC[k].x);
+            const F2 D1 = la - lp, D2 = sC[k] - la, D3 = mk2(sC[k].y, r1) - sC[k];
+            L.q[k] = la + half_slope<LIM>(D1, D2, lim, c);
+            R.q[k] = sC[k] - half_slope<LIM>(D2, D3, lim, c);
+          }
         }
         const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, LA + 1, alpha_lf[LA], c);
 #pragma unroll
@@ -844,6 +950,8 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
         const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, 1, alpha_lf[0], c);
 #pragma unroll
         for (int k = 0; k < NV; ++k) FxR[k] = F.q[k];
+        // y face states of plane x+1 (its window slot has been complete since the previous barrier)
+        if constexpr (SHARE) y_faces(sNs, fs ^ 1, sP, mYn);
       }
       // RK2 combine input (centre pair of s0), consumed after the barrier
       F2 s0v[NV];
@@ -905,9 +1013,9 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
       fs ^= 1;
     };
     for (int x = xs;;) {
-      step(x, d0, F0, d1, F1);
+      step(x, d0, F0, mY0, d1, F1, mY1);
       if (++x >= xe) break;
-      step(x, d1, F1, d0, F0);
+      step(x, d1, F1, mY1, d0, F0, mY0);
       if (++x >= xe) break;
     }
     cp_async_wait<0>();
