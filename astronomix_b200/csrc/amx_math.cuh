@@ -14,6 +14,9 @@
 #ifndef AMX_STRICT
 #define AMX_STRICT 0
 #endif
+#ifndef AMX_MINMOD_ALU
+#define AMX_MINMOD_ALU 0
+#endif
 
 namespace amx {
 
@@ -100,6 +103,15 @@ AMX_F2_BINOP(operator+, "add.rn.f32x2")
 AMX_F2_BINOP(operator-, "sub.rn.f32x2")
 AMX_F2_BINOP(operator*, "mul.rn.f32x2")
 #undef AMX_F2_BINOP
+// a * b + c as one packed FFMA2
+AMX_DI F2 fma2(F2 a, F2 b, F2 c) {
+  F2 d;
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
 #endif
 AMX_DI F2 operator-(F2 a) { return mk2(-a.x, -a.y); }
 AMX_DI F2 operator/(F2 a, F2 b) { return mk2(a.x / b.x, a.y / b.y); }  // IEEE division per half
@@ -300,9 +312,14 @@ AMX_DI T limited_slope(T a, T b, int lim, const Consts<T>& c) {
 // FMNMX3 per cell on the half-rate ALU pipe instead of four FMNMX, the sums as packed adds.  The sum
 // rounds (error <= ulp(a + b)); the exact min / max form stays in the STRICT flavour.
 AMX_DI F2 minmod(F2 a, F2 b) {
+#if AMX_MINMOD_ALU
+  // median(a, b, 0) = max(min(a, b), min(max(a, b), 0)): exact, four FMNMX per cell, nothing on the FMA pipe
+  return mk2(fmaxf(fminf(a.x, b.x), fminf(fmaxf(a.x, b.x), 0.f)), fmaxf(fminf(a.y, b.y), fminf(fmaxf(a.y, b.y), 0.f)));
+#else
   const F2 hi = mk2(fmaxf(fmaxf(a.x, b.x), 0.f), fmaxf(fmaxf(a.y, b.y), 0.f));
   const F2 lo = mk2(fminf(fminf(a.x, b.x), 0.f), fminf(fminf(a.y, b.y), 0.f));
   return ((a + b) - hi) - lo;
+#endif
 }
 #endif
 

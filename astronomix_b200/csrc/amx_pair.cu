@@ -29,6 +29,7 @@
 // open / reflective side is a COPY of an interior R_{k+1}, not a cell with its own stencil);
 // x is periodic or resident halo planes (slab ranks).  Anything else runs as two single launches.
 #include "amx_vec_common.cuh"
+#include "amx_tma.h"
 
 #include <cstdlib>
 
@@ -58,6 +59,15 @@ struct PG {
 
 struct RawP {
   F2 B0[3], v0[3], rho, Bk[3], vk[3];
+};
+
+// Tensor maps of the four input arrays (boxes = the block's window of one plane: 72 x (TY + 4) cells x
+// all rows of the array): ONE thread pulls the window of a plane that will be loaded two steps later into
+// L2 with four cp.async.bulk.prefetch.tensor instructions (SASS UTMAPF) instead of every 16th lane
+// prefetching its 13 lines.  on = 0: the arrays cannot be described by a map (per-lane prefetch).
+struct PairMaps {
+  CUtensorMap B0, gas, Bk, vk;
+  int on, xpad;
 };
 
 AMX_DI float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -124,7 +134,8 @@ AMX_DI void psi_ring(const float* w, const float* wm, const F2 (&Bp)[3], const F
 // FIRST: evaluation 1 starts from R_k = R_0 (launch 0 of the fixed point).  MID: implicit midpoint
 // (argument (R + R_0)/2) or implicit Euler (argument R).
 template <bool FIRST, bool MID, int TY, bool EMIT>
-__global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf) {
+__global__ void __launch_bounds__(PG<TY>::kThreads, 1)
+mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_constant__ PairMaps maps) {
   if (a.ctl_ro && (a.ctl_ro->done || (!a.first && !a.ctl_ro->mag_active))) return;
   using G = PG<TY>;
   constexpr int RS = G::RS, PLA = G::PLA, PLB = G::PLB, SLOTA = G::SLOTA, SLOTB = G::SLOTB;
@@ -196,8 +207,24 @@ __global__ void __launch_bounds__(PG<TY>::kThreads, 1) mag_pair_vec(const MagIte
   // One block per SM and one barrier per plane leave nothing to overlap a DRAM miss with: the
   // lines of plane p + pf are pulled into L2 while plane p is loaded into registers (one lane per
   // 128-byte line asks; the side warp's pairs each sit in a line of their own).
-  const bool pf_lane = exists && (wid >= TY + 4 || (lane & 15) == 0);
+  const bool pf_lane = !maps.on && exists && (wid >= TY + 4 || (lane & 15) == 0);
   auto issue = [&](int p, RawP& r) {
+    if (maps.on && pf > 0 && tid == 32 * (TY + 4) && p + pf <= xe + 1) {
+      int q = p + pf;
+      if (xwrap) q += q < 0 ? g.n[0] : (q >= g.n[0] ? -g.n[0] : 0);
+      q += maps.xpad;
+      // The innermost box coordinate must be a multiple of 4 floats (every box row starts at a 16-byte
+      // aligned address, else the instruction faults: tools/micro/tma_probe.cu); negative coordinates and
+      // boxes that stick out of the array are fine (those parts are skipped).  Window cells z0-2 .. z0+65
+      // sit inside the 72-cell box that starts at z0-4.
+      const int pz = z0 - 4, py = y0 - 2;
+      tma_prefetch_4d(&maps.B0, pz, py, q, 0);
+      tma_prefetch_4d(&maps.gas, pz, py, q, 0);
+      if constexpr (!FIRST) {
+        tma_prefetch_4d(&maps.Bk, pz, py, q, 0);
+        tma_prefetch_4d(&maps.vk, pz, py, q, 0);
+      }
+    }
     if (!exists) return;
     if (pf > 0 && pf_lane && p + pf <= xe + 1) {
       const long long q = plane_off(p + pf);
@@ -416,7 +443,22 @@ cudaError_t launch_pair_e(const MagIterArgs& a, cudaStream_t st) {
   grid.z = (a.g.n[0] + xchunk - 1) / xchunk;
   // AMX_PAIR_PF: planes ahead whose lines are pulled into L2 (0: off)
   static const int pf = [] { const char* e = getenv("AMX_PAIR_PF"); return e ? atoi(e) : 2; }();
-  kern<<<grid, G::kThreads, G::smem_bytes, st>>>(a, xchunk, pf);
+  // AMX_PAIR_TMAPF=0: per-lane prefetch instructions instead of tensor-map prefetches
+  static const bool tmapf = [] { const char* e = getenv("AMX_PAIR_TMAPF"); return !(e && e[0] == '0'); }();
+  PairMaps maps;
+  maps.on = 0;
+  maps.xpad = a.g.bc[0][0] == BC_HALO ? 2 : 0;
+  if (tmapf && pf > 0) {
+    // (a box must fit into the array: small grids prefetch a clipped window)
+    const unsigned bz = a.g.n[2] < 72 ? (unsigned)a.g.n[2] : 72u, by = a.g.n[1] < TY + 4 ? (unsigned)a.g.n[1] : (unsigned)(TY + 4);
+    bool ok = tma_map_rows_3d(&maps.B0, a.B0, a.g, 3, maps.xpad, bz, by, 3) &&
+              tma_map_rows_3d(&maps.gas, a.gas0, a.g, 4, maps.xpad, bz, by, 4);
+    if (ok && !FIRST)
+      ok = tma_map_rows_3d(&maps.Bk, a.Bk, a.g, 3, maps.xpad, bz, by, 3) &&
+           tma_map_rows_3d(&maps.vk, a.vk, a.g, 3, maps.xpad, bz, by, 3);
+    maps.on = ok ? 1 : 0;
+  }
+  kern<<<grid, G::kThreads, G::smem_bytes, st>>>(a, xchunk, pf, maps);
   return cudaGetLastError();
 }
 

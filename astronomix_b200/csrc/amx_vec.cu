@@ -476,6 +476,31 @@ AMX_DI F2 half_slope(F2 dm, F2 dp, int lim, const Consts<F2>& c) {
 #endif
 }
 
+// The slope quantity a thread keeps or shares per variable, and the two face states it gives:
+// FAST + minmod: the unscaled minmod(dm, dp), faces s +- 0.5 * q as one FFMA2 each; otherwise the
+// half slope (g * dx) / 2 in the reference's operation order, faces s +- q.
+template <int LIM>
+AMX_DI F2 slope_q(F2 dm, F2 dp, int lim, const Consts<F2>& c) {
+#if !AMX_STRICT
+  if constexpr (LIM == LIM_MINMOD) return minmod(dm, dp);
+#endif
+  return half_slope<LIM>(dm, dp, lim, c);
+}
+template <int LIM>
+AMX_DI F2 face_hi(F2 s, F2 q) {
+#if !AMX_STRICT
+  if constexpr (LIM == LIM_MINMOD) return fma2(F2(0.5f), q, s);
+#endif
+  return s + q;
+}
+template <int LIM>
+AMX_DI F2 face_lo(F2 s, F2 q) {
+#if !AMX_STRICT
+  if constexpr (LIM == LIM_MINMOD) return fma2(F2(-0.5f), q, s);
+#endif
+  return s - q;
+}
+
 AMX_DI Consts<F2> make_consts2(const NumPar& np) {
   Consts<F2> c;
   const float gamma = (float)np.gamma;
@@ -515,7 +540,12 @@ struct HG {
   static constexpr int NV = ND + 2;
   static constexpr int TY = ND == 3 ? 2 * kHydroCW : 1, TQ = ND == 3 ? 16 : 32 * kHydroCW, TZ = 2 * TQ;
   static constexpr int WY = ND == 3 ? TY + 4 : 1, YO = ND == 3 ? 2 : 0;
-  static constexpr int RSW = TZ + 8;       // window row: cells z0-2, z0-1 at columns 2, 3; own pairs from column 4
+#ifndef AMX_HYDRO_RSW_PAD
+#define AMX_HYDRO_RSW_PAD 8
+#endif
+  // window row: cells z0-2, z0-1 at columns 2, 3; own pairs from column 4.  3-D pitch 42: the halo warp
+  // reads one column of consecutive rows per lane, and 42 mod 32 = 10 spreads 14 rows over 14 banks
+  static constexpr int RSW = TZ + AMX_HYDRO_RSW_PAD;
   static constexpr int PLW = WY * RSW;     // floats per variable per window slot
   static constexpr int WSLOT = NV * PLW;
   static constexpr int PLFY = ND == 3 ? (TY + 1) * TZ : 0;  // y fluxes: lower interfaces of rows 0 .. TY
@@ -547,6 +577,14 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
   float* const flx = smem + 3 * WSLOT;     // [2][NV][PLFY + PLFZ]
   float* const ply = flx + 2 * FSLOT;      // [2][NV][TY + 1][TZ]  upper y face states, slot = plane parity
   float* const edl = ply + 2 * PSLOT;      // [2][NV][16]          upper z face state of cell z0-1 per row
+  // Split barriers (one arrival per warp): barF "the fluxes of plane x are published" (arrive after the
+  // y / z fluxes, wait before the update; the x flux and the next plane's y face states run in between),
+  // barP "plane x+2 has landed, the face states of plane x+1 are published" (arrive after them, wait at the
+  // start of the next plane; the update and the stores run in between).  A warp never runs ahead by more
+  // than the work between an arrive and its wait, and nobody waits for the slowest warp in lockstep.
+  __shared__ unsigned long long bars[2];
+  unsigned long long* const barF = &bars[0];
+  unsigned long long* const barP = &bars[1];
 
   const Consts<F2> c = make_consts2(a.np);
   const Geom& g = a.g;
@@ -559,6 +597,10 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
   const int xs = chunk * xchunk;
   const int xe = min(xs + xchunk, g.n[0]);
   if (xs >= xe) return;
+  if (tid == 0) {
+    mbar_init(barF, kHydroCW + 1);
+    mbar_init(barP, kHydroCW + 1);
+  }
   const float dts = *static_cast<const float*>(a.dt) * (float)a.dt_scale;
   const int ta = ND == 3 ? min(TY, g.n[1] - y0) : 1;   // active rows / pairs of a ragged tile
   const int tqa = min(TQ, (g.n[LA] - z0) >> 1);
@@ -585,8 +627,8 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const F2 d0 = s0[k] - m1[k];
-      L.q[k] = m1[k] + half_slope<LIM>(m1[k] - m2[k], d0, lim, c);
-      R.q[k] = s0[k] - half_slope<LIM>(d0, p1[k] - s0[k], lim, c);
+      L.q[k] = face_hi<LIM>(m1[k], slope_q<LIM>(m1[k] - m2[k], d0, lim, c));
+      R.q[k] = face_lo<LIM>(s0[k], slope_q<LIM>(d0, p1[k] - s0[k], lim, c));
     }
     return riemann<F2, ND, RS>(L, R, ax, alpha, c);
   };
@@ -680,7 +722,7 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
               for (int k = 0; k < NV; ++k) {
                 const F2 m1 = lds2(wp + k * PLW - RSW), s0 = lds2(wp + k * PLW), p1 = lds2(wp + k * PLW + RSW);
                 L.q[k] = lds2(pl + k * PLPY);
-                R.q[k] = s0 - half_slope<LIM>(s0 - m1, p1 - s0, lim, c);
+                R.q[k] = face_lo<LIM>(s0, slope_q<LIM>(s0 - m1, p1 - s0, lim, c));
               }
               F = riemann<F2, ND, RS>(L, R, 2, alpha_lf[1], c);
             } else {
@@ -729,7 +771,7 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
               const F2 m1 = lds2(wp + k * PLW - RSW), s0 = lds2(wp + k * PLW), p1 = lds2(wp + k * PLW + RSW);
-              sts2(pp + k * PLPY, s0 + half_slope<LIM>(s0 - m1, p1 - s0, lim, c));
+              sts2(pp + k * PLPY, face_hi<LIM>(s0, slope_q<LIM>(s0 - m1, p1 - s0, lim, c)));
             }
           }
         } else if (l - TQ < ta) {
@@ -739,7 +781,7 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
             const F2 m1 = F2(wp[k * PLW - 1]), s0 = F2(wp[k * PLW]), p1 = F2(wp[k * PLW + 1]);
-            pe[k * 16] = (s0 + half_slope<LIM>(s0 - m1, p1 - s0, lim, c)).x;
+            pe[k * 16] = face_hi<LIM>(s0, slope_q<LIM>(s0 - m1, p1 - s0, lim, c)).x;
           }
         }
       }
@@ -757,11 +799,14 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
     }
     int sC = 1, sN = 2, sF = 0, fs = 0;
     for (int x = xs; x < xe; ++x) {
+      if (x > xs) mbar_wait(barP, fs ^ 1);
       edge_fluxes(sC, fs, fs);
+      mbar_arrive_warp(barF);
       halo_plus(sN, fs ^ 1);
       cp_async_wait<0>();
       fixup(x + 2, sF);
-      __syncthreads();
+      mbar_arrive_warp(barP);
+      mbar_wait(barF, fs);
       issue(x + 3, sC);
       const int t = sC; sC = sN; sN = sF; sF = t;
       fs ^= 1;
@@ -806,7 +851,7 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
     auto read_own = [&](int slot, F2 (&v)[NV]) {
       const float* w = win + slot * WSLOT + smW;
 #pragma unroll
-      for (int k = 0; k < NV; ++k) v[k] = active ? lds2(w + k * PLW) : F2(1.f);
+      for (int k = 0; k < NV; ++k) v[k] = lds2(w + k * PLW);  // (rows / pairs beyond a ragged tile: never stored)
     };
 
     // ---- prologue: planes xs-2, xs-1 in registers; xs, xs+1 in the ring; xs+2 in flight.
@@ -830,10 +875,9 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const F2 dd = sC[k] - sM1[k];
-        const F2 dM1 = half_slope<LIM>(sM1[k] - sM2[k], dd, lim, c);
-        d0[k] = half_slope<LIM>(dd, sP[k] - sC[k], lim, c);
-        L.q[k] = sM1[k] + dM1;
-        R.q[k] = sC[k] - d0[k];
+        d0[k] = slope_q<LIM>(dd, sP[k] - sC[k], lim, c);
+        L.q[k] = face_hi<LIM>(sM1[k], slope_q<LIM>(sM1[k] - sM2[k], dd, lim, c));
+        R.q[k] = face_lo<LIM>(sC[k], d0[k]);
       }
       const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, 1, alpha_lf[0], c);
 #pragma unroll
@@ -848,9 +892,9 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const F2 m1 = lds2(wn + k * PLW - RSW), p1 = lds2(wn + k * PLW + RSW);
-        const F2 dy = half_slope<LIM>(sv[k] - m1, p1 - sv[k], lim, c);
-        if (active) sts2(pp + k * PLPY, sv[k] + dy);
-        lower[k] = sv[k] - dy;
+        const F2 qy = slope_q<LIM>(sv[k] - m1, p1 - sv[k], lim, c);
+        if (active) sts2(pp + k * PLPY, face_hi<LIM>(sv[k], qy));
+        lower[k] = face_lo<LIM>(sv[k], qy);
       }
     };
     F2 mY0[NV], mY1[NV];
@@ -867,6 +911,7 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
                     F2 (&FxR)[NV], F2 (&mYn)[NV]) {
       const float* w = win + sCs * WSLOT + smW;
       float* f = flx + fs * FSLOT;
+      if (x > xs) mbar_wait(barP, fs ^ 1);  // window of plane x+1 complete, face states of plane x published
       F2 sC[NV];
       read_own(sCs, sC);
       // ---- phase 1a: flux at the lower y interface
@@ -884,8 +929,8 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
           for (int k = 0; k < NV; ++k) {
             const F2 m2 = lds2(w + k * PLW - 2 * RSW), m1 = lds2(w + k * PLW - RSW), p1 = lds2(w + k * PLW + RSW);
             const F2 dd = sC[k] - m1;
-            L.q[k] = m1 + half_slope<LIM>(m1 - m2, dd, lim, c);
-            R.q[k] = sC[k] - half_slope<LIM>(dd, p1 - sC[k], lim, c);
+            L.q[k] = face_hi<LIM>(m1, slope_q<LIM>(m1 - m2, dd, lim, c));
+            R.q[k] = face_lo<LIM>(sC[k], slope_q<LIM>(dd, p1 - sC[k], lim, c));
           }
         }
         const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, 2, alpha_lf[1], c);
@@ -907,9 +952,9 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
           for (int k = 0; k < NV; ++k) {
             const float l1 = w[k * PLW - 1], r1 = w[k * PLW + 2];
             const F2 D2 = sC[k] - mk2(l1, sC[k].x), D3 = mk2(sC[k].y, r1) - sC[k];
-            const F2 d = half_slope<LIM>(D2, D3, lim, c);
-            const F2 pz = sC[k] + d;
-            R.q[k] = sC[k] - d;
+            const F2 qz = slope_q<LIM>(D2, D3, lim, c);
+            const F2 pz = face_hi<LIM>(sC[k], qz);
+            R.q[k] = face_lo<LIM>(sC[k], qz);
             float nb = __shfl_up_sync(0xffffffffu, pz.y, 1, 16);
             if (tq == 0) nb = pe[k * 16];
             L.q[k] = mk2(nb, pz.x);
@@ -921,8 +966,8 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
             const float r1 = w[k * PLW + 2];
             const F2 la = mk2(lp.y, sC[k].x);
             const F2 D1 = la - lp, D2 = sC[k] - la, D3 = mk2(sC[k].y, r1) - sC[k];
-            L.q[k] = la + half_slope<LIM>(D1, D2, lim, c);
-            R.q[k] = sC[k] - half_slope<LIM>(D2, D3, lim, c);
+            L.q[k] = face_hi<LIM>(la, slope_q<LIM>(D1, D2, lim, c));
+            R.q[k] = face_lo<LIM>(sC[k], slope_q<LIM>(D2, D3, lim, c));
           }
         }
         const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, LA + 1, alpha_lf[LA], c);
@@ -933,6 +978,7 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
           for (int k = 0; k < NV; ++k) f[k * (PLFY + PLFZ) + PLFY + ty * (TQ + 1) + tq] = F.q[k].x;
         }
       }
+      mbar_arrive_warp(barF);  // y / z fluxes of plane x published
       // ---- phase 1c: x direction; plane x+2 has landed in ring slot sFs
       cp_async_wait<0>();
       fixup(x + 2, sFs);
@@ -943,9 +989,9 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
         Gas<F2, ND> L, R;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-          dP[k] = half_slope<LIM>(sP[k] - sC[k], sN[k] - sP[k], lim, c);
-          L.q[k] = sC[k] + dC[k];
-          R.q[k] = sP[k] - dP[k];
+          dP[k] = slope_q<LIM>(sP[k] - sC[k], sN[k] - sP[k], lim, c);
+          L.q[k] = face_hi<LIM>(sC[k], dC[k]);
+          R.q[k] = face_lo<LIM>(sP[k], dP[k]);
         }
         const Gas<F2, ND> F = riemann<F2, ND, RS>(L, R, 1, alpha_lf[0], c);
 #pragma unroll
@@ -960,8 +1006,9 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
 #pragma unroll
         for (int k = 0; k < NV; ++k) s0v[k] = active ? ldg2<0>(p0 + k * vin0) : F2(1.f);
       }
-      __syncthreads();  // fluxes of plane x published; window of plane x+2 complete
-      issue(x + 3, sCs);  // ring slot of plane x is free (its last readers were phase 1)
+      mbar_arrive_warp(barP);  // own part of plane x+2 landed, y face states of plane x+1 published
+      mbar_wait(barF, fs);     // fluxes of plane x published by everybody; nobody reads window slot sCs any more
+      issue(x + 3, sCs);
 
       // ---- phase 2: conservative update axis by axis like the reference, prim (+ RK2 combine)
       {

@@ -67,6 +67,32 @@ AMX_DI int map_index(int i, int n, int bcl, int bcr, bool& flip) {
   return i;
 }
 
+// ---- shared-memory mbarriers (split arrive / wait, TMA completion)
+AMX_DI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+AMX_DI void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+AMX_DI void mbar_arrive(unsigned long long* b) {
+  asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(smem_u32(b)) : "memory");
+}
+AMX_DI void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+AMX_DI void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{ .reg .pred p;\n"
+      "W_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=: }"
+      ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// one arrival per warp: the lanes' shared-memory writes are ordered before lane 0's (releasing) arrive
+AMX_DI void mbar_arrive_warp(unsigned long long* b) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(b);
+}
+
 AMX_DI unsigned long long bits_of(float v) { return (unsigned long long)__float_as_uint(v); }
 
 // A column is the element offset of its plane-0 cell, shared by every array of the launch
