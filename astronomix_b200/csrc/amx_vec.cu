@@ -460,61 +460,6 @@ cudaError_t launch_mag(const MagIterArgs& a, cudaStream_t st) {
 //     half of the right neighbour's pair, read back after the barrier;
 //   * the fluxes on the upper tile edges (top row, right column) are extra work of the halo warp.
 // Every flux is computed exactly once; slopes of rows y-1 / cells z-1 are recomputed (cheap).
-template <int LIM>
-AMX_DI F2 half_slope(F2 dm, F2 dp, int lim, const Consts<F2>& c) {
-#if AMX_STRICT
-  const F2 a = dm / c.dx, b = dp / c.dx;
-  const F2 g = (LIM == LIM_MINMOD) ? minmod(a, b) : limited_slope(a, b, lim, c);
-  return (g * c.dx) / F2(2);
-#else
-  if constexpr (LIM == LIM_MINMOD) {
-    return F2(0.5f) * minmod(dm, dp);
-  } else {
-    const F2 g = limited_slope(dm * c.inv_dx, dp * c.inv_dx, lim, c);
-    return (g * c.dx) * F2(0.5f);
-  }
-#endif
-}
-
-// The slope quantity a thread keeps or shares per variable, and the two face states it gives:
-// FAST + minmod: the unscaled minmod(dm, dp), faces s +- 0.5 * q as one FFMA2 each; otherwise the
-// half slope (g * dx) / 2 in the reference's operation order, faces s +- q.
-template <int LIM>
-AMX_DI F2 slope_q(F2 dm, F2 dp, int lim, const Consts<F2>& c) {
-#if !AMX_STRICT
-  if constexpr (LIM == LIM_MINMOD) return minmod(dm, dp);
-#endif
-  return half_slope<LIM>(dm, dp, lim, c);
-}
-template <int LIM>
-AMX_DI F2 face_hi(F2 s, F2 q) {
-#if !AMX_STRICT
-  if constexpr (LIM == LIM_MINMOD) return fma2(F2(0.5f), q, s);
-#endif
-  return s + q;
-}
-template <int LIM>
-AMX_DI F2 face_lo(F2 s, F2 q) {
-#if !AMX_STRICT
-  if constexpr (LIM == LIM_MINMOD) return fma2(F2(-0.5f), q, s);
-#endif
-  return s - q;
-}
-
-AMX_DI Consts<F2> make_consts2(const NumPar& np) {
-  Consts<F2> c;
-  const float gamma = (float)np.gamma;
-  const float gm1 = gamma - 1.0f;
-  c.gamma = F2(gamma);
-  c.gm1 = F2(gm1);
-  c.inv_gm1 = F2(1.0f / gm1);
-  c.dx = F2((float)np.dx);
-  c.inv_dx = F2((float)(1.0 / np.dx));
-  c.half_dx = F2((float)(np.dx / 2));
-  c.va_eps = F2((float)(3 * np.dx));
-  return c;
-}
-
 AMX_DI void cp_async8(float* smem_dst, const float* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");

@@ -95,6 +95,62 @@ AMX_DI void mbar_arrive_warp(unsigned long long* b) {
 
 AMX_DI unsigned long long bits_of(float v) { return (unsigned long long)__float_as_uint(v); }
 
+// ---- limited slopes and face states of the plane-streaming hydro kernels (amx_vec.cu, amx_tma_stage.cu)
+template <int LIM>
+AMX_DI F2 half_slope(F2 dm, F2 dp, int lim, const Consts<F2>& c) {
+#if AMX_STRICT
+  const F2 a = dm / c.dx, b = dp / c.dx;
+  const F2 g = (LIM == LIM_MINMOD) ? minmod(a, b) : limited_slope(a, b, lim, c);
+  return (g * c.dx) / F2(2);
+#else
+  if constexpr (LIM == LIM_MINMOD) {
+    return F2(0.5f) * minmod(dm, dp);
+  } else {
+    const F2 g = limited_slope(dm * c.inv_dx, dp * c.inv_dx, lim, c);
+    return (g * c.dx) * F2(0.5f);
+  }
+#endif
+}
+
+// The slope quantity a thread keeps or shares per variable, and the two face states it gives:
+// FAST + minmod: the unscaled minmod(dm, dp), faces s +- 0.5 * q as one FFMA2 each; otherwise the
+// half slope (g * dx) / 2 in the reference's operation order, faces s +- q.
+template <int LIM>
+AMX_DI F2 slope_q(F2 dm, F2 dp, int lim, const Consts<F2>& c) {
+#if !AMX_STRICT
+  if constexpr (LIM == LIM_MINMOD) return minmod(dm, dp);
+#endif
+  return half_slope<LIM>(dm, dp, lim, c);
+}
+template <int LIM>
+AMX_DI F2 face_hi(F2 s, F2 q) {
+#if !AMX_STRICT
+  if constexpr (LIM == LIM_MINMOD) return fma2(F2(0.5f), q, s);
+#endif
+  return s + q;
+}
+template <int LIM>
+AMX_DI F2 face_lo(F2 s, F2 q) {
+#if !AMX_STRICT
+  if constexpr (LIM == LIM_MINMOD) return fma2(F2(-0.5f), q, s);
+#endif
+  return s - q;
+}
+
+AMX_DI Consts<F2> make_consts2(const NumPar& np) {
+  Consts<F2> c;
+  const float gamma = (float)np.gamma;
+  const float gm1 = gamma - 1.0f;
+  c.gamma = F2(gamma);
+  c.gm1 = F2(gm1);
+  c.inv_gm1 = F2(1.0f / gm1);
+  c.dx = F2((float)np.dx);
+  c.inv_dx = F2((float)(1.0 / np.dx));
+  c.half_dx = F2((float)(np.dx / 2));
+  c.va_eps = F2((float)(3 * np.dx));
+  return c;
+}
+
 // A column is the element offset of its plane-0 cell, shared by every array of the launch
 // (vec_mag_supported checks that all views have the same x / y strides).
 using Col = long long;
