@@ -508,7 +508,7 @@ struct HG {
 };
 
 template <int ND, int RS, int LIM, bool COMBINE>
-__global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stage_vec(const StageArgs a, const int xchunk) {
+__global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stage_vec(const StageArgs a, const int xchunk, const int work) {
   if (a.ctl_ro && a.ctl_ro->done) return;
   using G = HG<ND>;
   constexpr int NV = G::NV, TY = G::TY, TQ = G::TQ, TZ = G::TZ, YO = G::YO, RSW = G::RSW, PLW = G::PLW;
@@ -536,19 +536,11 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
   const int lim = a.np.lim;
   const int tid = threadIdx.x;
   const bool compute = tid < kCompute;
-  const int z0 = blockIdx.x * TZ;
-  const int y0 = ND == 3 ? blockIdx.y * TY : 0;
-  const int chunk = ND == 3 ? blockIdx.z : blockIdx.y;
-  const int xs = chunk * xchunk;
-  const int xe = min(xs + xchunk, g.n[0]);
-  if (xs >= xe) return;
   if (tid == 0) {
     mbar_init(barF, kHydroCW + 1);
     mbar_init(barP, kHydroCW + 1);
   }
   const float dts = *static_cast<const float*>(a.dt) * (float)a.dt_scale;
-  const int ta = ND == 3 ? min(TY, g.n[1] - y0) : 1;   // active rows / pairs of a ragged tile
-  const int tqa = min(TQ, (g.n[LA] - z0) >> 1);
   const long long sx = a.in.s[0], sy = ND == 3 ? a.in.s[1] : 0;  // common strides (vec_stage_supported)
   const float* const fin = static_cast<const float*>(a.in.p);
   const long long vin = a.in.vs;
@@ -579,6 +571,28 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
   };
 
   float wbx = 0.f, wby = 0.f, wbz = 0.f;  // running max of |u_axis| + c (axes x, y, z; 2-D: x, y in wbx, wby)
+
+  // Work list: the plane-tiles of the launch in (x chunk, tile, plane) order, cut into equal shares, one per
+  // block (launch_stage_vec: as many blocks as the GPU holds at once), so that no SM idles behind a partial
+  // last wave.  A share is a few segments [xs, xe) of consecutive tiles; neighbouring tiles stay a few planes
+  // apart in x, so their halo rows meet in L2.
+  const int ztiles = (g.n[LA] + TZ - 1) / TZ;
+  const int ntiles = ztiles * (ND == 3 ? (g.n[1] + TY - 1) / TY : 1);
+  const int nchunks = (g.n[0] + xchunk - 1) / xchunk;
+  const int u_end = min((int)(blockIdx.x + 1) * work, nchunks * ntiles * xchunk);  // (launcher: fits an int)
+  unsigned pb = 0;  // parity of the mbarrier phases completed by earlier segments
+  for (int u = blockIdx.x * work; u < u_end;) {
+  const int tl = u / xchunk, xoff = u - tl * xchunk;
+  const int chunk = tl / ntiles, tile = tl - chunk * ntiles;
+  const int z0 = (tile % ztiles) * TZ;
+  const int y0 = ND == 3 ? (tile / ztiles) * TY : 0;
+  const int xs = chunk * xchunk + xoff;
+  const int ce = min(chunk * xchunk + xchunk, g.n[0]);
+  const int xe = min(ce, xs + (u_end - u));
+  u = xe >= ce ? (tl + 1) * xchunk : u_end;
+  if (xs >= xe) continue;
+  const int ta = ND == 3 ? min(TY, g.n[1] - y0) : 1;   // active rows / pairs of a ragged tile
+  const int tqa = min(TQ, (g.n[LA] - z0) >> 1);
 
   if (!compute) {
     // ================= halo warp
@@ -744,14 +758,14 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
     }
     int sC = 1, sN = 2, sF = 0, fs = 0;
     for (int x = xs; x < xe; ++x) {
-      if (x > xs) mbar_wait(barP, fs ^ 1);
+      if (x > xs) mbar_wait(barP, fs ^ 1 ^ pb);
       edge_fluxes(sC, fs, fs);
       mbar_arrive_warp(barF);
       halo_plus(sN, fs ^ 1);
       cp_async_wait<0>();
       fixup(x + 2, sF);
       mbar_arrive_warp(barP);
-      mbar_wait(barF, fs);
+      mbar_wait(barF, fs ^ pb);
       issue(x + 3, sC);
       const int t = sC; sC = sN; sN = sF; sF = t;
       fs ^= 1;
@@ -856,7 +870,7 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
                     F2 (&FxR)[NV], F2 (&mYn)[NV]) {
       const float* w = win + sCs * WSLOT + smW;
       float* f = flx + fs * FSLOT;
-      if (x > xs) mbar_wait(barP, fs ^ 1);  // window of plane x+1 complete, face states of plane x published
+      if (x > xs) mbar_wait(barP, fs ^ 1 ^ pb);  // window of plane x+1 complete, face states of plane x published
       F2 sC[NV];
       read_own(sCs, sC);
       // ---- phase 1a: flux at the lower y interface
@@ -952,7 +966,7 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
         for (int k = 0; k < NV; ++k) s0v[k] = active ? ldg2<0>(p0 + k * vin0) : F2(1.f);
       }
       mbar_arrive_warp(barP);  // own part of plane x+2 landed, y face states of plane x+1 published
-      mbar_wait(barF, fs);     // fluxes of plane x published by everybody; nobody reads window slot sCs any more
+      mbar_wait(barF, fs ^ pb);     // fluxes of plane x published by everybody; nobody reads window slot sCs any more
       issue(x + 3, sCs);
 
       // ---- phase 2: conservative update axis by axis like the reference, prim (+ RK2 combine)
@@ -1012,6 +1026,9 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
     }
     cp_async_wait<0>();
   }
+  __syncthreads();  // the rings are free for the next segment
+  pb ^= (unsigned)(xe - xs) & 1u;
+  }  // segments
 
   if (a.alpha_slots) {
     float wb[3] = {wbx, wby, wbz};
@@ -1043,16 +1060,12 @@ cudaError_t launch_stage_vec(const StageArgs& a, cudaStream_t st) {
     cudaError_t e = opt.ensure(kern, G::smem_bytes);
     if (e != cudaSuccess) return e;
   }
-  dim3 grid;
   const int LA = ND - 1;
-  grid.x = (a.g.n[LA] + G::TZ - 1) / G::TZ;
-  const int ytiles = ND == 3 ? (a.g.n[1] + G::TY - 1) / G::TY : 1;
-  const int nch = pick_chunks(a.g.n[0], (long long)grid.x * ytiles, AMX_HYDRO_MINB, 4);
-  const int xchunk = (a.g.n[0] + nch - 1) / nch;
-  const int nchunks = (a.g.n[0] + xchunk - 1) / xchunk;
-  if (ND == 3) { grid.y = ytiles; grid.z = nchunks; }
-  else { grid.y = nchunks; grid.z = 1; }
-  kern<<<grid, 32 * kHydroCW + 32, G::smem_bytes, st>>>(a, xchunk);
+  const long long tiles = (long long)((a.g.n[LA] + G::TZ - 1) / G::TZ) * (ND == 3 ? (a.g.n[1] + G::TY - 1) / G::TY : 1);
+  int xchunk, work;
+  const int nblocks = pick_shares(a.g.n[0], tiles, AMX_HYDRO_MINB, xchunk, work);
+  const dim3 grid(nblocks);
+  kern<<<grid, 32 * kHydroCW + 32, G::smem_bytes, st>>>(a, xchunk, work);
   return cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 #include "amx_math.cuh"
 
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #if AMX_STRICT
@@ -169,6 +170,30 @@ inline int pick_chunks(int nx, long long tiles, int blocks_per_sm, int prologue)
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nch; }
   }
   return best;
+}
+
+// Equal shares of a launch's plane-tiles for a grid that is resident all at once: `tiles` columns of nx
+// planes, 148 * blocks_per_sm blocks (fewer when a share would drop below 16 planes, where the 4-plane
+// prologue of a segment dominates).  The x axis is cut into chunks of about one share, the work list runs
+// (chunk, tile, plane): a block gets `work` consecutive entries, i.e. two or three segments of neighbouring
+// tiles, and neighbouring tiles run only `work - xchunk` planes apart (their halo rows meet in L2).
+inline int pick_shares(int nx, long long tiles, int blocks_per_sm, int& xchunk, int& work) {
+  const long long slots = 148LL * blocks_per_sm;
+  const long long total = tiles * nx;
+  long long nb = total / 16 < slots ? (total / 16 > 0 ? total / 16 : 1) : slots;
+  long long w = (total + nb - 1) / nb;
+  int nch = (int)((nx + w / 2) / w);
+  if (nch < 1) nch = 1;
+  xchunk = (nx + nch - 1) / nch;
+  nch = (nx + xchunk - 1) / xchunk;
+  const long long padded = (long long)nch * tiles * xchunk;  // a ragged last chunk leaves dead entries
+  w = (padded + nb - 1) / nb;
+  // AMX_SHARE_SKEW=k (tests): shares k entries longer, so that they stop lining up with the tiles and
+  // every block runs several segments, short ones included
+  static const int skew = [] { const char* e = getenv("AMX_SHARE_SKEW"); return e ? atoi(e) : 0; }();
+  if (skew > 0) w += skew;
+  work = (int)w;
+  return (int)((padded + w - 1) / w);
 }
 
 inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
