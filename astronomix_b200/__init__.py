@@ -14,5 +14,5 @@ from .registered_variables import RegisteredVariables, get_registered_variables 
 from .helpers import get_helper_data, construct_primitive_state, HelperData  # noqa: F401
 
 
-from .stepping import time_integration, StateStruct  # noqa: F401,E402
+from .stepping import time_integration, StateStruct, SlabSharding  # noqa: F401,E402
 from .snapshots import SnapshotData  # noqa: F401,E402

@@ -13,7 +13,7 @@ from . import option_classes as oc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libamx.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 AMX_F32, AMX_F64 = 0, 1
 AMX_ARITH_FAST, AMX_ARITH_STRICT = 0, 1
@@ -42,7 +42,11 @@ class AmxDesc(C.Structure):
         ("exact_end_time", C.c_int32),
         ("use_max_adaptive_timestep", C.c_int32),
         ("arithmetic", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("peer_flags", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("peer_delta_lo", C.c_int64),
+        ("peer_delta_hi", C.c_int64),
+        ("reserved", C.c_int32 * 2),
         ("dx", C.c_double),
         ("gamma", C.c_double),
         ("C_cfl", C.c_double),
@@ -104,6 +108,9 @@ PROTOTYPES = {
     "amx_magnetic_check_pair": (C.c_int, [_D, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "amx_magnetic_fix_guarded": (C.c_int, [_D, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
     "amx_magnetic_state": (C.c_int, [_D, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "amx_peer_push_supported": (C.c_int, [_D]),
+    "amx_peer_comm_bytes": (C.c_size_t, []),
+    "amx_peer_allreduce_max": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, _P, C.c_int, C.c_int, _P]),
 }
 
 _lib = None

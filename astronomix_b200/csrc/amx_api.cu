@@ -137,6 +137,9 @@ int validate(const amx_desc* d) {
       return fail(AMX_EINVAL, "n[a] must be >= 4 on active axes and 1 on absent ones");
   }
   if (d->dtype != AMX_F32 && d->dtype != AMX_F64) return fail(AMX_EINVAL, "dtype must be AMX_F32 or AMX_F64");
+  if (d->peer_flags & ~3) return fail(AMX_EINVAL, "peer_flags: only bits 0 (lower) and 1 (upper neighbour) exist");
+  if (((d->peer_flags & 1) && d->bc[0][0] != AMX_BC_HALO) || ((d->peer_flags & 2) && d->bc[0][1] != AMX_BC_HALO))
+    return fail(AMX_EINVAL, "peer_flags need AMX_BC_HALO on that side of axis 0");
   if (d->mhd && d->ndim == 1) return fail(AMX_EUNSUPPORTED, "MHD currently not supported in 1D.");
   if (d->riemann < AMX_HLL || d->riemann > 5) return fail(AMX_EINVAL, "Riemann solver not supported.");
   if (d->limiter < 0 || d->limiter > 5) return fail(AMX_EINVAL, "Unknown limiter.");
@@ -491,6 +494,53 @@ __global__ void set_dt_kernel(Ctl* ctl, const T* dt_dev) {
 // ---------------------------------------------------------------- layout kernels
 // dst (padded by ng on active axes) <- src (unpadded).  Gas rows take the boundary rule of
 // their side, the other rows are edge-padded (np.pad mode="edge", Q9).
+// ---- peer-memory MAX all-reduce / barrier of a slab run (amx_peer_allreduce_max) ------------------------
+// Communication buffer of a rank (peer-mapped, zeroed once): epoch counter, per parity a flag per source
+// rank and 8 value slots per source rank.  Call number e (parity e & 1): every rank stores its values into
+// slot [parity][own rank] of EVERY rank's buffer, fences, then raises flag [parity][own rank] = e on every
+// rank (release, system scope); it waits until all `world` flags of its own buffer read e (acquire) and
+// takes the maximum of the slots.  A rank cannot start call e + 2 (which reuses the parity) before every
+// rank has raised its flag of call e + 1, i.e. has finished reading the slots of call e.
+struct PeerBufs {
+  unsigned long long p[8];
+};
+constexpr size_t kPeerFlagsOff = 64, kPeerValsOff = 128, kPeerCommBytes = 128 + 2 * 8 * 8 * sizeof(double);
+
+template <typename T>
+__global__ void __launch_bounds__(64) peer_allreduce_max_kernel(PeerBufs bufs, int rank, int world, T* vals, int count) {
+  char* const mine = reinterpret_cast<char*>(bufs.p[rank]);
+  __shared__ unsigned e_s;
+  const int tid = threadIdx.x;
+  if (tid == 0) e_s = *reinterpret_cast<volatile unsigned*>(mine) + 1u;
+  __syncthreads();
+  const unsigned e = e_s, par = e & 1u;
+  const int r = tid >> 3, i = tid & 7;
+  if (r < world && i < count) {
+    volatile double* dst = reinterpret_cast<volatile double*>(reinterpret_cast<char*>(bufs.p[r]) + kPeerValsOff) +
+                           ((par * 8 + rank) * 8 + i);
+    *dst = (double)vals[i];
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (tid < world) {
+    unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(bufs.p[tid]) + kPeerFlagsOff) + (par * 8 + rank);
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(e) : "memory");
+    const unsigned* own = reinterpret_cast<const unsigned*>(mine + kPeerFlagsOff) + (par * 8 + tid);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(own) : "memory");
+    } while (seen != e);
+  }
+  __syncthreads();
+  if (tid < count) {
+    const volatile double* src = reinterpret_cast<const volatile double*>(mine + kPeerValsOff) + par * 64 + tid;
+    double m = src[0];
+    for (int q = 1; q < world; ++q) m = fmax(m, src[q * 8]);
+    vals[tid] = (T)m;
+  }
+  if (tid == 0) *reinterpret_cast<volatile unsigned*>(mine) = e;
+}
+
 template <typename T>
 __global__ void pad_kernel(Geom g, int ng, int rows, int gas_rows, View src, View dst) {
   long long e[3], tot = 1;
@@ -649,12 +699,15 @@ struct Engine {
   // ghost shell (ShellArgs): where the shell is read / written by the next update; off unless set
   bool shell_on = false;
   View shell_src, shell_dst;
+  Peers peers;  // in-kernel halo stores (slab ranks; amx_desc::peer_*)
 
   Engine(const amx_desc* d_, void* ws_, void* stream)
       : d(d_), L(make_layout(d_)), g(geom_of(d_)), np(numpar_of(d_)), ws(static_cast<char*>(ws_)),
         ctl(reinterpret_cast<Ctl*>(static_cast<char*>(ws_) + L.off_ctl)), st(static_cast<cudaStream_t>(stream)),
         strict(d_->arithmetic == AMX_ARITH_STRICT), is32(d_->dtype == AMX_F32),
-        lf(d_->riemann == AMX_LAX_FRIEDRICHS || (d_->limiter == 5 && d_->split == AMX_UNSPLIT)) {}
+        lf(d_->riemann == AMX_LAX_FRIEDRICHS || (d_->limiter == 5 && d_->split == AMX_UNSPLIT)) {
+    peers.lo = d_->peer_delta_lo; peers.hi = d_->peer_delta_hi; peers.flags = d_->peer_flags & 3;
+  }
 
   // view over an internal workspace buffer (x ghost planes resident in slab mode)
   View internal(size_t off, int first_row = 0) const {
@@ -753,6 +806,7 @@ struct Engine {
     a.ctl_ro = guarded ? ctl : nullptr;
     a.dt = dt; a.dt_scale = dt_scale; a.alpha_lf = alpha_lf;
     a.alpha_slots = want_alpha ? aslots() : nullptr;
+    a.peers = peers;
     ++launches;
     {
       ProfScope ps(PC_HYDRO_STAGE, st);
@@ -833,6 +887,7 @@ struct Engine {
     a.dt = dt; a.change_slots = cslots(); a.change_slots2 = &ctl->change2_slots[0][0];
     a.fix_base = -1;
     a.emit = 0; a.emit_gas = B0; a.emit_B = B0;
+    a.peers = peers;
     return a;
   }
   bool pair_supported(const MagIterArgs& a) const {
@@ -886,6 +941,7 @@ struct Engine {
     a.ctl_ro = ctl; a.fixed_final = fixed_final; a.alpha_slots = want_alpha ? aslots() : nullptr;
     a.skip_if_emitted = skip_if_emitted ? 1 : 0;
     a.final_runs = &ctl->final_runs;
+    a.peers = peers;
     ++launches;
     {
       ProfScope ps(PC_MAG_FINAL, st);
@@ -1507,6 +1563,54 @@ int amx_magnetic_state(const amx_desc* d, void* ws, void* stream, int32_t* activ
   *active_out = m->mag_active;
   *iterations_out = m->mag_iter;
   if (m->not_converged) return fail(AMX_ENOTCONVERGED, "magnetic fixed point hit the 1000-iteration cap");
+  return AMX_OK;
+}
+
+int amx_peer_push_supported(const amx_desc* d) {
+  if (validate(d)) return 0;
+  if (d->bc[0][0] != AMX_BC_HALO && d->bc[0][1] != AMX_BC_HALO) return 0;
+  Engine E(d, nullptr, nullptr);
+  int pad[3];
+  internal_pad(d, pad);
+  const View v = make_view(reinterpret_cast<void*>(uintptr_t(256)), d, pad, 0, 0);
+  int bits = 0;
+  if (d->split == AMX_UNSPLIT && !force_generic() && !no_vec()) {
+    StageArgs a{};
+    a.g = E.g; a.np = E.np; a.in = a.in0 = a.out = v;
+    if (E.strict ? amx_strict::vec_stage_supported(a) : amx_fast::vec_stage_supported(a)) bits |= 1;
+  }
+  if (d->mhd) {
+    MagIterArgs a{};
+    a.g = E.g; a.np = E.np;
+    a.B0 = a.gas0 = a.Bk = a.vk = a.Bk1 = a.vk1 = v;
+    a.change_slots = a.change_slots2 = reinterpret_cast<unsigned long long*>(uintptr_t(256));
+    a.fix_base = -1;
+    const bool vec = !force_generic() && !no_vec() &&
+                     (E.strict ? amx_strict::vec_mag_supported(a) : amx_fast::vec_mag_supported(a));
+    if (vec) bits |= 2;
+    bits |= 4;
+  }
+  return bits;
+}
+
+size_t amx_peer_comm_bytes(void) { return kPeerCommBytes; }
+
+int amx_peer_allreduce_max(void* const* comm_bufs, int rank, int world, void* vals_inout, int count, int dtype,
+                           void* stream) {
+  if (!comm_bufs || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(AMX_EINVAL, "peer all-reduce: 1 <= world <= 8, 0 <= rank < world");
+  if (count < 0 || count > 8 || (count > 0 && !vals_inout)) return fail(AMX_EINVAL, "peer all-reduce: 0 <= count <= 8");
+  if (dtype != AMX_F32 && dtype != AMX_F64) return fail(AMX_EINVAL, "dtype must be AMX_F32 or AMX_F64");
+  int rc = amx_device_check();
+  if (rc) return rc;
+  PeerBufs b{};
+  for (int r = 0; r < world; ++r) {
+    if (!comm_bufs[r]) return fail(AMX_EINVAL, "peer all-reduce: null communication buffer");
+    b.p[r] = reinterpret_cast<unsigned long long>(comm_bufs[r]);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == AMX_F32) peer_allreduce_max_kernel<float><<<1, 64, 0, st>>>(b, rank, world, static_cast<float*>(vals_inout), count);
+  else peer_allreduce_max_kernel<double><<<1, 64, 0, st>>>(b, rank, world, static_cast<double*>(vals_inout), count);
+  CK(cudaGetLastError());
   return AMX_OK;
 }
 

@@ -44,6 +44,25 @@ __host__ __device__ inline T jet_vector_value(int type_handled, int comp) {  // 
   return type_handled == 1 ? (T)800.0 : (T)14.142135623730951;  // 200 ** 0.5
 }
 
+// In-kernel halo stores of a slab rank (include/amx.h amx_desc::peer_*): a kernel that writes active plane
+// x of an output array repeats the store into the neighbour's copy of the array, plane x + n of the lower
+// neighbour (its right ghost planes) for x < 2 and plane x - n of the upper neighbour for x >= n - 2.
+struct Peers {
+  long long lo, hi;  // byte deltas from an own pointer to the same element of the neighbour's array
+  int flags;         // bit 0: lower neighbour, bit 1: upper neighbour
+};
+// element offset (in units of the x stride) and byte delta of the extra store for plane x, or false
+__host__ __device__ inline bool peer_target(const Peers& P, int x, int n, int k, long long& byte_delta, int& plane_shift) {
+  if (k == 0) {
+    if (!(P.flags & 1) || x >= 2) return false;
+    byte_delta = P.lo; plane_shift = n;
+    return true;
+  }
+  if (!(P.flags & 2) || x < n - 2) return false;
+  byte_delta = P.hi; plane_shift = -n;
+  return true;
+}
+
 struct NumPar {
   int dtype;  // 0 f32, 1 f64
   int rs, lim;
@@ -88,6 +107,7 @@ struct StageArgs {
   double dt_scale;    // 1 or 0.5 (exact)
   const void* alpha_lf;  // device, 3 values of the working type (Lax-Friedrichs only)
   unsigned long long* alpha_slots;  // nullable: [3][kAlphaSlots] wave bounds of the result
+  Peers peers;      // in-kernel halo stores of `out` (vec family only; see amx_peer_push_supported)
 };
 
 struct SweepArgs {
@@ -121,6 +141,7 @@ struct MagIterArgs {
   // (_magnetic_field_update.py:208-240): gas rows (rho, v_n, p_2) to emit_gas, B_n to emit_B
   int emit;
   View emit_gas, emit_B;
+  Peers peers;  // in-kernel halo stores of Bk1 / vk1 (and emit_gas / emit_B); vec / pair kernels only
 };
 
 struct MagFinalArgs {
@@ -135,6 +156,7 @@ struct MagFinalArgs {
   int skip_if_emitted;  // do nothing when ctl->final_emitted (an emitting pair launch did the work)
   long long* final_runs;  // nullable: counts launches that did work
   unsigned long long* alpha_slots;
+  Peers peers;  // in-kernel halo stores of gas_out / B_out
 };
 
 struct AlphaArgs {

@@ -629,6 +629,23 @@ __global__ void __launch_bounds__(256) mag_final_kernel(const MagFinalArgs a) {
     for (int k = 0; k < ND; ++k) { s.q[k + 1] = vn[k]; po[(k + 1) * a.gas_out.vs] = vn[k]; }
     s.q[ND + 1] = p2;
     po[(ND + 1) * a.gas_out.vs] = p2;
+    if (a.peers.flags) {  // slab rank: edge planes of gas_out / B_out -> the neighbours' ghost planes
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        long long bd;
+        int ps;
+        if (peer_target(a.peers, cell.i[0], a.g.n[0], side, bd, ps)) {
+          T* qo = reinterpret_cast<T*>(reinterpret_cast<char*>(po) + bd) + (long long)ps * a.gas_out.s[0];
+          T* qb = reinterpret_cast<T*>(reinterpret_cast<char*>(pb) + bd) + (long long)ps * a.B_out.s[0];
+          qo[0] = s.q[0];
+#pragma unroll
+          for (int k = 0; k < ND; ++k) qo[(k + 1) * a.gas_out.vs] = vn[k];
+          qo[(ND + 1) * a.gas_out.vs] = p2;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) qb[k * a.B_out.vs] = px[k * X.vs];
+        }
+      }
+    }
     if (a.alpha_slots) {
 #pragma unroll
       for (int k = 0; k < ND; ++k) wb[k] = rmax(wb[k], wave_bound(s, k + 1, c));

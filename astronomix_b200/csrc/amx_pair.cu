@@ -147,19 +147,12 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
 
   const Geom& g = a.g;
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  const int z0 = blockIdx.x * 64;
-  const int y0 = blockIdx.y * TY;
-  const int xs = blockIdx.z * xchunk;
-  const int xe = min(xs + xchunk, g.n[0]);
-  if (xs >= xe) return;
   const float dt = *static_cast<const float*>(a.dt);
 #if AMX_STRICT
   const float dpar = (float)a.np.dx;
 #else
   const float dpar = 0.5f * (float)(1.0 / a.np.dx);
 #endif
-  const int ta = min(TY, g.n[1] - y0);
-  const int tqa = min(32, (g.n[2] - z0) >> 1);
   const long long sx = a.B0.s[0], sy = a.B0.s[1];
   const float* const fB0 = static_cast<const float*>(a.B0.p);
   const float* const fG = static_cast<const float*>(a.gas0.p);
@@ -171,6 +164,16 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
   const long long vB1 = a.Bk1.vs, vv1 = a.vk1.vs;
   const bool xwrap = g.bc[0][0] == BC_PERIODIC;
 
+  F2 n1B = bc2(0.f), n1v = bc2(0.f), n2B = bc2(0.f), n2v = bc2(0.f);
+  // (A work list of equal shares as in hydro_stage_vec was measured and dropped: 96 tiles on 148 one-block
+  // SMs put neighbouring tiles 40 planes apart in x, their frame rows no longer met in L2, 0.51 -> 0.70 ms.)
+  const int z0 = blockIdx.x * 64;
+  const int y0 = blockIdx.y * TY;
+  const int xs = blockIdx.z * xchunk;
+  const int xe = min(xs + xchunk, g.n[0]);
+  if (xs >= xe) return;
+  const int ta = min(TY, g.n[1] - y0);
+  const int tqa = min(32, (g.n[2] - z0) >> 1);
   // ---- role of this thread: window row j, window cell column c, what it computes
   int j, c;
   bool exists, e1, e2 = false, need_rho = true;
@@ -309,7 +312,6 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
     mv = max2(mv, dv);
   };
 
-  F2 n1B = bc2(0.f), n1v = bc2(0.f), n2B = bc2(0.f), n2v = bc2(0.f);
   RawP rawX, rawY;
 #pragma unroll
   for (int k = 0; k < 3; ++k)
@@ -368,6 +370,24 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
         stg2(fB1 + o + k * vB1, Bn[k]);
         stg2(fv1 + o + k * vv1, vn[k]);
       }
+      // slab rank: the edge planes also go into the neighbours' ghost planes (stores over NVLink)
+      long long pbd[2];
+      int pps[2];
+      bool pon[2] = {false, false};
+      if (a.peers.flags) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          pon[side] = peer_target(a.peers, i, g.n[0], side, pbd[side], pps[side]);
+          if (pon[side]) {
+            const long long po = o + (long long)pps[side] * sx;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              stg2(reinterpret_cast<float*>(reinterpret_cast<char*>(fB1 + po + k * vB1) + pbd[side]), Bn[k]);
+              stg2(reinterpret_cast<float*>(reinterpret_cast<char*>(fv1 + po + k * vv1) + pbd[side]), vn[k]);
+            }
+          }
+        }
+      }
       if constexpr (EMIT) {
         // this launch is expected to end the loop: write what mag_final would from R_{k+2}
         // (rho, v_n, p_2 -> emit_gas; B_n -> emit_B); valid only if the while-condition agrees
@@ -391,6 +411,20 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
           stg2(eb + k * veb, Bn[k]);
         }
         stg2(eg + 4 * veg, p2);
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          if (pon[side]) {
+            float* const pg = reinterpret_cast<float*>(reinterpret_cast<char*>(eg) + pbd[side]) + (long long)pps[side] * sx;
+            float* const pb = reinterpret_cast<float*>(reinterpret_cast<char*>(eb) + pbd[side]) + (long long)pps[side] * sx;
+            stg2(pg, rho);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              stg2(pg + (k + 1) * veg, vn[k]);
+              stg2(pb + k * veb, Bn[k]);
+            }
+            stg2(pg + 4 * veg, p2);
+          }
+        }
       }
     }
     __syncthreads();

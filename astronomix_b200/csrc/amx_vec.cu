@@ -361,6 +361,17 @@ __global__ void __launch_bounds__(32 * CW + 32, CW == 7 ? 2 : AMX_MAG_MINB8) mag
         dv = dv + ev * ev;
         stg2(qB + k * vB1, Bn);
         stg2(qv + k * vv1, vn);
+        if (a.peers.flags) {  // slab rank: edge planes -> the neighbours' ghost planes
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            long long bd;
+            int ps;
+            if (peer_target(a.peers, x, g.n[0], side, bd, ps)) {
+              stg2(reinterpret_cast<float*>(reinterpret_cast<char*>(qB + k * vB1) + bd) + (long long)ps * sx, Bn);
+              stg2(reinterpret_cast<float*>(reinterpret_cast<char*>(qv + k * vv1) + bd) + (long long)ps * sx, vn);
+            }
+          }
+        }
       }
       ch0 = max2(ch0, dB);
       ch1 = max2(ch1, dv);
@@ -1004,6 +1015,18 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
           float* po = fout + (long long)x * sx + col;
 #pragma unroll
           for (int k = 0; k < NV; ++k) stg2(po + k * vout, s.q[k]);
+          if (a.peers.flags) {  // slab rank: the edge planes also go into the neighbours' ghost planes (NVLink stores)
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+              long long bd;
+              int ps;
+              if (peer_target(a.peers, x, g.n[0], side, bd, ps)) {
+                float* pp = reinterpret_cast<float*>(reinterpret_cast<char*>(po) + bd) + (long long)ps * sx;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) stg2(pp + k * vout, s.q[k]);
+              }
+            }
+          }
           if (a.alpha_slots) {
             const F2 bx = wave_bound(s, 1, c), by = wave_bound(s, 2, c);
             wbx = fmaxf(wbx, fmaxf(bx.x, bx.y));

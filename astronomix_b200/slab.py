@@ -59,6 +59,24 @@ class AmxBackend:
     def _s(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    # ---- peer memory (include/amx.h "peer-memory plumbing")
+    def set_peers(self, flags, delta_lo, delta_hi):
+        """Arrays handed to the stage entry points from now on live in peer-mapped memory: kernels also
+        store their edge planes into the neighbours' ghost planes.  Returns amx_peer_push_supported."""
+        self.desc.peer_flags = int(flags)
+        self.desc.peer_delta_lo = int(delta_lo)
+        self.desc.peer_delta_hi = int(delta_hi)
+        return int(self.lib.amx_peer_push_supported(C.byref(self.desc))) if flags else 0
+
+    def peer_comm_bytes(self):
+        return int(self.lib.amx_peer_comm_bytes())
+
+    def peer_allreduce_max(self, comm_ptrs, rank, world, vals, count):
+        code = _lib.AMX_F32 if self.dtype == torch.float32 else _lib.AMX_F64
+        _lib.check(self.lib.amx_peer_allreduce_max(comm_ptrs, int(rank), int(world), self._p(vals), int(count), code,
+                                                   self._s()))
+        self.launches += 1
+
     @staticmethod
     def _p(t):
         return C.c_void_p(t.data_ptr()) if t is not None else None
@@ -206,24 +224,63 @@ class SlabDriver:
                 print(f"[slab] symmetric memory unavailable ({e!r}); NCCL send/recv halo exchange", flush=True)
                 self.p2p = False
 
-        def z(rows):
-            if self.p2p:
-                try:
-                    t = self._symm_mem.empty((rows,) + shape, dtype=dtype, device=device)
-                    t.zero_()
-                    h = self._symm_mem.rendezvous(t, self._symm_group)
-                    self._symm.append((t, h))
-                    return t
-                except Exception as e:  # pragma: no cover
-                    print(f"[slab] symmetric-memory rendezvous failed ({e!r}); NCCL send/recv halo exchange",
-                          flush=True)
-                    self.p2p = False
-            return torch.zeros((rows,) + shape, dtype=dtype, device=device)
-
-        self.S = [z(self.nv), z(self.nv)]
-        self.A, self.G = z(self.ng), z(self.ng)
-        self.X = [z(6), z(6)] if self.mhd else None
-        self.Gf = z(self.ng) if self.mhd else None  # gas after the magnetic write-back
+        # One symmetric allocation holds every slab array, so that ONE pair of byte deltas (own pointer ->
+        # the same element in the lower / upper neighbour's copy) serves all of them: the kernels that write an
+        # array also store its edge planes into the neighbours' ghost planes (amx_desc::peer_*), and a halo
+        # exchange of such an array is only a barrier.  A second, tiny symmetric buffer carries the MAX
+        # all-reduces / barriers (amx_peer_allreduce_max).
+        rows_of = [self.nv, self.nv, self.ng, self.ng] + ([6, 6, self.ng] if self.mhd else [])
+        plane = 1
+        for v in shape:
+            plane *= int(v)
+        self._arena = self._arena_h = None
+        self._comm = None
+        self.push = 0          # amx_peer_push_supported bits of the backend
+        self._pushed = {}      # data_ptr of an array whose producer stored its halos -> sync count at that time
+        self._sync_seq = 0     # collectives (all-reduces, barriers) enqueued so far
+        if self.p2p:
+            try:
+                total = sum(rows_of) * plane
+                self._arena = self._symm_mem.empty((total,), dtype=dtype, device=device)
+                self._arena.zero_()
+                self._arena_h = self._symm_mem.rendezvous(self._arena, self._symm_group)
+                self._symm.append((self._arena, self._arena_h))
+            except Exception as e:  # pragma: no cover
+                print(f"[slab] symmetric-memory rendezvous failed ({e!r}); NCCL send/recv halo exchange", flush=True)
+                self.p2p = False
+                self._arena = None
+        arrays, off = [], 0
+        for rows in rows_of:
+            if self._arena is not None:
+                arrays.append(self._arena[off:off + rows * plane].view((rows,) + shape))
+                off += rows * plane
+            else:
+                arrays.append(torch.zeros((rows,) + shape, dtype=dtype, device=device))
+        self.S = [arrays[0], arrays[1]]
+        self.A, self.G = arrays[2], arrays[3]
+        self.X = [arrays[4], arrays[5]] if self.mhd else None
+        self.Gf = arrays[6] if self.mhd else None  # gas after the magnetic write-back
+        if self.p2p and os.environ.get("AMX_SLAB_PUSH", "1") != "0" and hasattr(self.backend, "set_peers"):
+            try:
+                h = self._arena_h
+                left, right = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+                periodic = self.bcx[0] == oc.PERIODIC_BOUNDARY
+                flags = (1 if (periodic or self.rank > 0) else 0) | (2 if (periodic or self.rank < self.world - 1) else 0)
+                ptrs = [int(q) for q in h.buffer_ptrs]
+                nbytes = self.backend.peer_comm_bytes()
+                self._comm = self._symm_mem.empty((max(nbytes, 2048),), dtype=torch.uint8, device=device)
+                self._comm.zero_()
+                hc = self._symm_mem.rendezvous(self._comm, self._symm_group)
+                self._comm_h = hc
+                self._comm_ptrs = (C.c_void_p * self.world)(*[int(q) for q in hc.buffer_ptrs])
+                torch.cuda.synchronize(device)
+                dist.barrier(group=group)  # every rank's communication buffer is zeroed before anybody signals
+                self.push = self.backend.set_peers(flags, ptrs[left] - ptrs[self.rank], ptrs[right] - ptrs[self.rank])
+                self._push_flags = flags
+            except Exception as e:  # pragma: no cover
+                print(f"[slab] peer-memory plumbing unavailable ({e!r}); copies + NCCL all-reduce", flush=True)
+                self._comm = None
+                self.push = 0
         self.alpha = torch.zeros(3, dtype=dtype, device=device)
         self.change = torch.zeros(2, dtype=dtype, device=device)
         self.change4 = torch.zeros(4, dtype=dtype, device=device)
@@ -267,15 +324,13 @@ class SlabDriver:
                 break
         else:
             return False
-        row_bytes = base[0].numel() * base.element_size()
-        r0 = off // row_bytes
-        rows = t.shape[0]
+        off_e = off // base.element_size()
 
         def peer(rank):
             key = (base.data_ptr(), rank)
             if key not in self._peer_views:
                 self._peer_views[key] = h.get_buffer(rank, tuple(base.shape), base.dtype)
-            return self._peer_views[key][r0:r0 + rows]
+            return self._peer_views[key][off_e:off_e + t.numel()].view(t.shape)
 
         if send_l:   # my first active planes are the left neighbour's right ghost planes
             peer(left)[:, n + NG:].copy_(t[:, NG:2 * NG])
@@ -283,12 +338,30 @@ class SlabDriver:
             peer(right)[:, :NG].copy_(t[:, n:n + NG])
         h.barrier(channel=0)
         self.collectives += 1
+        self._sync_seq += 1
         return True
 
     def _allreduce_max(self, t):
         if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            if self._comm is not None:  # one kernel through peer memory instead of an NCCL launch
+                self.backend.peer_allreduce_max(self._comm_ptrs, self.rank, self.world, t, t.numel())
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
             self.collectives += 1
+            self._sync_seq += 1
+
+    def _barrier(self):
+        self.backend.peer_allreduce_max(self._comm_ptrs, self.rank, self.world, None, 0)
+        self.collectives += 1
+        self._sync_seq += 1
+
+    def _wrote(self, t, bit):
+        """``t`` was just written by a kernel of push class ``bit`` (1 stage, 2 iterate, 4 write-back): if that
+        kernel stores halos itself, remember it so that exchange(t) shrinks to a barrier (or to nothing when a
+        collective has passed since).  Safe against write-after-read: between any kernel that reads the ghost
+        planes of an array and the next kernel that writes the array there is a collective on every rank."""
+        if self.push & bit:
+            self._pushed[t.data_ptr()] = self._sync_seq
 
     def exchange(self, t, flip_rows=()):
         """Refresh the x ghost planes of ``t`` ([rows][nxl+4][...]).  flip_rows: rows negated in
@@ -305,7 +378,14 @@ class SlabDriver:
         else:
             send_l = periodic or not at_left
             send_r = periodic or not at_right
-            if self.p2p and self._exchange_p2p(t, left, right, send_l, send_r):
+            seq = self._pushed.pop(t.data_ptr(), None)
+            if seq is not None:
+                # the producer stored the edge planes into the neighbours' ghost planes while it ran; they are
+                # complete once every rank has passed a collective enqueued after its producer
+                if seq == self._sync_seq:
+                    self._barrier()
+                send_l = send_r = False
+            elif self.p2p and self._exchange_p2p(t, left, right, send_l, send_r):
                 send_l = send_r = False  # done
             # one packed buffer per direction (a single strided copy each) instead of one message
             # per row: 4 NCCL point-to-point operations per exchange, grouped into one launch.
@@ -377,9 +457,14 @@ class SlabDriver:
         x0 = self.rank * self.nxl
         loc = torch.as_tensor(global_state)[:, x0:x0 + self.nxl].to(self.device, self.dtype)
         self.S[0][:, NG:NG + self.nxl].copy_(loc)
-        self.cur = 0
+        self.reset()
         self.time.zero_()
         self._alpha_of(self.S[0][: self.ng])
+
+    def reset(self):
+        """S[0] holds a new initial state (active planes): restart the time loop from it."""
+        self.cur = 0
+        self._pushed.clear()  # nobody stored the halos of the new state
 
     def local_result(self):
         return self.S[self.cur][:, NG:NG + self.nxl]
@@ -407,11 +492,13 @@ class SlabDriver:
         if cfg.split == oc.UNSPLIT:
             self.exchange(gas_in, flip_rows=(1,))
             b.hydro_stage(gas_in, None, self.A, self.dt, scale, self.alpha, self.alpha if self.lf else None)
+            self._wrote(self.A, 1)
             if self.lf:
                 self._allreduce_max(self.alpha)
             self.exchange(self.A, flip_rows=(1,))
             want = final_alpha or self.lf
             b.hydro_stage(self.A, gas_in, gas_out, self.dt, scale, self.alpha, self.alpha if want else None)
+            self._wrote(gas_out, 1)
             if want:
                 self._allreduce_max(self.alpha)
             return
@@ -455,12 +542,17 @@ class SlabDriver:
                 emit = self.pairs and not self.lf and c + 2 == self.expect_evals
                 b.magnetic_pair_guarded(B0, gas, src, dst, self.dt, self.change4, c,
                                         self.Gf if emit else None, B_out if emit else None)
+                self._wrote(dst, 2)
+                if emit:
+                    self._wrote(self.Gf, 2)
+                    self._wrote(B_out, 2)
                 self._allreduce_max(self.change4)
                 b.magnetic_check_pair(self.change4, c, nl & 1, emit)
                 b.magnetic_fix_guarded(B0, gas, src, dst, self.dt, c)
                 c += 2
             else:
                 b.magnetic_iter_guarded(B0, gas, src, dst, self.dt, self.change, nl)
+                self._wrote(dst, 2)
                 self._allreduce_max(self.change)
                 b.magnetic_check(self.change, nl)
                 c += 1
@@ -478,6 +570,8 @@ class SlabDriver:
             active, it = b.magnetic_state()
         self.expect_evals = it + 1
         b.magnetic_final_guarded(gas, self.Gf, self.X[0], self.X[1], B_out, self.alpha if self.lf else None)
+        self._wrote(self.Gf, 4)
+        self._wrote(B_out, 4)
         if self.lf:
             self._allreduce_max(self.alpha)
         return it
@@ -509,41 +603,61 @@ class SlabDriver:
         return StepInfo(steps, float(self.time.item()), iters, getattr(self.backend, "launches", 0))
 
 
-def bench_weak(n, K, W, device):
-    """bench.py's N > 1 arm: 3-D MHD blast, n^3 cells per rank, slabs along x (weak scaling)."""
-    import json
-    import os
-    import time as _time
+# ---------------------------------------------------------------------------------------- bench.py, N > 1
+#: north-star weak-scaling series (SURVEY.md 8d, C5 geometry): 512^3 cells per GPU, slabs along x;
+#: world size -> global grid.  8 GPUs = the 1024^3 domain as 128 x 1024^2 slabs.
+WEAK_SERIES = {1: (512, 512, 512), 2: (1024, 512, 512), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}
+
+
+def fill_blast_lattice(drv, cell_n, p_in=1000.0, p_out=0.1, B0=None, r_inj=0.1):
+    """Initial state of the local slab, built on the device: the 3-D MHD blast of tests/mhd_tests/mhd_blast3D.py
+    repeated with period 1 in every direction on a grid of spacing 1 / cell_n (a cubic cell_n^3 grid gives
+    exactly problems.mhd_blast3d): every 512^3 block of the series holds the same problem, so dt and the
+    fixed-point iteration counts equal the single-GPU run's."""
+    import math
 
     import numpy as np
+    B0 = 100.0 / math.sqrt(4.0 * math.pi) if B0 is None else B0
+    dev, n = drv.device, drv.nxl
+    dx = 1.0 / cell_n
 
-    from . import problems as pr
+    def d2(i0, m):
+        c = (torch.arange(i0, i0 + m, device=dev, dtype=torch.float64) + 0.5) * dx
+        c = torch.remainder(c, 1.0) - 0.5
+        return c * c
 
-    world, rank = dist.get_world_size(), dist.get_rank()
-    nx = n * world
-    config, params, rv = pr.make(3, n, mhd=True)
-    params = params._replace(t_end=1.0e9)
-    # global grid nx x n x n with the cell size of the n^3 problem (non-cubic: Q14 is bypassed by
-    # building the local state directly; the physics is the periodic array of blasts)
-    local = np.ascontiguousarray(pr.mhd_blast3d(n, np.float32))  # every rank holds one blast
-    drv = SlabDriver(config, params, rv, (nx, n, n), torch.float32, device)
-    host = torch.from_numpy(local).pin_memory()
-    drv.S[0][:, NG:NG + n].copy_(host.to(device, non_blocking=True))
-    drv.cur = 0
+    gy, gz = drv.global_n[1], drv.global_n[2]
+    r2 = d2(drv.rank * n, n)[:, None, None] + d2(0, gy)[None, :, None] + d2(0, gz)[None, None, :]
+    act = drv.S[0][:, NG:NG + n]
+    act[0].fill_(1.0)
+    act[1:4].zero_()
+    act[4].copy_(torch.where(r2 < r_inj ** 2, p_in, p_out))
+    del r2
+    theta, phi = np.pi / 2, np.pi / 4
+    act[5].fill_(float(B0 * np.sin(theta) * np.cos(phi)))
+    act[6].fill_(float(B0 * np.sin(theta) * np.sin(phi)))
+    act[7].fill_(float(B0 * np.cos(theta)))
+    drv.reset()
+    drv.time.zero_()
     drv._alpha_of(drv.S[0][: drv.ng])
+
+
+def _timed_steps(drv, K, W, device, sample_clocks):
+    import time as _time
+    world, rank = dist.get_world_size(), dist.get_rank()
     for _ in range(W):
         drv.step()
     torch.cuda.synchronize()
     dist.barrier()
-    from bench import ClockSampler  # the driver script is on sys.path when this runs
-    sampler = ClockSampler(device.index or 0)
-    if rank == 0:
+    sampler = None
+    if sample_clocks and rank == 0:
+        from bench import ClockSampler  # the driver script is on sys.path when this runs
+        sampler = ClockSampler(device.index or 0)
         sampler.start()
         _time.sleep(0.3)
     dist.barrier()
     torch.cuda.synchronize()
-    l0 = drv.backend.launches
-    c0 = drv.collectives
+    l0, c0 = drv.backend.launches, drv.collectives
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = _time.time()
     ev0.record()
@@ -554,26 +668,47 @@ def bench_weak(n, K, W, device):
     torch.cuda.synchronize()
     dist.barrier()
     t1 = _time.time()
-    ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-    launches = drv.backend.launches - l0
-    colls = drv.collectives - c0
-    # end to end: pinned host slab -> device -> K steps -> host
-    out_host = torch.empty(local.shape, dtype=torch.float32, pin_memory=True)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    drv.S[0][:, NG:NG + n].copy_(host.to(device, non_blocking=True))
-    drv.cur = 0
-    drv.time.zero_()
-    drv._alpha_of(drv.S[0][: drv.ng])
-    for _ in range(K):
-        drv.step()
-    out_host.copy_(drv.local_result(), non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1)
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # device time, max over ranks
+    clocks = sampler.stop(t0, t1) if sampler is not None else None
+    return float(ms.item()), iters, drv.backend.launches - l0, drv.collectives - c0, clocks
+
+
+def _slab_equals_single(device, n=256, steps=2):
+    """FAST-arithmetic check that rides with every multi-GPU bench run: the n^3 blast split into slabs gives
+    the same bits as amx_integrate on one GPU (max is the only reduction on the path)."""
+    import numpy as np
+
+    from . import problems as pr
+    from . import stepping as ti
+    rank = dist.get_rank()
+    config, params, rv = pr.make(3, n, mhd=True)
+    params = params._replace(t_end=1.0e9)
+    drv = SlabDriver(config, params, rv, (n, n, n), torch.float32, device)
+    fill_blast_lattice(drv, n)
+    info = drv.run(max_steps=steps)
+    out = drv.gather()
+    same = True
+    if rank == 0:
+        ref = ti.integrate_steps(torch.from_numpy(pr.mhd_blast3d(n, np.float32)).to(device), config, params, rv, steps)
+        same = bool(torch.equal(out, ref)) and info.magnetic_iterations == ti.last_info.magnetic_iterations
+    flag = torch.tensor([1 if same else 0], device=device)
+    dist.broadcast(flag, 0)
+    del drv
+    torch.cuda.empty_cache()
+    return bool(flag.item())
+
+
+def bench_weak(n, K, W, device):
+    """bench.py's N > 1 arm.  Headline: the north-star weak series, 512^3 cells per GPU (WEAK_SERIES; 8 GPUs =
+    1024^3 as 128 x 1024^2 slabs).  Secondary: n^3 cells per rank (global n*world x n x n, round 1's
+    geometry).  Both: 3-D MHD blast lattice, fp32, slabs along x."""
+    import json
+    import os
+
+    from . import problems as pr
+
+    world, rank = dist.get_world_size(), dist.get_rank()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
@@ -581,15 +716,80 @@ def bench_weak(n, K, W, device):
     except OSError:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
-    bytes_cell = (10 * 5 + 13 + 19 * (iters / K)) * 4
-    value = world * n ** 3 * K / (ms * 1e-3)
+    same = _slab_equals_single(device)
+
+    def run(cell_n, global_n, with_e2e, sample_clocks):
+        config, params, rv = pr.make(3, cell_n, mhd=True)
+        params = params._replace(t_end=1.0e9)
+        drv = SlabDriver(config, params, rv, global_n, torch.float32, device)
+        fill_blast_lattice(drv, cell_n)
+        ms, iters, launches, colls, clocks = _timed_steps(drv, K, W, device, sample_clocks)
+        cells = global_n[0] * global_n[1] * global_n[2]
+        res = {"ms": ms, "iters": iters, "launches": launches, "colls": colls, "clocks": clocks, "cells": cells,
+               "value": cells * K / (ms * 1e-3), "push": drv.push, "p2p": drv.p2p,
+               "local": (drv.nxl,) + tuple(global_n[1:])}
+        if with_e2e:
+            # end to end: pinned host slab -> device -> K steps -> the same pinned buffer
+            n_loc = drv.nxl
+            host = torch.empty((drv.nv, n_loc) + tuple(global_n[1:]), dtype=torch.float32, pin_memory=True)
+            fill_blast_lattice(drv, cell_n)
+            host.copy_(drv.S[0][:, NG:NG + n_loc])
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            drv.S[0][:, NG:NG + n_loc].copy_(host, non_blocking=True)
+            drv.reset()
+            drv.time.zero_()
+            drv._alpha_of(drv.S[0][: drv.ng])
+            for _ in range(K):
+                drv.step()
+            host.copy_(drv.local_result(), non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res["e2e_ms"] = float(t.item())
+            res["host_bytes"] = host.numel() * 4
+            del host
+        del drv
+        torch.cuda.empty_cache()
+        return res
+
+    series = WEAK_SERIES.get(world)
+    if series is not None and os.environ.get("AMX_BENCH_SERIES", "1") != "0":
+        main = run(512, series, True, True)
+        second = run(n, (n * world, n, n), False, False)
+        workload = (f"3D MHD blast lattice, 512^3 cells per GPU (north-star weak series: global "
+                    f"{series[0]}x{series[1]}x{series[2]}, local slab {main['local'][0]}x{main['local'][1]}x{main['local'][2]}), "
+                    "fp32, HLL, minmod, unsplit RK2-SSP, Pang-Wu implicit-midpoint magnetic step, periodic, C_cfl=0.4")
+    else:
+        main = run(n, (n * world, n, n), True, True)
+        second = None
+        workload = None
+    bytes_cell = (10 * 5 + 13 + 19 * (main["iters"] / K)) * 4
+    per_gpu = main["value"] / world
     roofline = {"bound": "hbm", "kernel": "whole step (per-kernel event timing is N=1 only)",
-                "achieved": value / world * bytes_cell / 1e9, "peak": hbm, "unit": "GB/s",
-                "frac": value / world * bytes_cell / 1e9 / hbm, "traffic": None,
+                "achieved": per_gpu * bytes_cell / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": per_gpu * bytes_cell / 1e9 / hbm, "traffic": None,
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"}
-    return {"ms": ms, "e2e_ms": e2e_ms, "h2d_bytes": local.nbytes, "d2h_bytes": local.nbytes, "launches": launches,
-            "clocks": clocks, "roofline": roofline, "kernels": {}, "mag_iters": iters,
-            "config": {"collectives_per_step": colls / K, "halo": "2 planes per side per exchange, " + (
-                           "edge planes stored into the neighbours' ghost planes over NVLink (symmetric memory) "
-                           "+ device-side barrier" if drv.p2p else "NCCL send/recv (packed)"),
-                       "reductions": "NCCL all-reduce MAX of 3 (dt) + 2 (fixed point) scalars"}}
+    if main["push"]:
+        halo = ("edge planes stored into the neighbours' ghost planes by the producing kernels themselves (P2P "
+                "stores over NVLink, overlapped with the launch); an exchange is a barrier")
+        red = "MAX all-reduce of 3 (dt) / 4 (fixed point) scalars in one kernel through peer memory"
+    elif main["p2p"]:
+        halo = "edge planes copied into the neighbours' ghost planes over NVLink (symmetric memory) + device-side barrier"
+        red = "NCCL all-reduce MAX of 3 (dt) + 4 (fixed point) scalars"
+    else:
+        halo, red = "NCCL send/recv (packed)", "NCCL all-reduce MAX"
+    cfg = {"collectives_per_step": main["colls"] / K, "halo": halo, "reductions": red,
+           "slab_equals_single_gpu_bitwise_256": same}
+    if second is not None:
+        cfg["secondary"] = {"workload": f"{n}^3 cells per rank, global {n * world}x{n}x{n}",
+                            "value": second["value"], "ms_per_step": second["ms"] / K,
+                            "collectives_per_step": second["colls"] / K,
+                            "magnetic_iterations_per_step": second["iters"] / K}
+    return {"ms": main["ms"], "e2e_ms": main["e2e_ms"], "h2d_bytes": main["host_bytes"],
+            "d2h_bytes": main["host_bytes"], "launches": main["launches"], "clocks": main["clocks"],
+            "roofline": roofline, "kernels": {}, "mag_iters": main["iters"], "cells": main["cells"],
+            "workload": workload, "config": cfg}

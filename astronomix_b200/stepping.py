@@ -72,24 +72,47 @@ def _reject_unsupported(config, registered_variables=None):
         raise NotImplementedError("extra registered variables (wind density, cosmic rays) are not built")
 
 
+#: pinned staging buffers for NumPy / CPU-tensor states, by direction ("in" / "out"); allocated once per size
+#: (cudaHostAlloc of half a gigabyte costs more than the copy it serves)
+_staging = {}
+
+
+def _pinned(shape, dtype, slot):
+    need = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    ent = _staging.get(slot)
+    if ent is None or ent[0].numel() < need:
+        ent = [torch.empty(max(need, 1), dtype=torch.uint8, pin_memory=True), None]
+        _staging[slot] = ent
+    if ent[1] is not None:  # the previous transfer out of / into this buffer must have finished
+        ent[1].synchronize()
+    return ent[0][:need].view(dtype).view(tuple(shape)), ent
+
+
 def _to_device(state):
     """-> (contiguous CUDA tensor, kind) ; kind remembers how to hand the result back."""
     if isinstance(state, torch.Tensor):
-        if not state.is_cuda:
-            t = state.contiguous().pin_memory().cuda(non_blocking=True)
-            return t, "torch_cpu"
-        return state.contiguous(), "torch_cuda"
-    arr = np.ascontiguousarray(state)
-    if arr.dtype not in (np.float32, np.float64):
-        raise TypeError(f"state dtype must be float32 or float64, got {arr.dtype}")
-    t = torch.from_numpy(arr).pin_memory().cuda(non_blocking=True)
-    return t, "numpy"
+        if state.is_cuda:
+            return state.contiguous(), "torch_cuda"
+        src, kind = state.contiguous(), "torch_cpu"
+    else:
+        arr = np.ascontiguousarray(state)
+        if arr.dtype not in (np.float32, np.float64):
+            raise TypeError(f"state dtype must be float32 or float64, got {arr.dtype}")
+        src, kind = torch.from_numpy(arr), "numpy"
+    if src.is_pinned():
+        return src.cuda(non_blocking=True), kind
+    stage, ent = _pinned(src.shape, src.dtype, "in")
+    stage.copy_(src)
+    t = stage.cuda(non_blocking=True)
+    ent[1] = torch.cuda.Event()
+    ent[1].record()
+    return t, kind
 
 
 def _from_device(t, kind):
     if kind == "torch_cuda":
         return t
-    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host, ent = _pinned(t.shape, t.dtype, "out")
     host.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return host.numpy().copy() if kind == "numpy" else host.clone()
@@ -133,9 +156,7 @@ def time_integration(primitive_state, config, params, registered_variables: Regi
     if config.activate_snapshot_callback and snapshot_callable is None:
         raise ValueError("activate_snapshot_callback needs a snapshot_callable")
     if sharding is not None:
-        raise NotImplementedError(
-            "jax shardings do not exist here; multi-GPU runs use astronomix_b200.slab.SlabDriver"
-        )
+        return _time_integration_sharded(primitive_state, config, params, registered_variables, sharding)
     struct = config.state_struct
     state = primitive_state.primitive_state if struct else primitive_state
     t, kind = _to_device(state)
@@ -168,6 +189,74 @@ def time_integration(primitive_state, config, params, registered_variables: Regi
                                 stats.kernel_launches, stats.pair_launches, stats.single_launches,
                                 stats.final_launches)
     res = _from_device(out, kind)
+    return StateStruct(primitive_state=res) if struct else res
+
+
+class SlabSharding(NamedTuple):
+    """What ``time_integration(..., sharding=...)`` takes here.  The reference takes a jax ``NamedSharding`` of
+    the ``[var, x, y, z]`` state (time_integration.py:61-68, :108-118; the scaling scripts shard axis x:
+    arena/arena_tests/scaling/scaling.py:93-98) and lets GSPMD insert the collectives; here the same
+    decomposition is explicit: one process per GPU under ``torch.distributed``, x slabs in rank order
+    (astronomix_b200.slab).  ``"x"`` and partition tuples such as ``(None, "x", None, None)`` are accepted
+    as shorthands for ``SlabSharding()``."""
+
+    group: object = None        # torch.distributed process group (None: the default group)
+    local_input: bool = False   # primitive_state is this rank's slab [var, n_x / P, ...], not the global array
+    local_output: bool = False  # return this rank's slab instead of the gathered global array
+
+
+def _as_slab_sharding(sharding):
+    if isinstance(sharding, SlabSharding):
+        return sharding
+    if sharding == "x":
+        return SlabSharding()
+    if isinstance(sharding, (tuple, list)) and len(sharding) >= 2 and sharding[1] is not None \
+            and all(a is None for i, a in enumerate(sharding) if i != 1):
+        return SlabSharding()
+    raise NotImplementedError(
+        f"sharding={sharding!r}: only the x-slab decomposition is built (SlabSharding(), 'x' or (None, 'x', ...))")
+
+
+def _time_integration_sharded(primitive_state, config, params, registered_variables, sharding):
+    """time_integration on an x-slab decomposition: every rank of the group makes the same call."""
+    global last_info
+    import torch.distributed as dist
+
+    from .slab import SlabDriver
+    sh = _as_slab_sharding(sharding)
+    if not dist.is_initialized():
+        raise RuntimeError("sharding needs torch.distributed (one process per GPU, e.g. under torchrun)")
+    if (config.turbulent_forcing_config.turbulent_forcing or config.return_snapshots
+            or config.activate_snapshot_callback):
+        raise NotImplementedError("snapshots / callbacks / turbulent forcing on a sharded run are not built")
+    struct = config.state_struct
+    state = primitive_state.primitive_state if struct else primitive_state
+    world = dist.get_world_size(sh.group)
+    device = torch.device("cuda", torch.cuda.current_device())
+    if isinstance(state, torch.Tensor):
+        kind = "torch_cuda" if state.is_cuda else "torch_cpu"
+        src = state
+    else:
+        kind, src = "numpy", torch.from_numpy(np.ascontiguousarray(state))
+    if src.dtype not in _TORCH_DTYPES:
+        raise TypeError(f"state dtype must be float32 or float64, got {src.dtype}")
+    shape = tuple(int(v) for v in src.shape[1:])
+    global_n = ((shape[0] * world,) + shape[1:]) if sh.local_input else shape
+    if src.dim() != config.dimensionality + 1 or src.shape[0] != registered_variables.num_vars:
+        raise ValueError(f"state must be [{registered_variables.num_vars}, ...], got {tuple(src.shape)}")
+    drv = SlabDriver(config, params, registered_variables, global_n, src.dtype, device, group=sh.group)
+    if sh.local_input:
+        from .slab import NG
+        drv.S[0][:, NG:NG + drv.nxl].copy_(src.to(device))
+        drv.reset()
+        drv.time.zero_()
+        drv._alpha_of(drv.S[0][: drv.ng])
+    else:
+        drv.scatter(src)
+    info = drv.run()
+    last_info = IntegrationInfo(info.steps, info.time, float(drv.dt.item()), info.magnetic_iterations, info.launches)
+    out = drv.local_result().contiguous() if sh.local_output else drv.gather()
+    res = out if kind == "torch_cuda" else (out.cpu().numpy() if kind == "numpy" else out.cpu())
     return StateStruct(primitive_state=res) if struct else res
 
 

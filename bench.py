@@ -1,17 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- cell-updates/s of the fused finite-volume MHD step on B200.
 
-Workload (BASELINE.json config 3): 3-D MHD blast wave, 256^3 cells per GPU, fp32, HLL,
-minmod, unsplit RK2-SSP, Pang-Wu magnetic sub-step (implicit midpoint), periodic,
-C_cfl 0.4, synthetic initial condition of tests/mhd_tests/mhd_blast3D.py.  One "step" is
-one full time step: CFL dt + hydro(dt/2) . magnetic(dt) . hydro(dt/2).  For N > 1 the
-domain is slab-decomposed along x with 256^3 cells per rank (weak scaling), halo exchange
-and dt / fixed-point all-reduces over NCCL.
+N = 1 (BASELINE.json config 4, the configuration the north star's 60 % target is quoted on): 3-D MHD blast
+wave, 256^3 cells, fp32, HLL, minmod, unsplit RK2-SSP, Pang-Wu magnetic sub-step (implicit midpoint),
+periodic, C_cfl 0.4, synthetic initial condition of tests/mhd_tests/mhd_blast3D.py.  One "step" is one
+full time step: CFL dt + hydro(dt/2) . magnetic(dt) . hydro(dt/2).  The timed region is blocks of exactly
+K steps (one amx_integrate call each, always from the same warmed-up state), repeated until it is at
+least one second long.  `secondary` carries the other BASELINE configurations (C1 Sod, C2
+Kelvin-Helmholtz 1024^2, C3 Orszag-Tang 2048^2), the published benchmark's flux (Lax-Friedrichs,
+C_cfl 0.8, PERIODIC_ROLL; arena/fv_mhd.py:36-49) and the 512^3 single-GPU point of the weak series.
+
+N > 1 (config 5 geometry): the north-star weak series, 512^3 cells per GPU in slabs along x
+(1024x512^2 on 2, 1024^2x512 on 4, 1024^3 = 128x1024^2 slabs on 8), halo planes stored into the
+neighbours' ghost planes by the producing kernels, dt / fixed-point MAX all-reduces through peer memory;
+`config.secondary` keeps round 1's 256^3-per-rank line.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
 
-prints ONE JSON line (rank 0).  --impl reference times the CPU oracle (the NumPy
-restatement of the reference; JAX is not installable here) on the host cores.
+prints ONE JSON line (rank 0).  --impl reference times the CPU oracle (the NumPy restatement of the
+reference; JAX is not installable here) on the host cores, on a bounded sample that its
+`config.workload` names.
 """
 import argparse
 import json
@@ -141,7 +149,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * cores * n ** 3 / rate, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(), "wall_s": wall,
+            "config": {"workload": f"3D MHD blast, bounded sample of the native arm's workload: {cores} replicas of "
+                                   f"{n}^3 cells (one per host core), fp32, HLL, minmod, unsplit RK2-SSP, Pang-Wu "
+                                   "implicit-midpoint magnetic step, periodic, C_cfl=0.4",
+                       "cells_per_step": cores * n ** 3, "native_workload": workload_config()["workload"]},
+            "wall_s": wall,
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -176,22 +188,24 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         from astronomix_b200 import slab
-        result = slab.bench_weak(n, K, W, dev)
-        t_ms = torch.tensor([result["ms"]], device=dev, dtype=torch.float64)
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        ms = float(t_ms.item())
-        e_ms = torch.tensor([result["e2e_ms"]], device=dev, dtype=torch.float64)
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        result = slab.bench_weak(n, K, W, dev)  # times are already the max over ranks
+        ms, e2e_ms = result["ms"], result["e2e_ms"]
         if rank == 0:
-            cells = world * n ** 3
+            cells = result["cells"]
+            cfg = workload_config(n)
+            if result["workload"]:
+                cfg = {"workload": result["workload"], "cells_per_gpu": cells // world,
+                       "l2_policy": "inputs larger than L2 (state 4.3 GB per GPU)"}
+            else:
+                cfg["decomposition"] = f"slab along x, {n}^3 per rank, global {world * n}x{n}x{n}"
             line = {"metric": METRIC, "value": cells * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
                     "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                    "config": dict(workload_config(n), decomposition=f"slab along x, {n}^3 per rank, "
-                                   f"global {world * n}x{n}x{n}", **result["config"]),
-                    "e2e": {"value": cells * K / (float(e_ms.item()) * 1e-3), "unit": UNIT,
+                    "config": dict(cfg, **result["config"]),
+                    "e2e": {"value": cells * K / (e2e_ms * 1e-3), "unit": UNIT,
                             "h2d_bytes_per_step": result["h2d_bytes"] * world / K,
-                            "d2h_bytes_per_step": result["d2h_bytes"] * world / K},
+                            "d2h_bytes_per_step": result["d2h_bytes"] * world / K,
+                            "call": f"per rank: pinned host slab -> device, {K} steps of SlabDriver.step, device -> host"},
                     "gpu_launches": result["launches"], "clocks": result["clocks"],
                     "roofline": result["roofline"], "kernels": result["kernels"],
                     "magnetic_iterations_per_step": result["mag_iters"] / K}
@@ -217,23 +231,33 @@ def run_native(args):
                                      1.0e9, steps, ws_ptr, stream, C.byref(stats)))
         return stats.steps, stats.magnetic_iterations, stats.kernel_launches
 
-    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps
+    # ---- device-resident throughput: W warm-up steps, then blocks of exactly K timed steps (each block one
+    # amx_integrate call from the same warmed-up state s1) until the timed region is >= 1 s
     integrate(s0, s1, W)
     torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    integrate(s1, s2, K)  # untimed probe block: how many blocks fill a second
+    ev1.record()
+    torch.cuda.synchronize()
+    blocks = max(1, min(200, int(np.ceil(1000.0 / max(ev0.elapsed_time(ev1), 1e-3)))))
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.time()
     ev0.record()
-    steps_done, mag_iters, launches = integrate(s1, s2, K)
+    launches = 0
+    for _ in range(blocks):
+        steps_done, mag_iters, nl = integrate(s1, s2, K)
+        launches += nl
+        assert steps_done == K, steps_done
     ev1.record()
     torch.cuda.synchronize()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
-    ms = ev0.elapsed_time(ev1)
-    assert steps_done == K, steps_done
+    ms = ev0.elapsed_time(ev1) / blocks  # per block of K steps
+    launches //= blocks
     # ---- the same K steps again with per-kernel-class CUDA events on the launch stream (the events
     # add a little launch overhead, so this pass explains `value` but is not the one that is reported)
     lib.amx_profile_enable(1)
@@ -299,13 +323,16 @@ def run_native(args):
                             "evaluation); the fixed point runs two evaluations per launch, so the bytes "
                             "actually required are step_bytes_per_cell_with_fused_pairs")
     try:
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from this round's `ncu --set full` capture
+        # (tools/traffic_json.py writes the file and names the capture); a bench run is never under a profiler
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         roofline["traffic"] = prof.get(dom, {}).get("dram_bytes_per_launch")
+        roofline["traffic_source"] = prof.get("source")
     except (OSError, ValueError):
         pass
 
-    # ---- end to end through the public call: pinned host state -> H2D -> K steps -> D2H
-    from astronomix_b200 import stepping
+    # ---- end to end at the C-ABI (what a jax.ffi custom call sees when the caller's buffers are host
+    # memory): pinned host state -> H2D -> one amx_integrate call of K steps -> D2H
     out_host = torch.empty(state.shape, dtype=torch.float32, pin_memory=True)
 
     def e2e_once():
@@ -316,13 +343,41 @@ def run_native(args):
     e2e_once()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(1, min(blocks, 10))
     e0.record()
-    e2e_once()
+    for _ in range(reps):
+        e2e_once()
     e1.record()
     torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_ms = e0.elapsed_time(e1) / reps
     state_bytes = state.nbytes
-    del stepping
+    del ws, s1, s2, out_host
+    torch.cuda.empty_cache()
+
+    # ---- end to end through the public Python call with a plain (pageable) NumPy state: staging through
+    # pinned memory, workspace look-up, H2D, K steps, D2H and the copy into the NumPy result all inside
+    from astronomix_b200 import stepping
+    stepping.integrate_steps(state, config, params, rv, K)  # first call allocates the workspace / staging buffers
+    tp0 = time.perf_counter()
+    for _ in range(3):
+        res = stepping.integrate_steps(state, config, params, rv, K)
+    api_s = (time.perf_counter() - tp0) / 3
+    assert isinstance(res, np.ndarray) and res.shape == state.shape
+    e2e_api = {"value": cells * K / api_s, "unit": UNIT, "ms_per_call": api_s * 1e3,
+               "call": f"astronomix_b200.stepping.integrate_steps(numpy_state, ..., {K}): time_integration's path "
+                       "with the step count fixed; host wall clock around the call, pageable NumPy in and out"}
+    stepping._ws_cache.clear()
+    stepping._staging.clear()
+    del res
+    torch.cuda.empty_cache()
+
+    # ---- the other configurations as secondary keys (device-resident, same method, short runs)
+    secondary = None
+    if not args.no_secondary:
+        try:
+            secondary = secondary_configs(lib, dev, hbm_peak)
+        except Exception as e:  # a secondary line must never take the headline down
+            secondary = {"error": repr(e)}
 
     # ---- CPU baseline beside it (bounded sample of the same workload)
     cpu = None
@@ -337,14 +392,112 @@ def run_native(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(n),
+            "timed_blocks": blocks, "timed_region_ms": ms * blocks,
             "e2e": {"value": cells * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": state_bytes / K,
                     "d2h_bytes_per_step": state_bytes / K,
-                    "call": f"one amx_integrate call of {K} steps: pinned host state -> device -> host"},
+                    "call": f"C-ABI: pinned host state -> device, one amx_integrate call of {K} steps (workspace "
+                            "allocated once outside), device -> pinned host; copies amortised over the call's "
+                            f"{K} steps, as in the API's natural use; mean of {reps} calls"},
+            "e2e_public_api": e2e_api,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels, "ms_per_step_profiled_pass": ms_prof / K,
             "magnetic_iterations_per_step": mag_iters / K,
-            "arithmetic": "fast" if desc.arithmetic == 0 else "strict"}
+            "arithmetic": "fast" if desc.arithmetic == 0 else "strict", "secondary": secondary}
     print(json.dumps(line))
+
+
+def secondary_configs(lib, dev, hbm_peak):
+    """Device-resident throughput of the other BASELINE.json configurations and of the published benchmark's
+    flux, same timing method as the headline (CUDA events around one amx_integrate call after a warm-up call);
+    frac = cell-updates/s x SURVEY 8d's algorithmic bytes per cell-update / measured HBM bandwidth."""
+    import ctypes as C
+    import torch
+    from astronomix_b200 import _lib, option_classes as oc, problems as pr
+
+    out = {}
+
+    def run(key, name, state, config, params, steps, warm, alg_bytes, published=None):
+        params = params._replace(t_end=1.0e9)
+        s0 = torch.from_numpy(state).to(dev) if isinstance(state, np.ndarray) else state
+        desc = _lib.make_desc(config, params, tuple(s0.shape[1:]), _lib.AMX_F32)
+        nbytes = C.c_size_t()
+        _lib.check(lib.amx_workspace_bytes(C.byref(desc), C.byref(nbytes)))
+        ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = C.c_void_p((ws.data_ptr() + 255) & ~255)
+        s1, s2 = torch.empty_like(s0), torch.empty_like(s0)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stats = _lib.AmxStats()
+
+        def integ(a, b, k):
+            _lib.check(lib.amx_integrate(C.byref(desc), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), 1.0e9, k,
+                                         ws_ptr, stream, C.byref(stats)))
+        integ(s0, s1, warm)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        integ(s1, s2, steps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        cells = int(np.prod(s0.shape[1:]))
+        it = stats.magnetic_iterations / steps
+        v = cells * steps / (ms * 1e-3)
+        b = alg_bytes(it)
+        out[key] = {"workload": name, "value": v, "unit": UNIT, "steps": steps, "ms_per_step": ms / steps,
+                    "magnetic_iterations_per_step": it, "algorithmic_bytes_per_cell_update": b,
+                    "frac_of_hbm": v * b / 1e9 / hbm_peak}
+        if published:
+            out[key]["published"] = published
+        del ws, s0, s1, s2
+        torch.cuda.empty_cache()
+
+    w = 4
+    c, p, rv = pr.make(1, 101, boundaries="open", riemann_solver=oc.HLLC)
+    run("C1_sod_101", "C1 Sod 101 cells, HLLC, open (launch-bound)", pr.sod(101, np.float32), c, p, 200, 20,
+        lambda it: 5 * 3 * w)
+    c, p, rv = pr.make(2, 1024, riemann_solver=oc.HLLC)
+    run("C2_kelvin_helmholtz_1024", "C2 Kelvin-Helmholtz 1024^2 hydro, HLLC, RK2 (state 16 MB: L2-resident)",
+        pr.kelvin_helmholtz(1024, np.float32), c, p, 100, 10, lambda it: 5 * 4 * w)
+    c, p, rv = pr.make(2, 2048, mhd=True, box=2 * np.pi)
+    run("C3_orszag_tang_2048", "C3 Orszag-Tang 2048^2 MHD (Pang-Wu), HLL, RK2 (state 117 MB: about L2 size)",
+        pr.orszag_tang(2048, np.float32), c, p, 40, 5, lambda it: (10 * 4 + 13 + 19 * it) * w)
+    # the published benchmark (BASELINE.md: 2.97e8 cell-updates/s at 256^3, 3.11e8 at 512^3 on H200, jax):
+    # arena/fv_mhd.py:36-49 -- LAX_FRIEDRICHS, PERIODIC_ROLL, C_cfl 0.8 (limiter here: minmod)
+    for nn, pub in ((256, 2.97e8),):
+        c, p, rv = pr.make(3, nn, mhd=True, riemann_solver=oc.LAX_FRIEDRICHS, boundary_handling=oc.PERIODIC_ROLL)
+        p = p._replace(C_cfl=0.8)
+        run(f"published_flux_lf_{nn}", f"3-D MHD blast {nn}^3, LAX_FRIEDRICHS + PERIODIC_ROLL + C_cfl 0.8 (the flux of "
+            "the reference's published fv_mhd benchmark), minmod",
+            pr.mhd_blast3d(nn, np.float32, p_in=100.0, p_out=1.0, B0=10.0, r_inj=0.125), c, p, 10, 3,
+            lambda it: (10 * 5 + 13 + 19 * it) * w,
+            published={"value": pub, "unit": UNIT, "hardware": "H200, jax (BASELINE.md)", "note": "other hardware"})
+    c, p, rv = pr.make(3, 256, mhd=True, split=oc.SPLIT, time_integrator=oc.MUSCL)
+    run("C4_split_muscl_256", "C4 variant: 3-D MHD blast 256^3, Strang-split MUSCL-Hancock sweeps",
+        pr.mhd_blast3d(256, np.float32), c, p, 5, 2, lambda it: (2 * 5 * 2 * 5 + 13 + 19 * it) * w)
+    # single-GPU point of the north-star weak series (N > 1 runs 512^3 cells per GPU)
+    c, p, rv = pr.make(3, 512, mhd=True)
+    s512 = torch.empty((8, 512, 512, 512), dtype=torch.float32, device=dev)
+    blast_on_device(s512, 512)
+    run("weak_series_512_per_gpu", "3-D MHD blast 512^3 on one GPU (N = 1 point of the 512^3-per-GPU weak series)",
+        s512, c, p, 5, 2, lambda it: (10 * 5 + 13 + 19 * it) * w)
+    return out
+
+
+def blast_on_device(s, n, p_in=1000.0, p_out=0.1, r_inj=0.1):
+    """problems.mhd_blast3d(n) built on the device (512^3 is 4.3 GB: not worth a host array)."""
+    import torch
+    B0 = 100 / np.sqrt(4 * np.pi)
+    c = (torch.arange(n, device=s.device, dtype=torch.float64) + 0.5) / n - 0.5
+    c2 = c * c
+    r2 = c2[:, None, None] + c2[None, :, None] + c2[None, None, :]
+    s[0].fill_(1.0)
+    s[1:4].zero_()
+    s[4].copy_(torch.where(r2 < r_inj ** 2, p_in, p_out))
+    del r2
+    theta, phi = np.pi / 2, np.pi / 4
+    s[5].fill_(float(B0 * np.sin(theta) * np.cos(phi)))
+    s[6].fill_(float(B0 * np.sin(theta) * np.sin(phi)))
+    s[7].fill_(float(B0 * np.cos(theta)))
 
 
 def main():
@@ -355,6 +508,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cells", type=int, default=N_CELLS, help="cells per axis per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

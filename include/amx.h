@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AMX_ABI_VERSION 2
+#define AMX_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define AMX_API __attribute__((visibility("default")))
@@ -83,7 +83,16 @@ typedef struct amx_desc {
   int32_t exact_end_time;     /* config.exact_end_time */
   int32_t use_max_adaptive_timestep; /* config.use_max_adaptive_timestep (split CFL only, Q3) */
   int32_t arithmetic;         /* AMX_ARITH_* */
-  int32_t reserved[8];
+  /* Slab ranks (AMX_BC_HALO on axis 0) whose arrays live in peer-mapped memory with the same layout on
+   * every rank: the kernels that write an array also store its two first / last active x planes into the
+   * right / left ghost planes of the lower / upper neighbour's copy of that array, at
+   * (char*)own_pointer + peer_delta_{lo,hi} (P2P stores over NVLink, overlapped with the rest of the
+   * launch), so that a halo exchange is only a barrier.  peer_flags: bit 0 = lower neighbour, bit 1 =
+   * upper neighbour; 0 = off.  amx_peer_push_supported() tells which stage entry points honour it. */
+  int32_t peer_flags;
+  int32_t reserved0;
+  int64_t peer_delta_lo, peer_delta_hi;
+  int32_t reserved[2];
   double dx;                  /* config.grid_spacing */
   double gamma, C_cfl, dt_max;/* params.* (rounded to dtype on entry, Q20) */
   double fp_tol;              /* 1e-5 / 1e-10 from config.numerical_precision (Q6) */
@@ -242,6 +251,22 @@ AMX_API int amx_magnetic_fix_guarded(const amx_desc* d, const void* B0, const vo
 /* host look at the loop state (synchronises `stream`): still iterating?, while-body iterations so far */
 AMX_API int amx_magnetic_state(const amx_desc* d, void* ws, void* stream, int32_t* active_out,
                       int32_t* iterations_out);
+
+/* ---- peer-memory plumbing of a slab run (one process per GPU, arrays in peer-mapped memory) ----
+ * Which stage entry points honour amx_desc::peer_* for this descriptor (the kernels that would run):
+ * bit 0 amx_hydro_stage, bit 1 amx_magnetic_iter* / _pair_guarded / _fix_guarded, bit 2
+ * amx_magnetic_final*.  A caller still exchanges the halos of arrays written by the others itself. */
+AMX_API int amx_peer_push_supported(const amx_desc* d);
+/* MAX all-reduce of `count` <= 8 values of `dtype` (in place, device memory) over the ranks of the run
+ * through peer memory: replaces the NCCL all_reduce of the wave bounds (_timestep_estimator.py:118-128 on
+ * a decomposed grid) and of the fixed-point change norms (_magnetic_field_update.py:127-141); count = 0
+ * is a barrier (it closes a halo exchange made of in-kernel stores).  One launch, no host round trip.
+ * `comm_bufs[r]` = this process's mapping of rank r's communication buffer (amx_peer_comm_bytes() bytes,
+ * zeroed once before the first call, same buffer for every call); every rank must make the same
+ * sequence of calls.  max is order-independent: results are bitwise equal on all ranks. */
+AMX_API size_t amx_peer_comm_bytes(void);
+AMX_API int amx_peer_allreduce_max(void* const* comm_bufs, int rank, int world, void* vals_inout, int count,
+                      int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 ok = True
 for dim, n, mhd, rs, steps in [(3, 64, True, oc.HLL, 6), (2, 512, True, oc.HLL, 6), (3, 64, False, oc.HLLC, 6),
-                               (3, 64, True, oc.LAX_FRIEDRICHS, 4)]:
+                               (3, 64, True, oc.LAX_FRIEDRICHS, 4), (3, 64, True, oc.HLLC_LM, 3)]:
     s = pr.smooth_random(dim, n, mhd=mhd, seed=3, dtype=np.float32)
     config, params, rv = pr.make(dim, n, mhd=mhd, riemann_solver=rs)
     drv = SlabDriver(config, params, rv, (n,) * dim, torch.float32, dev, arithmetic=_lib.AMX_ARITH_STRICT)
@@ -36,6 +36,22 @@ for dim, n, mhd, rs, steps in [(3, 64, True, oc.HLL, 6), (2, 512, True, oc.HLL, 
               f"fixed-point iterations {info.magnetic_iterations} vs {ti.last_info.magnetic_iterations}; "
               f"max|diff| = {np.abs(out - ref).max():.3e}", flush=True)
     dist.barrier()
+# FAST arithmetic (the bench's), the 3-D MHD blast, through the public entry point with sharding=
+import astronomix_b200 as ax  # noqa: E402
+n = int(os.environ.get("AMX_CHECK_N", "128"))
+s = pr.mhd_blast3d(n, np.float32)
+config, params, rv = pr.make(3, n, mhd=True)
+params = params._replace(t_end=2.0e-3)
+out = ax.time_integration(s, config, params, rv, sharding=ax.SlabSharding())
+steps_n, iters_n = ti.last_info.steps, ti.last_info.magnetic_iterations
+if rank == 0:
+    ref = ax.time_integration(s, config, params, rv)
+    same = np.array_equal(out, ref) and (steps_n, iters_n) == (ti.last_info.steps, ti.last_info.magnetic_iterations)
+    ok &= same
+    print(f"time_integration(sharding=SlabSharding()), FAST, blast {n}^3 to t=2e-3: {dist.get_world_size()}-GPU == "
+          f"1-GPU bitwise: {same}; steps {steps_n} vs {ti.last_info.steps}, fixed-point iterations {iters_n} vs "
+          f"{ti.last_info.magnetic_iterations}", flush=True)
+dist.barrier()
 if rank == 0:
     print("SLAB_CHECK", "PASS" if ok else "FAIL")
 dist.destroy_process_group()
