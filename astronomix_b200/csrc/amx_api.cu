@@ -1416,6 +1416,7 @@ int amx_magnetic_final(const amx_desc* d, void* gas_inout, const void* bv_final,
   a.gas_out = a.gas; a.skip_if_emitted = 0; a.final_runs = nullptr;
   a.X[0] = X[0]; a.X[1] = X[1]; a.ctl_ro = nullptr; a.fixed_final = 0;
   a.alpha_slots = alpha_out ? E.aslots() : nullptr;
+  a.peers = E.peers;
   CK(E.strict ? amx_strict::launch_mag_final(a, E.st) : amx_fast::launch_mag_final(a, E.st));
   if (alpha_out) CK(E.finalize_alpha(alpha_out, false));
   return AMX_OK;
@@ -1465,6 +1466,7 @@ int amx_magnetic_final_guarded(const amx_desc* d, const void* gas_in, void* gas_
   a.gas_out = E.user_internal(gas_out); a.skip_if_emitted = 1; a.final_runs = nullptr;
   a.X[0] = E.user_internal(bv0); a.X[1] = E.user_internal(bv1); a.ctl_ro = E.ctl; a.fixed_final = -1;
   a.alpha_slots = alpha_out ? E.aslots() : nullptr;
+  a.peers = E.peers;
   CK(E.strict ? amx_strict::launch_mag_final(a, E.st) : amx_fast::launch_mag_final(a, E.st));
   if (alpha_out) CK(E.finalize_alpha(alpha_out, false));
   return AMX_OK;

@@ -48,8 +48,8 @@ __host__ __device__ inline T jet_vector_value(int type_handled, int comp) {  // 
 // x of an output array repeats the store into the neighbour's copy of the array, plane x + n of the lower
 // neighbour (its right ghost planes) for x < 2 and plane x - n of the upper neighbour for x >= n - 2.
 struct Peers {
-  long long lo, hi;  // byte deltas from an own pointer to the same element of the neighbour's array
-  int flags;         // bit 0: lower neighbour, bit 1: upper neighbour
+  long long lo = 0, hi = 0;  // byte deltas from an own pointer to the same element of the neighbour's array
+  int flags = 0;             // bit 0: lower neighbour, bit 1: upper neighbour
 };
 // element offset (in units of the x stride) and byte delta of the extra store for plane x, or false
 __host__ __device__ inline bool peer_target(const Peers& P, int x, int n, int k, long long& byte_delta, int& plane_shift) {

@@ -292,6 +292,7 @@ class SlabDriver:
         import os
         # AMX_SLAB_PACK=0: per-row messages without staging copies (A/B switch, see exchange)
         self.pack_halos = os.environ.get("AMX_SLAB_PACK", "1") != "0"
+        self._verify_push = os.environ.get("AMX_SLAB_PUSH_VERIFY", "0") == "1"
         # two fixed-point evaluations per launch where the kernel supports the problem (AMX_SLAB_PAIRS=0: off)
         self.pair_greedy = False  # tests: pair launches regardless of the expected count (exercises the re-run)
         # The pair kernel computes the intermediate iterate on ghost planes -1 / n with the stencil; that is
@@ -341,6 +342,27 @@ class SlabDriver:
         self._sync_seq += 1
         return True
 
+    def _check_pushed(self, t, left, right, send_l, send_r):
+        """AMX_SLAB_PUSH_VERIFY=1 (diagnostic): the ghost planes the neighbours' kernels stored here must equal
+        the neighbours' edge planes read back through the peer mapping."""
+        self._barrier()
+        base, h = self._symm[0]
+        off_e = (t.data_ptr() - base.data_ptr()) // base.element_size()
+        n = self.nxl
+
+        def peer(rank):
+            return h.get_buffer(rank, tuple(base.shape), base.dtype)[off_e:off_e + t.numel()].view(t.shape)
+
+        bad = []
+        if send_l and not torch.equal(t[:, :NG], peer(left)[:, n:n + NG]):
+            bad.append(("left ghosts", float((t[:, :NG] - peer(left)[:, n:n + NG]).abs().max())))
+        if send_r and not torch.equal(t[:, n + NG:], peer(right)[:, NG:2 * NG]):
+            bad.append(("right ghosts", float((t[:, n + NG:] - peer(right)[:, NG:2 * NG]).abs().max())))
+        name = {self.A.data_ptr(): "A", self.G.data_ptr(): "G"}.get(t.data_ptr(), f"rows={t.shape[0]}")
+        print(f"[slab push verify] rank {self.rank} array {name} rows {t.shape[0]} seq {self._sync_seq}: "
+              f"{'OK' if not bad else bad}", flush=True)
+        self._barrier()
+
     def _allreduce_max(self, t):
         if self.world > 1:
             if self._comm is not None:  # one kernel through peer memory instead of an NCCL launch
@@ -384,6 +406,8 @@ class SlabDriver:
                 # complete once every rank has passed a collective enqueued after its producer
                 if seq == self._sync_seq:
                     self._barrier()
+                if self._verify_push:
+                    self._check_pushed(t, left, right, send_l, send_r)
                 send_l = send_r = False
             elif self.p2p and self._exchange_p2p(t, left, right, send_l, send_r):
                 send_l = send_r = False  # done
