@@ -1,0 +1,129 @@
+// amx_rng.cu -- jax's default PRNG on the device, for the turbulent driving: the reference
+// draws raw_noise = normal(sk1, (3, n, n, n)) + 1j * normal(sk2, (3, n, n, n)) every step from keys split off
+// jax.random.key(42) (_turbulent_forcing.py:48-51, time_integration.py:787-789).  Threefry-2x32-20 block
+// function, jax's two counter layouts (threefry_partitionable on / off), bits -> uniform in
+// [nextafter(-1, 0), 1) -> sqrt(2) * erf_inv (fp32: XLA's ErfInv32 = Giles' polynomial; fp64: erfinv()).
+// oracle/threefry.py is the NumPy restatement the tests compare with (bit-exact for the bits and the uniforms).
+#include "../../include/amx.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+__device__ __forceinline__ uint32_t rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  x0 += ks[0];
+  x1 += ks[1];
+#pragma unroll
+  for (int blk = 0; blk < 5; ++blk) {
+    const int r0 = (blk & 1) ? 17 : 13, r1 = (blk & 1) ? 29 : 15, r2 = (blk & 1) ? 16 : 26, r3 = (blk & 1) ? 24 : 6;
+    x0 += x1; x1 = rotl(x1, r0); x1 ^= x0;
+    x0 += x1; x1 = rotl(x1, r1); x1 ^= x0;
+    x0 += x1; x1 = rotl(x1, r2); x1 ^= x0;
+    x0 += x1; x1 = rotl(x1, r3); x1 ^= x0;
+    x0 += ks[(blk + 1) % 3];
+    x1 += ks[(blk + 2) % 3] + (uint32_t)(blk + 1);
+  }
+}
+
+__device__ __forceinline__ float erfinv32(float x) {  // xla/client/lib/math.cc ErfInv32
+  float w = -log1pf(-(x * x));
+  float p;
+  if (w < 5.0f) {
+    w = w - 2.5f;
+    p = 2.81022636e-08f;
+    p = 3.43273939e-07f + p * w;
+    p = -3.5233877e-06f + p * w;
+    p = -4.39150654e-06f + p * w;
+    p = 0.00021858087f + p * w;
+    p = -0.00125372503f + p * w;
+    p = -0.00417768164f + p * w;
+    p = 0.246640727f + p * w;
+    p = 1.50140941f + p * w;
+  } else {
+    w = sqrtf(w) - 3.0f;
+    p = -0.000200214257f;
+    p = 0.000100950558f + p * w;
+    p = 0.00134934322f + p * w;
+    p = -0.00367342844f + p * w;
+    p = 0.00573950773f + p * w;
+    p = -0.0076224613f + p * w;
+    p = 0.00943887047f + p * w;
+    p = 1.00167406f + p * w;
+    p = 2.83297682f + p * w;
+  }
+  return fabsf(x) == 1.0f ? copysignf(INFINITY, x) : p * x;
+}
+
+__device__ __forceinline__ float normal_from_bits(uint32_t bits) {
+  const float u01 = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  const float lo = -0.99999994f;  // nextafter(-1, 0)
+  const float u = fmaxf(lo, __fadd_rn(__fmul_rn(u01, __fsub_rn(1.0f, lo)), lo));
+  return __fmul_rn(1.41421354f, erfinv32(u));
+}
+__device__ __forceinline__ double normal_from_bits(uint64_t bits) {
+  const double u01 = __longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ull)) - 1.0;
+  const double lo = -0.99999999999999989;  // nextafter(-1, 0)
+  const double u = fmax(lo, __dadd_rn(__dmul_rn(u01, __dsub_rn(1.0, lo)), lo));
+  return 1.4142135623730951 * erfinv(u);
+}
+
+// partitionable layout: sample i <- block(counter = (i >> 32, i)); fp32 bits = out0 ^ out1, fp64 bits = out0:out1
+template <typename T>
+__global__ void normal_partitionable(uint32_t k0, uint32_t k1, long long n, T* out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t x0 = (uint32_t)((unsigned long long)i >> 32), x1 = (uint32_t)i;
+    threefry2x32(k0, k1, x0, x1);
+    if constexpr (sizeof(T) == 4) out[i] = normal_from_bits(x0 ^ x1);
+    else out[i] = normal_from_bits(((uint64_t)x0 << 32) | x1);
+  }
+}
+
+// original layout: the 32-bit words w[j], j < W (W = n words for fp32, 2n for fp64, padded to even), come from
+// blocks b < W/2 with counter (b, b + W/2): w[b] = out0, w[b + W/2] = out1; fp64 sample i = w[i] : w[i + n]
+__global__ void normal_original_f32(uint32_t k0, uint32_t k1, long long n, float* out) {
+  const long long half = (n + 1) / 2;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < half; b += (long long)gridDim.x * blockDim.x) {
+    uint32_t x0 = (uint32_t)b, x1 = (uint32_t)(b + half);
+    if ((n & 1) && b + half == n) x1 = 0u;  // the padding word of an odd count is a zero counter
+    threefry2x32(k0, k1, x0, x1);
+    out[b] = normal_from_bits(x0);
+    if (b + half < n) out[b + half] = normal_from_bits(x1);
+  }
+}
+__global__ void normal_original_f64(uint32_t k0, uint32_t k1, long long n, double* out) {
+  // W = 2n words (even): block b < n gives w[b] (high word of sample b) and w[b + n] (low word of sample b)
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += (long long)gridDim.x * blockDim.x) {
+    uint32_t x0 = (uint32_t)b, x1 = (uint32_t)(b + n);
+    threefry2x32(k0, k1, x0, x1);
+    out[b] = normal_from_bits(((uint64_t)x0 << 32) | x1);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int amx_threefry_normal(uint32_t key0, uint32_t key1, int64_t count, void* out, int dtype, int partitionable,
+                        void* stream) {
+  if (count < 0 || (count > 0 && !out) || (dtype != AMX_F32 && dtype != AMX_F64)) return AMX_EINVAL;
+  if (!partitionable && count * (dtype == AMX_F64 ? 2 : 1) > 0xFFFFFFFFll) return AMX_EUNSUPPORTED;  // 32-bit iota
+  if (count == 0) return AMX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  const long long work = partitionable || dtype == AMX_F64 ? count : (count + 1) / 2;
+  const unsigned blocks = (unsigned)((work + threads - 1) / threads < 148ll * 16 ? (work + threads - 1) / threads : 148ll * 16);
+  if (partitionable) {
+    if (dtype == AMX_F32) normal_partitionable<float><<<blocks, threads, 0, st>>>(key0, key1, count, static_cast<float*>(out));
+    else normal_partitionable<double><<<blocks, threads, 0, st>>>(key0, key1, count, static_cast<double*>(out));
+  } else {
+    if (dtype == AMX_F32) normal_original_f32<<<blocks, threads, 0, st>>>(key0, key1, count, static_cast<float*>(out));
+    else normal_original_f64<<<blocks, threads, 0, st>>>(key0, key1, count, static_cast<double*>(out));
+  }
+  return cudaGetLastError() == cudaSuccess ? AMX_OK : AMX_ECUDA;
+}
+
+}  // extern "C"

@@ -8,10 +8,13 @@ out, three inverse FFTs (cuFFT through torch.fft: library plumbing, the finite-v
 libamx), and an amplitude that injects ``energy_injection_rate * dt`` of kinetic energy (the root of
 a quadratic in two global sums).
 
-The random stream is torch's (``torch.Generator`` seeded with 42, the number the reference seeds
-``jax.random.key`` with): the fields have the reference's statistics, not its bits -- jax is not
-installable here, so its Threefry / erfinv stream cannot be pinned.  The arithmetic after the noise
-is restated in the test oracle (``forcing_field``, ``apply_forcing``) and compared on identical noise.
+The random stream is jax's default PRNG restated (astronomix_b200/threefry.py, libamx amx_threefry_normal):
+the loop carries ``jax.random.key(42)``, every forced step splits it in three and draws the real and the
+imaginary part of the noise from the second and third key, as _turbulent_forcing.py:48-51 does.  Threefry is
+pinned to its published known-answer vectors and the layers above it to values the jax documentation prints
+(tests/test_threefry.py); jax itself cannot be run here, so the bits are not compared against a jax run.  The
+arithmetic after the noise is restated in the test oracle (``forcing_field``, ``apply_forcing``) and compared
+both on the reference's recorded noise and on this stream.
 """
 from __future__ import annotations
 
@@ -26,16 +29,19 @@ from . import option_classes as oc
 
 
 class ForcingNoise:
-    """(3, n, n, n) complex standard-normal noise per step: real and imaginary part drawn separately"""
+    """(3, n, n, n) complex standard-normal noise per step: ``key, sk1, sk2 = split(key, 3)``, real part from
+    sk1, imaginary part from sk2 (_turbulent_forcing.py:48-51); the carried key starts as key(42)."""
 
     def __init__(self, n, dtype, device, seed=42):
+        from . import threefry
+        self.tf = threefry
         self.shape, self.dtype, self.device = (3, n, n, n), dtype, device
-        self.gen = torch.Generator(device=device)
-        self.gen.manual_seed(seed)
+        self.key = threefry.key(seed)
 
     def __call__(self, step):
-        re = torch.randn(self.shape, dtype=self.dtype, device=self.device, generator=self.gen)
-        im = torch.randn(self.shape, dtype=self.dtype, device=self.device, generator=self.gen)
+        self.key, sk1, sk2 = self.tf.split(self.key, 3)
+        re = self.tf.normal(sk1, self.shape, self.dtype, self.device)
+        im = self.tf.normal(sk2, self.shape, self.dtype, self.device)
         return torch.complex(re, im)
 
 
@@ -93,7 +99,7 @@ def integrate_per_step(t, kind, config, params, registered_variables, snapshot_c
     for the loop condition."""
     from .snapshots import Diagnostics, SnapshotData
     if config.use_specific_snapshot_timepoints:
-        raise NotImplementedError("use_specific_snapshot_timepoints is not built")
+        raise NotImplementedError("use_specific_snapshot_timepoints together with turbulent forcing is not built")
     lib = _lib.load()
     tdt = t.dtype
     npdt = np.float32 if tdt == torch.float32 else np.float64

@@ -96,8 +96,6 @@ class Diagnostics:
 
 def integrate_with_snapshots(t, kind, config, params, registered_variables, snapshot_callable, from_device):
     """The snapshot / callback variants of time_integration on the device tensor ``t`` (unpadded)."""
-    if config.use_specific_snapshot_timepoints:
-        raise NotImplementedError("use_specific_snapshot_timepoints is not built")
     if config.snapshot_settings.return_gravitational_energy and config.self_gravity:
         raise NotImplementedError("self-gravity is outside the finite-volume hot path")
     lib = _lib.load()
@@ -126,18 +124,52 @@ def integrate_with_snapshots(t, kind, config, params, registered_variables, snap
     states = torch.zeros((N,) + tuple(t.shape), dtype=tdt, device=t.device) if snaps and st.return_states else None
     t_end = npdt(params.t_end)
     time, cp, iters, launches, mag_iters = npdt(0.0), 0, 0, 0, 0
-    while time < t_end:
+
+    def take(cp):
+        if snaps and cp < N:
+            time_points[cp] = time
+            if states is not None:
+                states[cp].copy_(cur)
+            for k in series:
+                series[k][cp] = getattr(diag, k)(cur)
+        elif not snaps:
+            snapshot_callable(float(time), cur, registered_variables)
+        return cp + 1
+
+    if config.use_specific_snapshot_timepoints and snaps:
+        # time_integration.py:542-554, :671-678, :742-750: a snapshot at the start of a step when
+        # |time - snapshot_timepoints[cp]| < 1e-12, dt clipped to snapshot_timepoints[cp] - time INSTEAD of
+        # t_end - time (the index is clamped to the last entry, as jax clamps it), and one more snapshot after
+        # the step that reaches t_end.  A segment up to the next time point is one call of the device-resident
+        # loop with that point as the time the last dt is clipped to.
+        tps = np.asarray(params.snapshot_timepoints, dtype=npdt).reshape(-1)
+        desc_tp = _lib.make_desc(config._replace(exact_end_time=True), params, t.shape[1:],
+                                 _lib.AMX_F32 if tdt == torch.float32 else _lib.AMX_F64)
+        while time < t_end:
+            target = tps[min(cp, len(tps) - 1)]
+            if abs(time - target) < 1e-12:
+                cp = take(cp)
+                target = tps[min(cp, len(tps) - 1)]
+            if not target > time:
+                raise ValueError("snapshot_timepoints must increase and end at t_end (the reference's loop would "
+                                 "not advance: dt = snapshot_timepoints[current_checkpoint] - time <= 0)")
+            with torch.cuda.device(t.device):
+                _lib.check(lib.amx_integrate_from(C.byref(desc_tp), C.c_void_p(cur.data_ptr()),
+                                                  C.c_void_p(nxt.data_ptr()), float(time), float("inf"),
+                                                  float(target), -1, ws_ptr, stream, C.byref(stats)))
+            if stats.steps == 0:
+                raise RuntimeError("time integration made no progress")
+            cur, nxt = nxt, cur
+            time = npdt(stats.time)
+            iters += stats.steps
+            launches += stats.kernel_launches
+            mag_iters += stats.magnetic_iterations
+            if abs(time - t_end) < 1e-12:
+                cp = take(cp)
+    while time < t_end and not (config.use_specific_snapshot_timepoints and snaps):
         thr = npdt(npdt(cp) * t_end) / npdt(N)  # cp * t_end / num_snapshots in the working dtype
         if time >= thr:
-            if snaps and cp < N:
-                time_points[cp] = time
-                if states is not None:
-                    states[cp].copy_(cur)
-                for k in series:
-                    series[k][cp] = getattr(diag, k)(cur)
-            elif not snaps:
-                snapshot_callable(float(time), cur, registered_variables)
-            cp += 1
+            cp = take(cp)
             thr = npdt(npdt(cp) * t_end) / npdt(N)
         # The next test of the snapshot condition is at the start of the NEXT step: one step runs in any
         # case.  Usually time < thr and a single call steps until thr has been passed (or t_end is

@@ -268,6 +268,15 @@ AMX_API size_t amx_peer_comm_bytes(void);
 AMX_API int amx_peer_allreduce_max(void* const* comm_bufs, int rank, int world, void* vals_inout, int count,
                       int dtype, void* stream);
 
+/* ---- jax's default PRNG on the device (turbulent driving) ----
+ * jax.random.normal(key, shape) for a raw Threefry key (key0, key1) = jax.random.key_data(key): `count` =
+ * prod(shape) samples of `dtype` written to `out` (device) in C order.  partitionable = 1: jax >= 0.5's
+ * default counter layout (jax_threefry_partitionable), 0: the older default.  Replaces the two draws of
+ * _physics_modules/_turbulent_forcing/_turbulent_forcing.py:50-51; key handling (key(42), split) is host-side
+ * integer work (astronomix_b200/threefry.py). */
+AMX_API int amx_threefry_normal(uint32_t key0, uint32_t key1, int64_t count, void* out, int dtype,
+                      int partitionable, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -791,9 +791,12 @@ def total_quantities(s, o, box_size, gamma, centers=None):
     return {k: t(v) for k, v in q.items()}
 
 
-def time_integration_snapshots(s0, o, num_snapshots, box_size=1.0, centers=None):
+def time_integration_snapshots(s0, o, num_snapshots, box_size=1.0, centers=None, timepoints=None):
     """time_integration.py:397-570, :628-737: the adaptive loop with a snapshot at the START of every
     step whose time has reached ``current_checkpoint * t_end / num_snapshots`` (one per step at most).
+    ``timepoints`` (use_specific_snapshot_timepoints, :542-554, :671-678, :742-750): a snapshot when
+    |time - timepoints[cp]| < 1e-12 at the start of a step, dt clipped to timepoints[cp] - time instead of
+    t_end - time (jax clamps the index cp to the last entry), and one more after the step that reaches t_end.
     Returns (final unpadded state, dict of time_points / states / totals, number of steps)."""
     t_ = s0.dtype.type
     gamma, C_cfl, dt_max, t_end = t_(o.gamma), t_(o.C_cfl), t_(o.dt_max), t_(o.t_end)
@@ -801,21 +804,35 @@ def time_integration_snapshots(s0, o, num_snapshots, box_size=1.0, centers=None)
     time, cp, steps = t_(0.0), 0, 0
     rec = {"time_points": np.zeros(num_snapshots, dtype=s0.dtype), "states": np.zeros((num_snapshots,) + s0.shape,
                                                                                     dtype=s0.dtype)}
+    tps = None if timepoints is None else np.asarray(timepoints, dtype=s0.dtype)
+
+    def take(cp):
+        if cp < num_snapshots:  # (.at[].set past the end is dropped)
+            u = unpad(s, o) if o.boundary_handling == GHOST_CELLS else s
+            rec["time_points"][cp] = time
+            rec["states"][cp] = u
+            for k, v in total_quantities(u, o, box_size, gamma, centers).items():
+                rec.setdefault(k, np.zeros(num_snapshots, dtype=s0.dtype))[cp] = v
+        return cp + 1
+
     while time < t_end:
-        if time >= t_(t_(cp) * t_end) / t_(num_snapshots):
-            if cp < num_snapshots:
-                u = unpad(s, o) if o.boundary_handling == GHOST_CELLS else s
-                rec["time_points"][cp] = time
-                rec["states"][cp] = u
-                for k, v in total_quantities(u, o, box_size, gamma, centers).items():
-                    rec.setdefault(k, np.zeros(num_snapshots, dtype=s0.dtype))[cp] = v
-            cp += 1
+        if tps is not None:
+            if abs(time - tps[min(cp, len(tps) - 1)]) < 1e-12:
+                cp = take(cp)
+        elif time >= t_(t_(cp) * t_end) / t_(num_snapshots):
+            cp = take(cp)
         dt = t_(cfl_time_step(s, o, gamma, C_cfl, dt_max))
-        if o.exact_end_time:
+        if tps is not None:
+            dt = min(dt, t_(tps[min(cp, len(tps) - 1)] - time))
+            if not dt > 0:
+                raise RuntimeError("snapshot_timepoints must increase and end at t_end (the reference would spin on dt = 0)")
+        elif o.exact_end_time:
             dt = min(dt, t_end - time)
         s = evolve_state_fv(s, dt, gamma, o)
         time = t_(time + dt)
         steps += 1
+        if tps is not None and abs(time - t_end) < 1e-12:
+            cp = take(cp)
     out = unpad(s, o) if o.boundary_handling == GHOST_CELLS else s
     rec["current_checkpoint"] = cp
     return out, rec, steps

@@ -36,6 +36,12 @@ SNAP_CASES = [
     ("snap_mhd3d_f32", 3, 16, True, "f32", 0.03, 4, 2, 6),
     ("snap_mhd3d_reflective_f64", 3, 12, True, "f64", 0.06, 4, 1, 110),
 ]
+SNAPTP_CASES = [
+    # use_specific_snapshot_timepoints: name, dim, n, mhd, dtype, time points (last = t_end), boundary code, seed
+    ("snaptp_mhd3d_f64", 3, 16, True, "f64", [0.0, 0.01, 0.017, 0.03], 2, 5),
+    ("snaptp_hydro2d_f32", 2, 32, False, "f32", [0.0, 0.013, 0.04], 2, 5),
+    ("snaptp_mhd2d_f64_late_start", 2, 32, True, "f64", [0.004, 0.02, 0.05], 2, 7),
+]
 FORCED_CASES = [
     # name, n, dtype, t_end, seed
     ("forced_mhd3d_f64", 12, "f64", 0.025, 12),
@@ -52,7 +58,7 @@ def _params(sp, wd, t_end, **extra):
     return sp.SimulationParams(**pk)
 
 
-def run_snapshots(name, dim, n, mhd, dt, t_end, ns, bcode, seed):
+def run_snapshots(name, dim, n, mhd, dt, t_end, ns, bcode, seed, timepoints=None):
     from astronomix_b200 import problems as pr
     x64 = dt == "f64"
     wd = np.float64 if x64 else np.float32
@@ -69,10 +75,12 @@ def run_snapshots(name, dim, n, mhd, dt, t_end, ns, bcode, seed):
                              return_radial_momentum=dim > 1, return_magnetic_divergence=mhd and dim == 3)
     config = sc.SimulationConfig(progress_bar=False, dimensionality=dim, mhd=mhd, box_size=1.0, num_cells=n,
                                  boundary_settings=b1 if dim == 1 else sc.BoundarySettings(b1, b1, b1),
-                                 return_snapshots=True, num_snapshots=ns, snapshot_settings=st)
+                                 return_snapshots=True, num_snapshots=ns, snapshot_settings=st,
+                                 use_specific_snapshot_timepoints=timepoints is not None)
     regs = rv.get_registered_variables(config)
     config = sc.finalize_config(config, s0.shape)
-    out = ti.time_integration(jnp.array(s0), config, _params(sp, wd, t_end), regs)
+    extra = {} if timepoints is None else {"snapshot_timepoints": jnp.array(np.array(timepoints, dtype=wd))}
+    out = ti.time_integration(jnp.array(s0), config, _params(sp, wd, t_end, **extra), regs)
     rec = {"initial_state": s0, "final_state": np.asarray(out.final_state).view(np.ndarray),
            "num_iterations": np.int64(out.num_iterations), "current_checkpoint": np.int64(out.current_checkpoint)}
     for f in ("time_points", "states", "total_mass", "total_energy", "internal_energy", "kinetic_energy",
@@ -84,6 +92,8 @@ def run_snapshots(name, dim, n, mhd, dt, t_end, ns, bcode, seed):
         if isinstance(v, np.ndarray) and v.dtype.kind == "f":
             assert v.dtype == wd, (name, k, v.dtype)
     spec = dict(name=name, dim=dim, n=n, mhd=mhd, dtype=dt, t_end=t_end, num_snapshots=ns, boundary=bcode, box=1.0)
+    if timepoints is not None:
+        spec["snapshot_timepoints"] = [float(v) for v in timepoints]
     np.savez_compressed(os.path.join(OUT, name + ".npz"), spec=np.array(json.dumps(spec)), **rec)
     print(f"{name:32s} steps={int(out.num_iterations)} snapshots taken={int(out.current_checkpoint)}", flush=True)
 
@@ -136,12 +146,14 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     for c in SNAP_CASES:
         run_snapshots(*c)
+    for name, dim, n, mhd, dt, tps, bcode, seed in SNAPTP_CASES:
+        run_snapshots(name, dim, n, mhd, dt, tps[-1], len(tps), bcode, seed, timepoints=tps)
     for c in FORCED_CASES:
         run_forced(*c)
     with open(os.path.join(OUT, "INDEX.json"), "w") as f:
         json.dump({"generator": "oracle/gen_reference_aux_vectors.py",
                    "reference": "leo1200/astronomix v0.5.1 sources executed over oracle/jaxshim (NumPy backend)",
-                   "cases": [c[0] for c in SNAP_CASES + FORCED_CASES]}, f, indent=1)
+                   "cases": [c[0] for c in SNAP_CASES + SNAPTP_CASES + FORCED_CASES]}, f, indent=1)
 
 
 if __name__ == "__main__":

@@ -88,6 +88,8 @@ def check_cuda_vector(name):
 # noise is an input here, not something to reproduce).
 AUX_DIR = os.path.join(HERE, "golden", "reference_vectors_aux")
 SNAP_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(AUX_DIR, "snap_*.npz")))
+# use_specific_snapshot_timepoints (time_integration.py:542-554, :671-678, :742-750)
+SNAP_NAMES += sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(AUX_DIR, "snaptp_*.npz")))
 FORCED_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(AUX_DIR, "forced_*.npz")))
 SERIES = ("total_mass", "total_energy", "internal_energy", "kinetic_energy")
 
@@ -104,14 +106,18 @@ def build_snap(spec):
                              return_total_energy=True, return_internal_energy=True, return_kinetic_energy=True,
                              return_radial_momentum=dim > 1, return_magnetic_divergence=mhd and dim == 3)
     bnd = {0: "open", 1: "reflective", 2: "periodic"}[spec["boundary"]]
+    tps = spec.get("snapshot_timepoints")
     config, params, rv = pr.make(dim, spec["n"], mhd=mhd, dtype=dtype, boundaries=bnd, return_snapshots=True,
                                  num_snapshots=spec["num_snapshots"], snapshot_settings=st,
+                                 use_specific_snapshot_timepoints=tps is not None,
                                  numerical_precision=oc.SINGLE_PRECISION)  # the reference's default
+    if tps is not None:
+        params = params._replace(snapshot_timepoints=tuple(tps))
     return config, params._replace(t_end=spec["t_end"]), rv, dtype
 
 
 def test_aux_vectors_present():
-    assert len(SNAP_NAMES) >= 6 and len(FORCED_NAMES) >= 2
+    assert len(SNAP_NAMES) >= 9 and len(FORCED_NAMES) >= 2
 
 
 @pytest.mark.parametrize("name", SNAP_NAMES)
@@ -121,7 +127,8 @@ def test_oracle_reproduces_reference_snapshots(name):
     dim, mhd, ns = spec["dim"], spec["mhd"], spec["num_snapshots"]
     centers = ax.get_helper_data(config, dtype=dtype).geometric_centers if dim > 1 else None
     ref, rec, steps = fo.time_integration_snapshots(z["initial_state"], fo.Opts.from_config(config, params), ns,
-                                                    box_size=config.box_size, centers=centers)
+                                                    box_size=config.box_size, centers=centers,
+                                                    timepoints=spec.get("snapshot_timepoints"))
     tol = 1e-13 if dtype == np.float64 else 2e-6
     assert steps == int(z["num_iterations"]) and rec["current_checkpoint"] == int(z["current_checkpoint"])
     np.testing.assert_allclose(rec["time_points"], z["time_points"], rtol=tol, atol=0)

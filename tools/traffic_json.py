@@ -25,5 +25,6 @@ for r in data:
     acc[name].append(float(r[ri].replace(",", "")) * scale[ur] + float(r[wi].replace(",", "")) * scale[uw])
 res = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches_captured": len(v), "source": sys.argv[1]}
        for k, v in acc.items()}
+res["source"] = sys.argv[3] if len(sys.argv) > 3 else sys.argv[1]
 json.dump(res, open(sys.argv[2], "w"), indent=1)
 print(json.dumps(res, indent=1))
