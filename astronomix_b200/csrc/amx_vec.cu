@@ -565,7 +565,11 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
 #pragma unroll
   for (int k = 0; k < ND; ++k) alpha_lf[k] = RS == RS_LF ? F2(static_cast<const float*>(a.alpha_lf)[k]) : F2(0.f);
 
-  auto plane_map = [&](int p, bool& fx) { return map_index(p, g.n[0], g.bc[0][0], g.bc[0][1], fx); };
+  // (the ring is filled one plane further ahead than a segment needs: on a slab rank (BC_HALO) that plane would lie
+  // beyond the two resident ghost planes, possibly beyond the allocation, so it is clamped to the last ghost plane)
+  auto plane_map = [&](int p, bool& fx) {
+    return min(max(map_index(p, g.n[0], g.bc[0][0], g.bc[0][1], fx), -2), g.n[0] + 1);
+  };
   // conservative update of one variable: U + ((1/dx) * (Fl - Fr)) * dt (evolve_state.py:398-403)
 #if AMX_STRICT
   const F2 dt2 = F2(dts);
