@@ -109,6 +109,8 @@ PROTOTYPES = {
     "amx_magnetic_fix_guarded": (C.c_int, [_D, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
     "amx_magnetic_state": (C.c_int, [_D, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "amx_threefry_normal": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int64, _P, C.c_int, C.c_int, _P]),
+    "amx_threefry_normal_range": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int,
+                                            C.c_int, _P]),
     "amx_peer_push_supported": (C.c_int, [_D]),
     "amx_peer_comm_bytes": (C.c_size_t, []),
     "amx_peer_allreduce_max": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, _P, C.c_int, C.c_int, _P]),

@@ -103,6 +103,35 @@ __global__ void normal_original_f64(uint32_t k0, uint32_t k1, long long n, doubl
   }
 }
 
+// samples [offset, offset + count) of a draw of `total` samples, either layout (one block per sample): what a
+// slab rank needs of a global (3, n, n, n) draw
+template <typename T>
+__global__ void normal_range(uint32_t k0, uint32_t k1, long long total, long long offset, long long count, int partitionable,
+                             T* out) {
+  constexpr bool f64 = sizeof(T) == 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const long long j = offset + i;
+    if (partitionable) {
+      uint32_t x0 = (uint32_t)((unsigned long long)j >> 32), x1 = (uint32_t)j;
+      threefry2x32(k0, k1, x0, x1);
+      if constexpr (f64) out[i] = normal_from_bits(((uint64_t)x0 << 32) | x1);
+      else out[i] = normal_from_bits(x0 ^ x1);
+    } else if constexpr (f64) {
+      uint32_t x0 = (uint32_t)j, x1 = (uint32_t)(j + total);
+      threefry2x32(k0, k1, x0, x1);
+      out[i] = normal_from_bits(((uint64_t)x0 << 32) | x1);
+    } else {
+      const long long half = (total + 1) / 2;
+      const bool second = j >= half;
+      const long long b = second ? j - half : j;
+      uint32_t x0 = (uint32_t)b, x1 = (uint32_t)(b + half);
+      if ((total & 1) && b + half == total) x1 = 0u;
+      threefry2x32(k0, k1, x0, x1);
+      out[i] = normal_from_bits(second ? x1 : x0);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -123,6 +152,23 @@ int amx_threefry_normal(uint32_t key0, uint32_t key1, int64_t count, void* out, 
     if (dtype == AMX_F32) normal_original_f32<<<blocks, threads, 0, st>>>(key0, key1, count, static_cast<float*>(out));
     else normal_original_f64<<<blocks, threads, 0, st>>>(key0, key1, count, static_cast<double*>(out));
   }
+  return cudaGetLastError() == cudaSuccess ? AMX_OK : AMX_ECUDA;
+}
+
+int amx_threefry_normal_range(uint32_t key0, uint32_t key1, int64_t total, int64_t offset, int64_t count, void* out,
+                              int dtype, int partitionable, void* stream) {
+  if (total < 0 || offset < 0 || count < 0 || offset + count > total || (count > 0 && !out) ||
+      (dtype != AMX_F32 && dtype != AMX_F64))
+    return AMX_EINVAL;
+  if (!partitionable && total * (dtype == AMX_F64 ? 2 : 1) > 0xFFFFFFFFll) return AMX_EUNSUPPORTED;
+  if (count == 0) return AMX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((count + threads - 1) / threads < 148ll * 16 ? (count + threads - 1) / threads : 148ll * 16);
+  if (dtype == AMX_F32)
+    normal_range<float><<<blocks, threads, 0, st>>>(key0, key1, total, offset, count, partitionable, static_cast<float*>(out));
+  else
+    normal_range<double><<<blocks, threads, 0, st>>>(key0, key1, total, offset, count, partitionable, static_cast<double*>(out));
   return cudaGetLastError() == cudaSuccess ? AMX_OK : AMX_ECUDA;
 }
 

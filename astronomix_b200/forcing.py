@@ -91,6 +91,122 @@ class Forcing:
         return state
 
 
+class SlabForcing:
+    """The same driving on an x-slab decomposition (one process per GPU, astronomix_b200.slab): a rank owns
+    planes [x0, x0 + n/P) of the n^3 grid -- of the k-space arrays (k_x slab) as well as of the state.
+
+      noise      each rank draws its slab of the global (3, n, n, n) Threefry draws (amx_threefry_normal_range)
+      spectrum   shaping and solenoidal projection are local to a wave vector
+      ifftn      2-D inverse FFTs over (y, z) on the k_x slab (cuFFT through torch.fft), all-to-all transpose
+                 over NVLink (NCCL) to y slabs, 1-D inverse FFTs along x, the real part, and the all-to-all back
+      amplitude  the two sums are local sums + one SUM all-reduce of two scalars
+    Results agree with the single-GPU field to round-off (another FFT factorisation, another summation order),
+    not bit for bit: the forced state is compared at the north-star tolerance (tools/slab_check.py,
+    tests/test_slab_gloo.py)."""
+
+    def __init__(self, config, params, registered_variables, dtype, device, rank, world, group=None, noise_fn=None):
+        import torch.distributed as dist
+        self.dist = dist
+        if config.dimensionality != 3:
+            raise ValueError("turbulent forcing needs a 3-D grid")
+        if config.boundary_handling != oc.PERIODIC_ROLL:
+            raise ValueError("turbulent forcing needs boundary_handling=PERIODIC_ROLL (unpadded state)")
+        n, L = config.num_cells, config.box_size
+        if n % world:
+            raise ValueError("num_cells must be divisible by the number of ranks")
+        self.n, self.rank, self.world, self.group = n, rank, world, group
+        self.nl = n // world
+        self.x0 = rank * self.nl
+        self.dtype, self.device = dtype, device
+        self.cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
+        self.rv = registered_variables
+        self.edot = float(params.turbulent_forcing_params.energy_injection_rate)
+        self.dV = config.grid_spacing ** 3
+        k1 = 2.0 * math.pi * torch.fft.fftfreq(n, d=L / n, dtype=dtype, device=device)
+        self.kx = k1[self.x0:self.x0 + self.nl].reshape(self.nl, 1, 1)
+        self.ky, self.kz = k1.reshape(1, n, 1), k1.reshape(1, 1, n)
+        self.k2 = self.kx ** 2 + self.ky ** 2 + self.kz ** 2
+        kk = torch.sqrt(self.k2)
+        kpk = 4.0 * math.pi / L
+        self.sqrtP = torch.sqrt(kk ** 6 * torch.exp(-8.0 * kk / kpk))
+        self.k2_safe = torch.where(self.k2 == 0.0, torch.ones_like(self.k2), self.k2)
+        self.noise_fn = noise_fn
+        self.key = None
+        self.steps = 0
+
+    def local_noise(self):
+        """this rank's slab [3, n/P, n, n] of the step's complex noise"""
+        if self.noise_fn is not None:  # tests: a recorded / restated global field
+            full = self.noise_fn(self.steps)
+            return full[:, self.x0:self.x0 + self.nl].to(self.device).clone()
+        from . import threefry
+        if self.key is None:
+            self.key = threefry.key(42)
+        self.key, sk1, sk2 = threefry.split(self.key, 3)
+        n, nl = self.n, self.nl
+        re = torch.empty((3, nl, n, n), dtype=self.dtype, device=self.device)
+        im = torch.empty_like(re)
+        for c in range(3):
+            off = (c * n + self.x0) * n * n
+            threefry.normal_range(sk1, 3 * n ** 3, off, re[c])
+            threefry.normal_range(sk2, 3 * n ** 3, off, im[c])
+        return torch.complex(re, im)
+
+    def _transpose_x_to_y(self, a):
+        """[3, n/P, n, n] (x slab) -> [3, n, n/P, n] (y slab)"""
+        P, nl, n = self.world, self.nl, self.n
+        if P == 1:
+            return a
+        send = a.reshape(3, nl, P, nl, n).permute(2, 0, 1, 3, 4).contiguous()   # [P][3, nl(x), nl(y), n]
+        recv = torch.empty_like(send)
+        self.dist.all_to_all_single(recv, send, group=self.group)
+        return recv.permute(1, 0, 2, 3, 4).reshape(3, n, nl, n)                  # x = (source rank, local x)
+
+    def _transpose_y_to_x(self, a):
+        """[3, n, n/P, n] (y slab) -> [3, n/P, n, n] (x slab)"""
+        P, nl, n = self.world, self.nl, self.n
+        if P == 1:
+            return a
+        send = a.reshape(3, P, nl, nl, n).permute(1, 0, 2, 3, 4).contiguous()   # [P][3, nl(x), nl(y), n]
+        recv = torch.empty_like(send)
+        self.dist.all_to_all_single(recv, send, group=self.group)
+        return recv.permute(1, 2, 0, 3, 4).reshape(3, nl, n, n)                  # y = (source rank, local y)
+
+    def field(self, noise):
+        """this rank's x slab [3, n/P, n, n] of the real solenoidal field"""
+        cw = self.sqrtP * noise
+        if self.rank == 0:
+            cw[:, 0, 0, 0] = 0.0
+        div_k = (self.kx * cw[0] + self.ky * cw[1] + self.kz * cw[2]) / self.k2_safe
+        if self.rank == 0:
+            div_k[0, 0, 0] = 0.0
+        cw = torch.stack([cw[0] - self.kx * div_k, cw[1] - self.ky * div_k, cw[2] - self.kz * div_k])
+        a = torch.fft.ifftn(cw, dim=(2, 3))
+        a = self._transpose_x_to_y(a)
+        a = torch.fft.ifft(a, dim=1).real.contiguous()
+        return self._transpose_y_to_x(a)
+
+    def apply(self, state, dt):
+        """state: this rank's active planes [rows, n/P, n, n] (a view; its velocity rows are updated in place)"""
+        w = self.field(self.local_noise())
+        self.steps += 1
+        rv = self.rv
+        rho = state[rv.density_index]
+        v = [state[rv.velocity_index.x], state[rv.velocity_index.y], state[rv.velocity_index.z]]
+        sums = torch.stack([0.5 * torch.sum(rho * (w[0] ** 2 + w[1] ** 2 + w[2] ** 2)),
+                            torch.sum(rho * v[0] * w[0] + rho * v[1] * w[1] + rho * v[2] * w[2])])
+        if self.world > 1:
+            self.dist.all_reduce(sums, op=self.dist.ReduceOp.SUM, group=self.group)
+        tempa, tempb = sums[0], sums[1]
+        tempc = -self.edot * dt / self.dV
+        disc = tempb ** 2 - 4.0 * tempa * tempc
+        ok = (disc >= 0) & (tempa.abs() > 1e-10)
+        amp = torch.where(ok, (-tempb + torch.sqrt(torch.clamp(disc, min=0))) / (2.0 * tempa), torch.zeros_like(tempa))
+        for i in range(3):
+            v[i].add_(amp * w[i])
+        return state
+
+
 def integrate_per_step(t, kind, config, params, registered_variables, snapshot_callable, from_device,
                        noise_fn=None):
     """The reference's loop body one step at a time (time_integration.py:397-737) for runs that touch

@@ -281,6 +281,7 @@ class SlabDriver:
                 print(f"[slab] peer-memory plumbing unavailable ({e!r}); copies + NCCL all-reduce", flush=True)
                 self._comm = None
                 self.push = 0
+        self.forcing = None  # forcing.SlabForcing: turbulent driving between dt and the step
         self.alpha = torch.zeros(3, dtype=dtype, device=device)
         self.change = torch.zeros(2, dtype=dtype, device=device)
         self.change4 = torch.zeros(4, dtype=dtype, device=device)
@@ -605,6 +606,11 @@ class SlabDriver:
         self.backend.dt_from_alpha(self.alpha, self.time if self.config.exact_end_time else None,
                                    self.params.t_end, self.dt)
         sin, sout = self.S[self.cur], self.S[self.cur ^ 1]
+        if self.forcing is not None:
+            # time_integration.py:699-711: the driving acts on the state between dt and the step; the ghost
+            # planes the previous step's kernels stored are those of the unforced state
+            self.forcing.apply(sin[:, NG:NG + self.nxl], self.dt)
+            self._pushed.pop(sin.data_ptr(), None)
         iters = 0
         if not self.mhd:
             self._hydro(sin, sout, 1.0, True, self.G)
@@ -780,6 +786,42 @@ def bench_weak(n, K, W, device):
         torch.cuda.empty_cache()
         return res
 
+    def run_c5(nc, steps, warm):
+        """BASELINE config 5: driven MHD turbulence on the nc^3 cube, slabs along x (rho 0.5, p 0.1, v 0,
+        B = (0.1, 0.1, 0) / sqrt 2, energy injection rate 2, PERIODIC_ROLL; arena_tests/turbulent_forcing)."""
+        from . import option_classes as oc
+        from .forcing import SlabForcing
+        tfc = oc.TurbulentForcingConfig(turbulent_forcing=True)
+        config, params, rv = pr.make(3, nc, mhd=True, boundary_handling=oc.PERIODIC_ROLL, turbulent_forcing_config=tfc)
+        params = params._replace(t_end=1.0e9, dt_max=0.1,
+                                 turbulent_forcing_params=params.turbulent_forcing_params._replace(energy_injection_rate=2.0))
+        drv = SlabDriver(config, params, rv, (nc, nc, nc), torch.float32, device)
+        act = drv.S[0][:, NG:NG + drv.nxl]
+        act.zero_()
+        act[0].fill_(0.5)
+        act[4].fill_(0.1)
+        act[5].fill_(0.1 / 2 ** 0.5)
+        act[6].fill_(0.1 / 2 ** 0.5)
+        drv.reset()
+        drv.time.zero_()
+        drv._alpha_of(drv.S[0][: drv.ng])
+        drv.forcing = SlabForcing(config, params, rv, torch.float32, device, drv.rank, drv.world)
+        ms, iters, launches, colls, _ = _timed_steps(drv, steps, warm, device, False)
+        vel = drv.local_result()[1:4]
+        ek = torch.stack([(0.5 * 0.5 * vel.double() ** 2).sum()])
+        dist.all_reduce(ek)
+        finite = bool(torch.isfinite(drv.local_result()).all())
+        res = {"workload": f"C5: 3-D driven MHD turbulence {nc}^3 on {world} GPUs (x slabs), fp32, HLL, minmod, "
+                           "PERIODIC_ROLL; per step: Threefry noise, spectrum + projection, distributed inverse FFT "
+                           "(cuFFT + NCCL all-to-all), amplitude from two all-reduced sums, then the MHD step",
+               "value": nc ** 3 * steps / (ms * 1e-3), "unit": "cell-updates/s", "steps": steps, "ms_per_step": ms / steps,
+               "magnetic_iterations_per_step": iters / steps, "finite": finite,
+               "kinetic_energy_after": float(ek.item()) * config.grid_spacing ** 3,
+               "time": float(drv.time.item())}
+        del drv
+        torch.cuda.empty_cache()
+        return res
+
     series = WEAK_SERIES.get(world)
     if series is not None and os.environ.get("AMX_BENCH_SERIES", "1") != "0":
         main = run(512, series, True, True)
@@ -808,6 +850,11 @@ def bench_weak(n, K, W, device):
         halo, red = "NCCL send/recv (packed)", "NCCL all-reduce MAX"
     cfg = {"collectives_per_step": main["colls"] / K, "halo": halo, "reductions": red,
            "slab_equals_single_gpu_bitwise_256": same}
+    if os.environ.get("AMX_BENCH_C5", "1") != "0" and 1024 % world == 0:
+        try:
+            cfg["c5_driven_turbulence"] = run_c5(1024 if world == 8 else 512, 5, 2)
+        except Exception as e:  # a secondary line must not take the headline down
+            cfg["c5_driven_turbulence"] = {"error": repr(e)}
     if second is not None:
         cfg["secondary"] = {"workload": f"{n}^3 cells per rank, global {n * world}x{n}x{n}",
                             "value": second["value"], "ms_per_step": second["ms"] / K,

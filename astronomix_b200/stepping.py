@@ -226,9 +226,8 @@ def _time_integration_sharded(primitive_state, config, params, registered_variab
     sh = _as_slab_sharding(sharding)
     if not dist.is_initialized():
         raise RuntimeError("sharding needs torch.distributed (one process per GPU, e.g. under torchrun)")
-    if (config.turbulent_forcing_config.turbulent_forcing or config.return_snapshots
-            or config.activate_snapshot_callback):
-        raise NotImplementedError("snapshots / callbacks / turbulent forcing on a sharded run are not built")
+    if config.return_snapshots or config.activate_snapshot_callback:
+        raise NotImplementedError("snapshots / callbacks on a sharded run are not built")
     struct = config.state_struct
     state = primitive_state.primitive_state if struct else primitive_state
     world = dist.get_world_size(sh.group)
@@ -245,6 +244,9 @@ def _time_integration_sharded(primitive_state, config, params, registered_variab
     if src.dim() != config.dimensionality + 1 or src.shape[0] != registered_variables.num_vars:
         raise ValueError(f"state must be [{registered_variables.num_vars}, ...], got {tuple(src.shape)}")
     drv = SlabDriver(config, params, registered_variables, global_n, src.dtype, device, group=sh.group)
+    if config.turbulent_forcing_config.turbulent_forcing:
+        from .forcing import SlabForcing
+        drv.forcing = SlabForcing(config, params, registered_variables, src.dtype, device, drv.rank, drv.world, sh.group)
     if sh.local_input:
         from .slab import NG
         drv.S[0][:, NG:NG + drv.nxl].copy_(src.to(device))

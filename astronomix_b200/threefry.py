@@ -68,3 +68,19 @@ def normal(k, shape, dtype=torch.float32, device=None, partitionable=None, out=N
     if rc:
         raise _lib.AmxError(rc, "amx_threefry_normal failed (count beyond the 32-bit counters of the old layout?)")
     return out
+
+
+def normal_range(k, total, offset, out, partitionable=None):
+    """Samples [offset, offset + out.numel()) of jax.random.normal(k, shape) with prod(shape) = total, into the
+    contiguous CUDA tensor ``out`` (a slab rank's part of a global draw)."""
+    part = PARTITIONABLE if partitionable is None else partitionable
+    _lib.require_device()
+    assert out.is_contiguous()
+    code = _lib.AMX_F32 if out.dtype == torch.float32 else _lib.AMX_F64
+    with torch.cuda.device(out.device):
+        rc = _lib.load().amx_threefry_normal_range(int(k[0]), int(k[1]), int(total), int(offset), out.numel(),
+                                                   C.c_void_p(out.data_ptr()), code, 1 if part else 0,
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        raise _lib.AmxError(rc, "amx_threefry_normal_range failed")
+    return out

@@ -276,6 +276,10 @@ AMX_API int amx_peer_allreduce_max(void* const* comm_bufs, int rank, int world, 
  * integer work (astronomix_b200/threefry.py). */
 AMX_API int amx_threefry_normal(uint32_t key0, uint32_t key1, int64_t count, void* out, int dtype,
                       int partitionable, void* stream);
+/* samples [offset, offset + count) of the same draw of `total` samples: what a slab rank needs of a global
+ * (3, n, n, n) draw */
+AMX_API int amx_threefry_normal_range(uint32_t key0, uint32_t key1, int64_t total, int64_t offset, int64_t count,
+                      void* out, int dtype, int partitionable, void* stream);
 
 #ifdef __cplusplus
 }

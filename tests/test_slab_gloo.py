@@ -259,3 +259,51 @@ def test_single_rank_driver_wraps_locally():
     drv.run(max_steps=3)
     ref = fo.time_integration(s, fo.Opts.from_config(config, params), max_steps=3)
     assert np.array_equal(drv.gather().numpy(), ref)
+
+
+# ---- turbulent driving on slab ranks (forcing.SlabForcing): distributed inverse FFT + global sums ----
+def _forcing_worker(rank, world, port, n, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from astronomix_b200.forcing import SlabForcing
+        from oracle import threefry as tf
+        tfc = oc.TurbulentForcingConfig(turbulent_forcing=True)
+        config, params, rv = pr.make(3, n, mhd=True, dtype=np.float64, boundary_handling=oc.PERIODIC_ROLL,
+                                     turbulent_forcing_config=tfc)
+        _, sk1, sk2 = tf.split(tf.seed_key(42), 3)
+        noise = torch.complex(torch.from_numpy(tf.normal(sk1, (3, n, n, n), np.float64)),
+                              torch.from_numpy(tf.normal(sk2, (3, n, n, n), np.float64)))
+        f = SlabForcing(config, params, rv, torch.float64, torch.device("cpu"), rank, world,
+                        noise_fn=lambda step: noise)
+        s = torch.from_numpy(pr.smooth_random(3, n, mhd=True, seed=9, dtype=np.float64))
+        nl = n // world
+        loc = s[:, rank * nl:(rank + 1) * nl].clone()
+        f.apply(loc, torch.tensor(1.0e-3, dtype=torch.float64))
+        parts = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(parts, loc.contiguous())
+        if rank == 0:
+            np.save(out_path, torch.cat(parts, dim=1).numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_forcing_equals_single_domain_forcing(world, tmp_path):
+    """k_x-slab spectrum + (2-D FFT, all-to-all, 1-D FFT) inverse transform + all-reduced sums against the oracle's
+    whole-domain forcing on the same (restated Threefry) noise: round-off agreement (another FFT factorisation)."""
+    n = 16
+    out = str(tmp_path / "forced.npy")
+    mp.spawn(_forcing_worker, args=(world, _free_port(), n, out), nprocs=world, join=True)
+    got = np.load(out)
+    from oracle import threefry as tf
+    tfc = oc.TurbulentForcingConfig(turbulent_forcing=True)
+    config, params, rv = pr.make(3, n, mhd=True, dtype=np.float64, boundary_handling=oc.PERIODIC_ROLL,
+                                 turbulent_forcing_config=tfc)
+    _, sk1, sk2 = tf.split(tf.seed_key(42), 3)
+    noise = tf.normal(sk1, (3, n, n, n), np.float64) + 1j * tf.normal(sk2, (3, n, n, n), np.float64)
+    s = pr.smooth_random(3, n, mhd=True, seed=9, dtype=np.float64)
+    ref = fo.apply_forcing(s, np.float64(1.0e-3), noise, params.turbulent_forcing_params.energy_injection_rate,
+                           fo.Opts.from_config(config, params), config.box_size)
+    assert pr.rel_l1(got, ref, 3, True) <= 1e-12
+    assert np.array_equal(got[0], s[0]) and np.array_equal(got[4:], s[4:])
