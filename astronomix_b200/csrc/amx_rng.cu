@@ -132,6 +132,102 @@ __global__ void normal_range(uint32_t k0, uint32_t k1, long long total, long lon
   }
 }
 
+// ---- turbulent driving, fused (_turbulent_forcing.py:15-65 up to the inverse FFT) -------------------------
+// One thread per wave vector of the rank's k_x slab [x0, x0 + nl) x n x n: the six normal samples of the
+// step (real parts from key A, imaginary parts from key B, component c at linear index ((c n + ix) n + iy) n + iz
+// of a (3, n, n, n) draw), spectrum sqrt(k^6 exp(-8 k / k_peak)), DC mode zero, compressive part projected
+// out; writes the three complex coefficients (interleaved re, im) that the inverse FFT reads.
+template <typename T>
+__device__ __forceinline__ T sample_at(uint32_t k0, uint32_t k1, long long total, long long j, int partitionable) {
+  constexpr bool f64 = sizeof(T) == 8;
+  uint32_t x0, x1;
+  bool second = false;
+  if (partitionable) {
+    x0 = (uint32_t)((unsigned long long)j >> 32); x1 = (uint32_t)j;
+  } else if (f64) {
+    x0 = (uint32_t)j; x1 = (uint32_t)(j + total);
+  } else {
+    const long long half = (total + 1) / 2;
+    second = j >= half;
+    const long long b = second ? j - half : j;
+    x0 = (uint32_t)b; x1 = (uint32_t)(b + half);
+    if ((total & 1) && b + half == total) x1 = 0u;
+  }
+  threefry2x32(k0, k1, x0, x1);
+  if constexpr (f64) return normal_from_bits(((uint64_t)x0 << 32) | x1);
+  else return normal_from_bits(partitionable ? (x0 ^ x1) : (second ? x1 : x0));
+}
+
+template <typename T>
+__global__ void forcing_spectrum_kernel(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, int n, int x0, int nl,
+                                        double box, int partitionable, T* out) {
+  const long long cells = (long long)nl * n * n, total = 3ll * n * n * n;
+  const T two_pi = (T)6.283185307179586476925286766559;
+  const T d = (T)(box / n);
+  const T kpk = (T)(4.0 * 3.14159265358979323846 / box);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+    const int iz = (int)(i % n), iy = (int)((i / n) % n), ixl = (int)(i / ((long long)n * n));
+    const int ix = x0 + ixl;
+    // numpy.fft.fftfreq(n, d): f = (i < (n + 1) / 2 ? i : i - n) / (n d); k = 2 pi f
+    auto kof = [&](int q) { return two_pi * ((T)(q < (n + 1) / 2 ? q : q - n) / ((T)n * d)); };
+    const T kx = kof(ix), ky = kof(iy), kz = kof(iz);
+    const T k2 = kx * kx + ky * ky + kz * kz;
+    const T kk = sqrt(k2);
+    const T k3 = kk * kk * kk;
+    const T sp = sqrt(k3 * k3 * exp((T)-8.0 * kk / kpk));
+    const bool dc = (ix | iy | iz) == 0;
+    T re[3], im[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const long long j = ((long long)c * n + ix) * n * n + (long long)iy * n + iz;
+      re[c] = dc ? (T)0 : sp * sample_at<T>(a0, a1, total, j, partitionable);
+      im[c] = dc ? (T)0 : sp * sample_at<T>(b0, b1, total, j, partitionable);
+    }
+    const T k2s = k2 == (T)0 ? (T)1 : k2;
+    const T dre = dc ? (T)0 : (kx * re[0] + ky * re[1] + kz * re[2]) / k2s;
+    const T dim = dc ? (T)0 : (kx * im[0] + ky * im[1] + kz * im[2]) / k2s;
+    const T kv[3] = {kx, ky, kz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T* o = out + 2 * ((long long)c * cells + i);
+      o[0] = re[c] - kv[c] * dre;
+      o[1] = im[c] - kv[c] * dim;
+    }
+  }
+}
+
+// The two sums of the amplitude equation (_turbulent_forcing.py:103-104) over the rank's cells, in double,
+// deterministic: per-block partial sums, then block 0 of a second launch adds them in index order.
+template <typename T>
+__global__ void __launch_bounds__(256) forcing_sums_kernel(const T* rho, const T* vx, const T* vy, const T* vz, const T* w,
+                                                         long long cells, double* partial) {
+  double sa = 0.0, sb = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+    const double r = rho[i], w0 = w[i], w1 = w[cells + i], w2 = w[2 * cells + i];
+    sa += r * (w0 * w0 + w1 * w1 + w2 * w2);
+    sb += r * ((double)vx[i] * w0 + (double)vy[i] * w1 + (double)vz[i] * w2);
+  }
+  __shared__ double red[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sa; red[1][threadIdx.x >> 5] = sb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < 8; ++k) { a += red[0][k]; b += red[1][k]; }
+    partial[2 * blockIdx.x] = a;
+    partial[2 * blockIdx.x + 1] = b;
+  }
+}
+__global__ void forcing_sums_finish(const double* partial, int nblocks, double* out2) {
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < nblocks; ++k) { a += partial[2 * k]; b += partial[2 * k + 1]; }
+  out2[0] = 0.5 * a;
+  out2[1] = b;
+}
+
 }  // namespace
 
 extern "C" {
@@ -169,6 +265,40 @@ int amx_threefry_normal_range(uint32_t key0, uint32_t key1, int64_t total, int64
     normal_range<float><<<blocks, threads, 0, st>>>(key0, key1, total, offset, count, partitionable, static_cast<float*>(out));
   else
     normal_range<double><<<blocks, threads, 0, st>>>(key0, key1, total, offset, count, partitionable, static_cast<double*>(out));
+  return cudaGetLastError() == cudaSuccess ? AMX_OK : AMX_ECUDA;
+}
+
+int amx_forcing_spectrum(uint32_t re_key0, uint32_t re_key1, uint32_t im_key0, uint32_t im_key1, int n, int x0, int nl,
+                         double box_size, void* out_complex, int dtype, int partitionable, void* stream) {
+  if (n < 2 || x0 < 0 || nl < 1 || x0 + nl > n || !out_complex || (dtype != AMX_F32 && dtype != AMX_F64) || !(box_size > 0))
+    return AMX_EINVAL;
+  if (!partitionable && 3ll * n * n * n * (dtype == AMX_F64 ? 2 : 1) > 0xFFFFFFFFll) return AMX_EUNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long cells = (long long)nl * n * n;
+  const unsigned blocks = (unsigned)((cells + 255) / 256 < 148ll * 32 ? (cells + 255) / 256 : 148ll * 32);
+  if (dtype == AMX_F32)
+    forcing_spectrum_kernel<float><<<blocks, 256, 0, st>>>(re_key0, re_key1, im_key0, im_key1, n, x0, nl, box_size,
+                                                           partitionable, static_cast<float*>(out_complex));
+  else
+    forcing_spectrum_kernel<double><<<blocks, 256, 0, st>>>(re_key0, re_key1, im_key0, im_key1, n, x0, nl, box_size,
+                                                            partitionable, static_cast<double*>(out_complex));
+  return cudaGetLastError() == cudaSuccess ? AMX_OK : AMX_ECUDA;
+}
+
+int amx_forcing_sums(const void* rho, const void* vx, const void* vy, const void* vz, const void* w3, int64_t cells,
+                     void* scratch, void* sums2_out, int dtype, void* stream) {
+  if (!rho || !vx || !vy || !vz || !w3 || !scratch || !sums2_out || cells < 1 || (dtype != AMX_F32 && dtype != AMX_F64))
+    return AMX_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (int)((cells + 255) / 256 < 1024 ? (cells + 255) / 256 : 1024);
+  double* partial = static_cast<double*>(scratch);
+  if (dtype == AMX_F32)
+    forcing_sums_kernel<float><<<blocks, 256, 0, st>>>((const float*)rho, (const float*)vx, (const float*)vy, (const float*)vz,
+                                                       (const float*)w3, cells, partial);
+  else
+    forcing_sums_kernel<double><<<blocks, 256, 0, st>>>((const double*)rho, (const double*)vx, (const double*)vy,
+                                                        (const double*)vz, (const double*)w3, cells, partial);
+  forcing_sums_finish<<<1, 1, 0, st>>>(partial, blocks, static_cast<double*>(sums2_out));
   return cudaGetLastError() == cudaSuccess ? AMX_OK : AMX_ECUDA;
 }
 

@@ -28,6 +28,50 @@ from . import _lib
 from . import option_classes as oc
 
 
+def _fused_spectrum(sk1, sk2, n, x0, nl, box, dtype, device):
+    """libamx amx_forcing_spectrum: noise + spectrum + projection of the k_x slab in one pass -> complex
+    [3, nl, n, n]"""
+    from . import threefry
+    cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
+    out = torch.empty((3, nl, n, n), dtype=cdtype, device=device)
+    code = _lib.AMX_F32 if dtype == torch.float32 else _lib.AMX_F64
+    with torch.cuda.device(device):
+        rc = _lib.load().amx_forcing_spectrum(int(sk1[0]), int(sk1[1]), int(sk2[0]), int(sk2[1]), int(n), int(x0), int(nl),
+                                              float(box), C.c_void_p(out.data_ptr()), code,
+                                              1 if threefry.PARTITIONABLE else 0,
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        raise _lib.AmxError(rc, "amx_forcing_spectrum failed")
+    return out
+
+
+def _fused_sums(state_rows, w, scratch):
+    """libamx amx_forcing_sums -> device tensor [0.5 sum rho |w|^2, sum rho v.w] (float64)"""
+    rho, vx, vy, vz = state_rows
+    assert w.is_contiguous() and all(t.is_contiguous() for t in state_rows)
+    out = torch.empty(2, dtype=torch.float64, device=w.device)
+    code = _lib.AMX_F32 if w.dtype == torch.float32 else _lib.AMX_F64
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    with torch.cuda.device(w.device):
+        rc = _lib.load().amx_forcing_sums(p(rho), p(vx), p(vy), p(vz), p(w), rho.numel(), p(scratch), p(out), code,
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        raise _lib.AmxError(rc, "amx_forcing_sums failed")
+    return out
+
+
+def _amplitude_and_push(sums, v, w, edot, dt, dV):
+    """root of a amp^2 + b amp + c = 0 (c = -Edot dt / dV) and v += amp w (_turbulent_forcing.py:105-125)"""
+    tempa, tempb = sums[0], sums[1]
+    tempc = -edot * dt.to(sums.dtype) / dV
+    disc = tempb ** 2 - 4.0 * tempa * tempc
+    ok = (disc >= 0) & (tempa.abs() > 1e-10)
+    amp = torch.where(ok, (-tempb + torch.sqrt(torch.clamp(disc, min=0))) / (2.0 * tempa), torch.zeros_like(tempa))
+    amp = amp.to(w.dtype)
+    for i in range(3):
+        v[i].addcmul_(w[i], amp)
+
+
 class ForcingNoise:
     """(3, n, n, n) complex standard-normal noise per step: ``key, sk1, sk2 = split(key, 3)``, real part from
     sk1, imaginary part from sk2 (_turbulent_forcing.py:48-51); the carried key starts as key(42)."""
@@ -53,6 +97,7 @@ class Forcing:
             raise ValueError("turbulent forcing needs boundary_handling=PERIODIC_ROLL (unpadded state)")
         n, L = config.num_cells, config.box_size
         self.rv = registered_variables
+        self.box, self.key = float(L), None
         self.edot = float(params.turbulent_forcing_params.energy_injection_rate)
         self.dV = config.grid_spacing ** 3
         k1 = (2.0 * math.pi * torch.fft.fftfreq(n, d=L / n, dtype=dtype, device=device))
@@ -72,6 +117,25 @@ class Forcing:
         div_k[0, 0, 0] = 0.0
         cw = [cw[0] - self.kx * div_k, cw[1] - self.ky * div_k, cw[2] - self.kz * div_k]
         return [torch.fft.ifftn(c).real for c in cw]
+
+    def apply_fused(self, state, dt):
+        """_apply_forcing with the library's kernels (CUDA): the step's keys are split off the carried
+        key(42); noise, spectrum and projection in one kernel, three inverse FFTs (cuFFT), the two sums in one
+        deterministic reduction, v += amp w.  No host synchronisation."""
+        from . import threefry
+        if self.key is None:
+            self.key = threefry.key(42)
+            self.scratch = torch.empty(2048, dtype=torch.float64, device=state.device)
+        self.key, sk1, sk2 = threefry.split(self.key, 3)
+        n = state.shape[-1]
+        cw = _fused_spectrum(sk1, sk2, n, 0, n, self.box, state.dtype, state.device)
+        w = torch.fft.ifftn(cw, dim=(1, 2, 3)).real.contiguous()
+        del cw
+        rv = self.rv
+        rows = (state[rv.density_index], state[rv.velocity_index.x], state[rv.velocity_index.y], state[rv.velocity_index.z])
+        sums = _fused_sums(rows, w, self.scratch)
+        _amplitude_and_push(sums, rows[1:], w, self.edot, dt, self.dV)
+        return state
 
     def apply(self, state, dt, noise):
         """_apply_forcing: state (device, unpadded) gets amp * w added to its velocity rows; dt is a
@@ -112,6 +176,7 @@ class SlabForcing:
         if config.boundary_handling != oc.PERIODIC_ROLL:
             raise ValueError("turbulent forcing needs boundary_handling=PERIODIC_ROLL (unpadded state)")
         n, L = config.num_cells, config.box_size
+        self.box = float(L)
         if n % world:
             raise ValueError("num_cells must be divisible by the number of ranks")
         self.n, self.rank, self.world, self.group = n, rank, world, group
@@ -181,16 +246,36 @@ class SlabForcing:
         if self.rank == 0:
             div_k[0, 0, 0] = 0.0
         cw = torch.stack([cw[0] - self.kx * div_k, cw[1] - self.ky * div_k, cw[2] - self.kz * div_k])
+        return self._inverse_transform(cw)
+
+    def _inverse_transform(self, cw):
         a = torch.fft.ifftn(cw, dim=(2, 3))
         a = self._transpose_x_to_y(a)
         a = torch.fft.ifft(a, dim=1).real.contiguous()
-        return self._transpose_y_to_x(a)
+        return self._transpose_y_to_x(a).contiguous()
 
     def apply(self, state, dt):
         """state: this rank's active planes [rows, n/P, n, n] (a view; its velocity rows are updated in place)"""
+        rv = self.rv
+        if self.noise_fn is None and state.is_cuda:
+            from . import threefry
+            if self.key is None:
+                self.key = threefry.key(42)
+                self.scratch = torch.empty(2048, dtype=torch.float64, device=state.device)
+            self.key, sk1, sk2 = threefry.split(self.key, 3)
+            cw = _fused_spectrum(sk1, sk2, self.n, self.x0, self.nl, self.box, self.dtype, self.device)
+            w = self._inverse_transform(cw)
+            del cw
+            self.steps += 1
+            rows = (state[rv.density_index], state[rv.velocity_index.x], state[rv.velocity_index.y],
+                    state[rv.velocity_index.z])
+            sums = _fused_sums(rows, w, self.scratch)
+            if self.world > 1:
+                self.dist.all_reduce(sums, op=self.dist.ReduceOp.SUM, group=self.group)
+            _amplitude_and_push(sums, rows[1:], w, self.edot, dt, self.dV)
+            return state
         w = self.field(self.local_noise())
         self.steps += 1
-        rv = self.rv
         rho = state[rv.density_index]
         v = [state[rv.velocity_index.x], state[rv.velocity_index.y], state[rv.velocity_index.z]]
         sums = torch.stack([0.5 * torch.sum(rho * (w[0] ** 2 + w[1] ** 2 + w[2] ** 2)),
@@ -228,8 +313,6 @@ def integrate_per_step(t, kind, config, params, registered_variables, snapshot_c
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     forced = config.turbulent_forcing_config.turbulent_forcing
     forcing = Forcing(config, params, registered_variables, tdt, t.device) if forced else None
-    if forcing is not None and noise_fn is None:
-        noise_fn = ForcingNoise(config.num_cells, tdt, t.device)
     snaps, cb = config.return_snapshots, config.activate_snapshot_callback
     st, N = config.snapshot_settings, int(config.num_snapshots)
     diag = Diagnostics(config, params, registered_variables, tdt, t.device) if snaps else None
@@ -265,7 +348,10 @@ def integrate_per_step(t, kind, config, params, registered_variables, snapshot_c
             if config.exact_end_time:
                 torch.minimum(dt, t_end_dev - time_dev, out=dt)
             if forcing is not None:
-                forcing.apply(cur, dt, noise_fn(steps))
+                if noise_fn is None:
+                    forcing.apply_fused(cur, dt)
+                else:  # tests: recorded / restated noise through the torch formulation
+                    forcing.apply(cur, dt, noise_fn(steps))
             _lib.check(lib.amx_step(C.byref(desc), C.c_void_p(cur.data_ptr()), C.c_void_p(nxt.data_ptr()),
                                     C.c_void_p(dt.data_ptr()), ws_ptr, stream, C.byref(stats)))
         time_dev.add_(dt)

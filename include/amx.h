@@ -281,6 +281,18 @@ AMX_API int amx_threefry_normal(uint32_t key0, uint32_t key1, int64_t count, voi
 AMX_API int amx_threefry_normal_range(uint32_t key0, uint32_t key1, int64_t total, int64_t offset, int64_t count,
                       void* out, int dtype, int partitionable, void* stream);
 
+/* _turbulent_forcing.py:15-65 up to the inverse FFT, fused: the rank's k_x slab [x0, x0 + nl) x n x n of the three
+ * complex coefficient arrays (noise drawn in the kernel from the two Threefry keys of the step, spectrum
+ * k^6 exp(-8 k / k_peak), DC mode zero, compressive part projected out) -> out_complex [3][nl][n][n] interleaved
+ * (re, im) of `dtype`.  x0 = 0, nl = n: the whole grid. */
+AMX_API int amx_forcing_spectrum(uint32_t re_key0, uint32_t re_key1, uint32_t im_key0, uint32_t im_key1, int n,
+                      int x0, int nl, double box_size, void* out_complex, int dtype, int partitionable,
+                      void* stream);
+/* _turbulent_forcing.py:103-104: sums2_out[0] = 0.5 sum rho |w|^2, sums2_out[1] = sum rho v.w over `cells` cells
+ * (double, deterministic two-pass reduction; w3 = [3][cells]; scratch >= 2048 doubles). */
+AMX_API int amx_forcing_sums(const void* rho, const void* vx, const void* vy, const void* vz, const void* w3,
+                      int64_t cells, void* scratch, void* sums2_out, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -630,3 +630,26 @@ def test_driven_turbulence_through_time_integration(cuda):
     assert np.isfinite(out).all() and ti.last_info.steps > 1
     ek = 0.5 * (out[0] * (out[1:4] ** 2).sum(axis=0)).sum() * config.grid_spacing ** 3
     assert 0.2 * 2.0 * 0.02 < ek <= 2.0 * 0.02 * 1.001     # at most Edot * t, part of it already thermalised
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-6)])
+def test_fused_forcing_kernels_equal_the_torch_formulation(cuda, dtype, tol):
+    """amx_forcing_spectrum (noise + spectrum + projection in one kernel) + amx_forcing_sums against the
+    torch formulation that the oracle pins, on the same Threefry keys; two consecutive steps (key carry)."""
+    import torch
+    from astronomix_b200 import forcing as fm
+    n = 24
+    tf = oc.TurbulentForcingConfig(turbulent_forcing=True)
+    config, params, rv = pr.make(3, n, mhd=True, dtype=dtype, boundary_handling=oc.PERIODIC_ROLL,
+                                 turbulent_forcing_config=tf)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    s = torch.from_numpy(pr.smooth_random(3, n, mhd=True, seed=12, dtype=dtype)).to(cuda)
+    fa, fb = fm.Forcing(config, params, rv, tdt, cuda), fm.Forcing(config, params, rv, tdt, cuda)
+    gen = fm.ForcingNoise(n, tdt, cuda, seed=42)
+    a, b = s.clone(), s.clone()
+    dt = torch.tensor(1.0e-3, dtype=tdt, device=cuda)
+    for step in range(2):
+        fa.apply_fused(a, dt)
+        fb.apply(b, dt, gen(step))
+        assert pr.rel_l1(a.cpu().numpy(), b.cpu().numpy(), 3, True) <= tol
+    assert float((a[1:4] - s[1:4]).abs().max()) > 0
