@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <unordered_map>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -424,6 +425,7 @@ __global__ void mag_check_fused_kernel(Ctl* ctl, double tol, int c0, int nevals,
     return;
   }
   ctl->mag_iter += 1;
+  ctl->mag_last_buf = nb;
   if (nevals == 2) {
     const T m2 = n[2] > n[3] ? n[2] : n[3];
     ctl->change[0] = (double)n[2];
@@ -437,6 +439,28 @@ __global__ void mag_check_fused_kernel(Ctl* ctl, double tol, int c0, int nevals,
       ctl->final_emitted = emit;  // the launch also wrote the write-back of exactly this iterate
     }
   }
+}
+
+// After the fixed-point launches a step was given.  mode 0 (amx_integrate's pipeline, which never waits for the
+// device inside a step): still iterating -> raise `stalled` and `done`; every kernel enqueued behind exits at once
+// and the host resumes the step when it looks.  mode 1 (amx_step without stats: a fixed launch budget and no host
+// round trip, so that the call can be captured into a CUDA graph / XLA command buffer): still iterating -> the
+// write-back takes the latest iterate and the sticky not_converged flag is raised (amx_magnetic_state reads it).
+__global__ void mag_guard_kernel(Ctl* ctl, int mode) {
+  if (ctl->done || !ctl->mag_active) return;
+  if (mode == 0) {
+    ctl->stalled = 1;
+    ctl->done = 1;
+  } else {
+    ctl->mag_active = 0;
+    ctl->mag_final = ctl->mag_last_buf;
+    ctl->final_emitted = 0;
+    ctl->not_converged = 1;
+  }
+}
+__global__ void clear_stall_kernel(Ctl* ctl) {
+  ctl->stalled = 0;
+  ctl->done = 0;
 }
 
 // the same condition for slab ranks, on norms that were all-reduced across ranks (amx_magnetic_check)
@@ -966,85 +990,107 @@ int read_ctl(Engine& E, Ctl** out) {
   return AMX_OK;
 }
 
-// One full step state_in -> state_out (views of nv rows) with dt already in ctl.
-// evolve_state.py:497-600.  kspec = fixed-point launches to enqueue before the host looks.
-int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
+// One full step state_in -> state_out (views of nv rows) with dt already in ctl: evolve_state.py:497-600.
+// MHD is Strang: hydro(dt/2) on the gas rows . magnetic(dt) . hydro(dt/2); the step is enqueued in two parts
+// around the fixed point so that amx_integrate can keep the device fed without looking at it.
+struct StepPlan {
+  View A, G, Gf, Bin, Bout, X[2];
+  bool pairs = false, emit_ok = false;
+  int expect = 1;
+  int c = 0, nl = 0;  // evaluations / launches enqueued so far in this step
+};
+
+// one fixed-point launch (_magnetic_field_update.py:82-205) + the device-side while-condition.  Launch number L
+// writes iterate buffer X[L & 1]; launches past convergence exit at once.
+int fp_enqueue(Engine& E, StepPlan& P, bool pair) {
+  const View* src = P.nl == 0 ? nullptr : &P.X[(P.nl - 1) & 1];
+  const View& dst = P.X[P.nl & 1];
+  if (pair) {
+    // The pair launch expected to end the loop also writes the write-back of its result (gas -> Gf, B -> the
+    // output state), which saves the separate mag_final pass (18 words per cell) whenever the expectation holds
+    const bool emit = P.emit_ok && P.c + 2 == P.expect;
+    CK(E.mag_pair(P.Bin, P.G, src, dst, E.dt_ptr(), P.c, emit ? &P.Gf : nullptr, emit ? &P.Bout : nullptr));
+    CK(E.mag_check_fused(P.c, 2, P.nl & 1, emit ? 1 : 0));
+    CK(E.mag_fix(P.Bin, P.G, src, dst, E.dt_ptr(), P.c));
+    P.c += 2;
+  } else {
+    CK(E.mag_iter(P.Bin, P.G, src, dst, E.dt_ptr(), P.nl, true));
+    CK(E.mag_check_fused(P.c, 1, P.nl & 1));
+    P.c += 1;
+  }
+  ++P.nl;
+  return AMX_OK;
+}
+
+// first part: hydro half step and the fixed-point launches the previous step needed (*kspec evaluations, as pair
+// launches where the kernel supports the problem, amx_pair.cu) plus `slack` more launches
+int step_front(Engine& E, const View& sin, const View& sout, int kspec, int slack, StepPlan& P) {
   const amx_desc* d = E.d;
   const Layout& L = E.L;
-  const View A = E.internal(L.off_A), G = E.internal(L.off_G);
+  P.A = E.internal(L.off_A);
+  P.G = E.internal(L.off_G);
   if (!d->mhd) {
-    CK(E.hydro(sin, sout, A, G, 1.0, true));
+    CK(E.hydro(sin, sout, P.A, P.G, 1.0, true));
     return AMX_OK;
   }
-  // Strang: hydro(dt/2) on the gas rows . magnetic(dt) . hydro(dt/2)
-  const View X[2] = {E.internal(L.off_X[0]), E.internal(L.off_X[1])};
-  const View Gf = E.internal(L.off_Gf);
-  const View Bin = rows_of(sin, L.ng, L.esz), Bout = rows_of(sout, L.ng, L.esz);
-  // second half-step needs two scratch buffers besides G: A and the gas rows of ... X is free by then
-  CK(E.hydro(sin, G, A, X[0], 0.5, false));
-  // Fixed point (_magnetic_field_update.py:82-205).  *kspec = evaluations the previous step needed:
-  // that many are enqueued (as pair launches where the kernel supports the problem, amx_pair.cu)
-  // plus one launch of slack, every launch followed by the device-side while-condition; launches
-  // past convergence exit at once.  Launch number L writes iterate buffer X[L & 1].
-  const bool pairs = E.pair_supported(E.mag_args(Bin, G, nullptr, X[0], E.dt_ptr(), 0, true));
-  // The pair launch expected to end the loop also writes the write-back of its result (gas -> Gf,
-  // B -> the output state), which saves the separate mag_final pass (18 words per cell) whenever
-  // the expectation holds; Lax-Friedrichs / PP need the wave bounds of the written-back gas and
-  // keep mag_final.  AMX_NO_EMIT=1 switches it off.
+  P.X[0] = E.internal(L.off_X[0]);
+  P.X[1] = E.internal(L.off_X[1]);
+  P.Gf = E.internal(L.off_Gf);
+  P.Bin = rows_of(sin, L.ng, L.esz);
+  P.Bout = rows_of(sout, L.ng, L.esz);
+  // the second half step needs two scratch buffers besides G: A and the gas rows of ... X is free by then
+  CK(E.hydro(sin, P.G, P.A, P.X[0], 0.5, false));
+  P.pairs = E.pair_supported(E.mag_args(P.Bin, P.G, nullptr, P.X[0], E.dt_ptr(), 0, true));
+  // Lax-Friedrichs / PP need the wave bounds of the written-back gas and keep mag_final.  AMX_NO_EMIT=1: off.
   static const bool no_emit = [] { const char* e = getenv("AMX_NO_EMIT"); return e && e[0] == '1'; }();
-  bool emit_ok = pairs && !E.lf && !no_emit && !E.shell_on;
-  if (emit_ok) {
-    MagIterArgs probe = E.mag_args(Bin, G, nullptr, X[0], E.dt_ptr(), 0, true);
-    probe.emit = 1; probe.emit_gas = Gf; probe.emit_B = Bout;
-    emit_ok = E.pair_supported(probe);
+  P.emit_ok = P.pairs && !E.lf && !no_emit && !E.shell_on;
+  if (P.emit_ok) {
+    MagIterArgs probe = E.mag_args(P.Bin, P.G, nullptr, P.X[0], E.dt_ptr(), 0, true);
+    probe.emit = 1; probe.emit_gas = P.Gf; probe.emit_B = P.Bout;
+    P.emit_ok = E.pair_supported(probe);
   }
-  const int expect = std::max(1, *kspec);
-  int c = 0, nl = 0;  // evaluations / launches enqueued
-  auto enqueue = [&](bool pair) -> int {
-    const View* src = nl == 0 ? nullptr : &X[(nl - 1) & 1];
-    const View& dst = X[nl & 1];
-    if (pair) {
-      const bool emit = emit_ok && c + 2 == expect;
-      CK(E.mag_pair(Bin, G, src, dst, E.dt_ptr(), c, emit ? &Gf : nullptr, emit ? &Bout : nullptr));
-      CK(E.mag_check_fused(c, 2, nl & 1, emit ? 1 : 0));
-      CK(E.mag_fix(Bin, G, src, dst, E.dt_ptr(), c));
-      c += 2;
-    } else {
-      CK(E.mag_iter(Bin, G, src, dst, E.dt_ptr(), nl, true));
-      CK(E.mag_check_fused(c, 1, nl & 1));
-      c += 1;
-    }
-    ++nl;
-    return AMX_OK;
-  };
+  P.expect = std::max(1, kspec);
+  P.c = P.nl = 0;
   int rc;
-  while (c < expect)
-    if ((rc = enqueue(pairs && (expect - c >= 2 || pair_greedy())))) return rc;
-  if ((rc = enqueue(pairs))) return rc;  // slack
-  // AMX_NOSYNC=1 (measurement only): trust the expected count and never look -- shows what the
-  // per-step host round trip costs
-  static const bool nosync = [] { const char* e = getenv("AMX_NOSYNC"); return e && e[0] == '1'; }();
-  if (nosync) {
-    CK(E.mag_final(G, Gf, Bout, X, -1, E.lf, nullptr, true));
-    if (E.shell_on && d->split == AMX_UNSPLIT) CK(E.shell(1, E.shell_src, E.shell_dst, &G, nullptr, X, false, true));
-    CK(E.hydro(Gf, sout, A, X[0], 0.5, true));
-    return AMX_OK;
-  }
+  while (P.c < P.expect)
+    if ((rc = fp_enqueue(E, P, P.pairs && (P.expect - P.c >= 2 || pair_greedy())))) return rc;
+  for (int k = 0; k < slack; ++k)
+    if ((rc = fp_enqueue(E, P, P.pairs))) return rc;
+  return AMX_OK;
+}
+
+// second part: write-back, ghost shell, hydro half step
+int step_back(Engine& E, const View& sout, StepPlan& P) {
+  const amx_desc* d = E.d;
+  if (!d->mhd) return AMX_OK;
+  CK(E.mag_final(P.G, P.Gf, P.Bout, P.X, -1, E.lf, nullptr, true));
+  if (E.shell_on && d->split == AMX_UNSPLIT) CK(E.shell(1, E.shell_src, E.shell_dst, &P.G, nullptr, P.X, false, true));
+  // X buffers are free again: reuse X[0] rows as sweep scratch
+  CK(E.hydro(P.Gf, sout, P.A, P.X[0], 0.5, true));
+  return AMX_OK;
+}
+
+// the host looks until the fixed point has ended (one round trip per extra launch): the slow path of a step whose
+// enqueued launches did not suffice, and amx_step with stats
+int fp_finish_blocking(Engine& E, StepPlan& P, int* kspec) {
   Ctl* m;
-  rc = read_ctl(E, &m);
+  int rc = read_ctl(E, &m);
   if (rc) return rc;
   while (m->mag_active && !m->done) {
-    if ((rc = enqueue(pairs))) return rc;
-    if (!pairs && (rc = enqueue(false))) return rc;
-    rc = read_ctl(E, &m);
-    if (rc) return rc;
+    if ((rc = fp_enqueue(E, P, P.pairs))) return rc;
+    if (!P.pairs && (rc = fp_enqueue(E, P, false))) return rc;
+    if ((rc = read_ctl(E, &m))) return rc;
   }
   if (!m->done) *kspec = m->mag_iter + 1;
-  CK(E.mag_final(G, Gf, Bout, X, -1, E.lf, nullptr, true));
-  if (E.shell_on && d->split == AMX_UNSPLIT) CK(E.shell(1, E.shell_src, E.shell_dst, &G, nullptr, X, false, true));
-  // X buffers are free again: reuse X[0] rows as sweep scratch
-  CK(E.hydro(Gf, sout, A, X[0], 0.5, true));
   return AMX_OK;
+}
+
+int run_step(Engine& E, const View& sin, const View& sout, int* kspec) {
+  StepPlan P;
+  int rc = step_front(E, sin, sout, *kspec, 1, P);
+  if (rc) return rc;
+  if (E.d->mhd && (rc = fp_finish_blocking(E, P, kspec))) return rc;
+  return step_back(E, sout, P);
 }
 
 int check_common(const amx_desc* d, const void* a, const void* b) {
@@ -1191,7 +1237,23 @@ int amx_step(const amx_desc* d, const void* seam_in, void* seam_out, const void*
     E.shell_dst = sout;
   }
   int kspec = d->dtype == AMX_F32 ? 4 : 8;  // first guess of the evaluations per step
-  if ((rc = run_step(E, sin, sout, &kspec))) return rc;
+  if (stats || !d->mhd) {
+    if ((rc = run_step(E, sin, sout, &kspec))) return rc;  // (MHD: the host looks at the fixed point)
+  } else {
+    // No stats wanted: a fixed budget of fixed-point launches (launches past convergence exit at once) and no
+    // host round trip, so the call is a pure stream of launches -- it can be captured into a CUDA graph / XLA
+    // command buffer.  A fixed point that is still iterating when the budget is spent (the
+    // reference would go on, up to 1000 iterations) raises the sticky not_converged flag, which
+    // amx_magnetic_state reports; AMX_STEP_EVALS sets the budget (default 12 evaluations in fp32, 24 in fp64).
+    static const int budget_env = [] { const char* e = getenv("AMX_STEP_EVALS"); return e ? atoi(e) : 0; }();
+    const int budget = budget_env > 0 ? budget_env : (d->dtype == AMX_F32 ? 12 : 24);
+    StepPlan P;
+    if ((rc = step_front(E, sin, sout, budget, 0, P))) return rc;
+    ++E.launches;
+    mag_guard_kernel<<<1, 1, 0, E.st>>>(E.ctl, 1);
+    CK(cudaGetLastError());
+    if ((rc = step_back(E, sout, P))) return rc;
+  }
   if (d->boundary_handling == AMX_GHOST_CELLS) {
     // ghosts of the result: what the reference's trailing _boundary_handler calls leave behind (shell
     // mode: the gas ghosts are the shell and are already in place)
@@ -1276,12 +1338,36 @@ int amx_integrate_from(const amx_desc* d, const void* unpadded_in, void* unpadde
     else set_time_kernel<double><<<1, 1, 0, E.st>>>(E.ctl, t_start);
     CK(cudaGetLastError());
   }
+  // Speculative pipeline: the host never waits for the device inside a step.  Every step is enqueued whole --
+  // begin, hydro half step, as many fixed-point launches as the previous step needed (+ slack), a guard, the
+  // write-back, the second half step, end -- and a copy of the control block taken after the guard is looked at
+  // one step (hydro: one batch of 8 steps) LATER, when the device already has the next step queued.  The look
+  // tells (a) how many evaluations the step needed (next steps enqueue that many), (b) whether the time loop has
+  // ended (everything enqueued since was a no-op), (c) whether the guard found the fixed point still iterating
+  // (`stalled`: it raised `done`, so everything behind it was a no-op too): then the host clears the flags, adds
+  // launches with a look after each (the slow path) and re-enqueues from that step on.
+  static thread_local std::unordered_map<const void*, int> kspec_hint;  // evaluations per step of the last run on ws
   int kspec = d->dtype == AMX_F32 ? 4 : 8;  // first guess of the evaluations per step
+  {
+    auto it = kspec_hint.find(ws);
+    if (d->mhd && it != kspec_hint.end()) kspec = it->second;
+  }
   long long issued = 0;
-  const int lookahead = d->mhd ? 1 : 8;  // hydro steps enqueued between host looks at the loop state
+  const int batch = d->mhd ? 1 : 8;  // steps between two copies of the control block
+  constexpr int kRing = 4;
+  static thread_local Ctl* ring = nullptr;
+  static thread_local cudaEvent_t ring_ev[kRing];
+  if (!ring) {
+    CK(cudaMallocHost(&ring, kRing * sizeof(Ctl)));
+    for (int k = 0; k < kRing; ++k) CK(cudaEventCreateWithFlags(&ring_ev[k], cudaEventDisableTiming));
+  }
+  auto head = [&](int slot) { return reinterpret_cast<Ctl*>(reinterpret_cast<char*>(ring) + (size_t)slot * sizeof(Ctl)); };
+  long long snaps = 0, looked = 0;  // copies enqueued / looked at
   Ctl* m = nullptr;
-  for (;;) {
-    for (int k = 0; k < lookahead; ++k, ++issued) {
+  bool ended = false;
+  while (!ended) {
+    StepPlan P;
+    for (int k = 0; k < batch; ++k, ++issued) {
       ++E.launches;
       if (E.is32) step_begin_kernel<float><<<1, 1, 0, E.st>>>(E.ctl, p, (long long)max_steps);
       else step_begin_kernel<double><<<1, 1, 0, E.st>>>(E.ctl, p, (long long)max_steps);
@@ -1291,16 +1377,67 @@ int amx_integrate_from(const amx_desc* d, const void* unpadded_in, void* unpadde
       // Lax-Friedrichs / PP stages want those of the ghost-FILLED state, i.e. of the interior
       // (also on the first step of a resumed segment, whose initial bounds include the carried shell)
       if (E.shell_on && E.lf) CK(E.alpha_of(sin, nullptr, true));
-      if ((rc = run_step(E, sin, S[issued & 1], &kspec))) return rc;
+      if ((rc = step_front(E, sin, S[issued & 1], kspec, 1, P))) return rc;
+      if (d->mhd) {
+        ++E.launches;
+        mag_guard_kernel<<<1, 1, 0, E.st>>>(E.ctl, 0);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(head((int)(snaps % kRing)), E.ctl, kCtlHead, cudaMemcpyDeviceToHost, E.st));
+        CK(cudaEventRecord(ring_ev[snaps % kRing], E.st));
+        ++snaps;
+      }
+      if ((rc = step_back(E, S[issued & 1], P))) return rc;
       ++E.launches;
       if (E.is32) step_end_kernel<float><<<1, 1, 0, E.st>>>(E.ctl);
       else step_end_kernel<double><<<1, 1, 0, E.st>>>(E.ctl);
       CK(cudaGetLastError());
     }
-    if ((rc = read_ctl(E, &m))) return rc;
-    if (m->done || !(m->time_d < p.t_end) || !(m->time_d < p.t_stop) || (max_steps >= 0 && m->steps >= max_steps))
-      break;
+    if (!d->mhd) {
+      CK(cudaMemcpyAsync(head((int)(snaps % kRing)), E.ctl, kCtlHead, cudaMemcpyDeviceToHost, E.st));
+      CK(cudaEventRecord(ring_ev[snaps % kRing], E.st));
+      ++snaps;
+    }
+    // look at every copy but the newest (whose step the device is still working on)
+    while (looked + 1 < snaps && !ended) {
+      CK(cudaEventSynchronize(ring_ev[looked % kRing]));
+      const Ctl* c = head((int)(looked % kRing));
+      ++looked;
+      if (c->stalled) {
+        // the fixed point of step c->steps needs more launches than it was given
+        CK(cudaStreamSynchronize(E.st));
+        if ((rc = read_ctl(E, &m))) return rc;
+        const long long s_idx = m->steps;  // the stalled step (0-based) = steps completed so far
+        ++E.launches;
+        clear_stall_kernel<<<1, 1, 0, E.st>>>(E.ctl);
+        CK(cudaGetLastError());
+        const View& sin = s_idx == 0 ? vin : S[(s_idx - 1) & 1];
+        StepPlan R;
+        // the plan of the stalled step, without enqueuing anything: its buffers and where the fixed point stands
+        R.A = E.internal(L.off_A); R.G = E.internal(L.off_G); R.Gf = E.internal(L.off_Gf);
+        R.X[0] = E.internal(L.off_X[0]); R.X[1] = E.internal(L.off_X[1]);
+        R.Bin = rows_of(sin, L.ng, L.esz); R.Bout = rows_of(S[s_idx & 1], L.ng, L.esz);
+        R.pairs = E.pair_supported(E.mag_args(R.Bin, R.G, nullptr, R.X[0], E.dt_ptr(), 0, true));
+        R.emit_ok = false;
+        R.c = m->mag_iter;                // evaluations completed: every one that kept the loop going counted itself
+        R.nl = (m->mag_last_buf ^ 1) | 2;  // next launch writes the other buffer; never "launch 0"
+        R.expect = 1 << 30;
+        if ((rc = fp_finish_blocking(E, R, &kspec))) return rc;
+        if ((rc = step_back(E, S[s_idx & 1], R))) return rc;
+        ++E.launches;
+        if (E.is32) step_end_kernel<float><<<1, 1, 0, E.st>>>(E.ctl);
+        else step_end_kernel<double><<<1, 1, 0, E.st>>>(E.ctl);
+        CK(cudaGetLastError());
+        issued = s_idx + 1;
+        looked = snaps;  // the later copies belong to launches that did nothing
+      } else if (c->done) {
+        ended = true;
+      } else if (d->mhd) {
+        kspec = c->mag_iter + 1;
+      }
+    }
   }
+  if ((rc = read_ctl(E, &m))) return rc;
+  if (d->mhd) kspec_hint[ws] = kspec;
   // a step that found the loop finished wrote nothing: the state lives where step `steps` put it
   const long long steps = m->steps;
   const size_t bytes = (size_t)L.cells * L.esz;
@@ -1579,6 +1716,7 @@ int amx_peer_push_supported(const amx_desc* d) {
   if (d->split == AMX_UNSPLIT && !force_generic() && !no_vec()) {
     StageArgs a{};
     a.g = E.g; a.np = E.np; a.in = a.in0 = a.out = v;
+    a.alpha_lf = reinterpret_cast<const void*>(uintptr_t(256));
     if (E.strict ? amx_strict::vec_stage_supported(a) : amx_fast::vec_stage_supported(a)) bits |= 1;
   }
   if (d->mhd) {

@@ -87,6 +87,10 @@ struct Ctl {
   int mag_fix;               // the loop ended on the FIRST evaluation of pair launch `mag_fix_base`:
   int mag_fix_base;          //   that evaluation is re-run alone (evaluations completed before the pair)
   int final_emitted;         // the pair launch that ended the loop already wrote the write-back (amx_pair.cu EMIT)
+  int mag_last_buf;          // iterate buffer the latest fixed-point launch wrote (while the loop is still active)
+  int stalled;               // the launches enqueued for this step's fixed point did not suffice: `done` was raised
+                             // with it, so everything enqueued behind exits at once; the host clears both, adds
+                             // launches and resumes the step (amx_integrate's speculative pipeline)
   long long steps;
   long long mag_iters_total;
   long long pair_runs, single_runs;  // fixed-point launches that did work (bench.py byte accounting)

@@ -420,8 +420,26 @@ def test_vec_hydro_stage_equals_generic_bitwise_in_strict_mode(cuda, dim, n, bnd
     assert np.array_equal(skewed, generic)
 
 
+@pytest.mark.parametrize("dim,n,bnd", [(3, 32, "periodic"), (3, 48, "reflective"), (2, 512, "open")])
+def test_vec_lax_friedrichs_stage_equals_generic_bitwise_in_strict_mode(cuda, dim, n, bnd):
+    """hydro_stage_vec<RS_LF> (global alpha per axis from the control block) against the generic kernel."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r);"
+        "from astronomix_b200 import problems as pr, stepping as ti, _lib, option_classes as oc;"
+        "s = pr.smooth_random(%d, %d, seed=9, dtype=np.float32);"
+        "c, p, rv = pr.make(%d, %d, boundaries=%r, riemann_solver=oc.LAX_FRIEDRICHS, limiter=oc.MINMOD);"
+        "out = ti.integrate_steps(s, c, p, rv, 3, arithmetic=_lib.AMX_ARITH_STRICT);"
+        "np.save(sys.argv[1], out)"
+    ) % (root, dim, n, dim, n, bnd)
+    vec, generic = _run_subprocess_variants(code, [{}, {"AMX_FORCE_GENERIC": "1"}])
+    assert np.isfinite(vec).all()
+    assert np.array_equal(vec, generic)
+
+
 @pytest.mark.parametrize("arith", ["fast", "strict"])
-@pytest.mark.parametrize("dim,n,rs", [(3, 64, oc.HLLC), (2, 512, oc.HLLC), (3, 32, oc.HLL)])
+@pytest.mark.parametrize("dim,n,rs", [(3, 64, oc.HLLC), (2, 512, oc.HLLC), (3, 32, oc.HLL), (3, 48, oc.LAX_FRIEDRICHS)])
 def test_vec_hydro_fp32_vs_oracle(cuda, dim, n, rs, arith):
     s = pr.smooth_random(dim, n, seed=61 + dim, dtype=np.float32)
     config, params, rv = pr.make(dim, n, riemann_solver=rs)
