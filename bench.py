@@ -295,6 +295,9 @@ def run_native(args):
         kernels["magnetic_iter"]["launches_with_work"] = singles
         first = 0 if pairs else K
         alg["magnetic_iter"] = (first * 13 + (singles - first) * 19) / singles * w * cells
+    if "hydro_stage" in kernels:
+        # the speculative pipeline enqueues a step or two past the end of the run; those launches exit at once
+        kernels["hydro_stage"]["launches_with_work"] = 4 * K
     alg["magnetic_final"] = (6 + ng + ng + 3) * w * cells  # reads iterate + gas, writes gas (rho, v, p) + B
     if "magnetic_final" in kernels:
         # write-back launches pre-empted by an emitting pair launch exit at once
