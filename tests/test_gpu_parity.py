@@ -671,3 +671,33 @@ def test_fused_forcing_kernels_equal_the_torch_formulation(cuda, dtype, tol):
         fb.apply(b, dt, gen(step))
         assert pr.rel_l1(a.cpu().numpy(), b.cpu().numpy(), 3, True) <= tol
     assert float((a[1:4] - s[1:4]).abs().max()) > 0
+
+
+def test_mhd_step_is_capturable_in_a_cuda_graph(cuda):
+    """amx_step without a stats pointer is a pure stream of launches (fixed budget of guarded fixed-point
+    launches, no host round trip): captured once into a CUDA graph and replayed on new inputs it gives what the
+    eager call gives -- which is what an XLA command buffer does with the jax.ffi custom call."""
+    import torch
+    n = 32
+    config, params, rv = pr.make(3, n, mhd=True)
+    helper = ax.get_helper_data(config)
+    states = [torch.from_numpy(pr.smooth_random(3, n, mhd=True, seed=k, dtype=np.float32)).to(cuda) for k in (3, 4)]
+    pad = [ti._boundary_handler(ti._pad(s, config), config) for s in states]
+    dts = [ti._cfl_time_step(p, config.grid_spacing, params.dt_max, params.gamma, config, rv, params.C_cfl) for p in pad]
+    eager = [ti._evolve_state_fv(p, dt, params.gamma, 0.0, config, params, helper, rv) for p, dt in zip(pad, dts)]
+    s_in, dt_in = pad[0].clone(), dts[0].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # warm-up on the capture stream: shared-memory opt-ins, workspace
+        ti._evolve_state_fv(s_in, dt_in, params.gamma, 0.0, config, params, helper, rv)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = ti._evolve_state_fv(s_in, dt_in, params.gamma, 0.0, config, params, helper, rv)
+    for k in (1, 0, 1):
+        s_in.copy_(pad[k])
+        dt_in.copy_(dts[k])
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, eager[k])
