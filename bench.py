@@ -464,16 +464,19 @@ def secondary_configs(lib, dev, hbm_peak):
     c, p, rv = pr.make(2, 2048, mhd=True, box=2 * np.pi)
     run("C3_orszag_tang_2048", "C3 Orszag-Tang 2048^2 MHD (Pang-Wu), HLL, RK2 (state 117 MB: about L2 size)",
         pr.orszag_tang(2048, np.float32), c, p, 40, 5, lambda it: (10 * 4 + 13 + 19 * it) * w)
-    # the published benchmark (2.97e8 cell-updates/s at 256^3, 3.11e8 at 512^3 on H200, jax):
-    # arena/fv_mhd.py:36-49 -- LAX_FRIEDRICHS, PERIODIC_ROLL, C_cfl 0.8 (limiter here: minmod)
-    for nn, pub in ((256, 2.97e8),):
+    # the published benchmark, like for like (2.97e8 cell-updates/s at 256^3, 3.11e8 at 512^3 on H200,
+    # jax): arena/fv_mhd.py:36-49 -- LAX_FRIEDRICHS, PERIODIC_ROLL, C_cfl 0.8, the default limiter (minmod), single
+    # precision; arena_tests/scaling/scaling.py:108-130 -- blast with p 100 : 1 inside r 0.125, B0 = 10
+    for nn, pub, steps in ((256, 2.97e8, 10), (512, 3.11e8, 4)):
         c, p, rv = pr.make(3, nn, mhd=True, riemann_solver=oc.LAX_FRIEDRICHS, boundary_handling=oc.PERIODIC_ROLL)
         p = p._replace(C_cfl=0.8)
-        run(f"published_flux_lf_{nn}", f"3-D MHD blast {nn}^3, LAX_FRIEDRICHS + PERIODIC_ROLL + C_cfl 0.8 (the flux of "
-            "the reference's published fv_mhd benchmark), minmod",
-            pr.mhd_blast3d(nn, np.float32, p_in=100.0, p_out=1.0, B0=10.0, r_inj=0.125), c, p, 10, 3,
+        s0 = torch.empty((8, nn, nn, nn), dtype=torch.float32, device=dev)
+        blast_on_device(s0, nn, p_in=100.0, p_out=1.0, r_inj=0.125, B0=10.0)
+        run(f"published_config_lf_{nn}", f"3-D MHD blast {nn}^3 in the configuration of the reference's published fv_mhd "
+            "benchmark: LAX_FRIEDRICHS, minmod, PERIODIC_ROLL, C_cfl 0.8, fp32", s0, c, p, steps, 2,
             lambda it: (10 * 5 + 13 + 19 * it) * w,
             published={"value": pub, "unit": UNIT, "hardware": "H200, jax (BASELINE.md)", "note": "other hardware"})
+        del s0
     c, p, rv = pr.make(3, 256, mhd=True, split=oc.SPLIT, time_integrator=oc.MUSCL)
     run("C4_split_muscl_256", "C4 variant: 3-D MHD blast 256^3, Strang-split MUSCL-Hancock sweeps",
         pr.mhd_blast3d(256, np.float32), c, p, 5, 2, lambda it: (2 * 5 * 2 * 5 + 13 + 19 * it) * w)
@@ -486,10 +489,10 @@ def secondary_configs(lib, dev, hbm_peak):
     return out
 
 
-def blast_on_device(s, n, p_in=1000.0, p_out=0.1, r_inj=0.1):
+def blast_on_device(s, n, p_in=1000.0, p_out=0.1, r_inj=0.1, B0=None):
     """problems.mhd_blast3d(n) built on the device (512^3 is 4.3 GB: not worth a host array)."""
     import torch
-    B0 = 100 / np.sqrt(4 * np.pi)
+    B0 = 100 / np.sqrt(4 * np.pi) if B0 is None else B0
     c = (torch.arange(n, device=s.device, dtype=torch.float64) + 0.5) / n - 0.5
     c2 = c * c
     r2 = c2[:, None, None] + c2[None, :, None] + c2[None, None, :]
