@@ -114,6 +114,7 @@ PROTOTYPES = {
     "amx_forcing_spectrum": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                        C.c_double, _P, C.c_int, C.c_int, _P]),
     "amx_forcing_sums": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int, _P]),
+    "amx_shell_update": (C.c_int, [_D, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "amx_peer_push_supported": (C.c_int, [_D]),
     "amx_peer_comm_bytes": (C.c_size_t, []),
     "amx_peer_allreduce_max": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, _P, C.c_int, C.c_int, _P]),

@@ -1705,6 +1705,29 @@ int amx_magnetic_state(const amx_desc* d, void* ws, void* stream, int32_t* activ
   return AMX_OK;
 }
 
+int amx_shell_update(const amx_desc* d, int mode, void* shell_inout, const void* u0, const void* u1, const void* bv0,
+                     const void* bv1, void* alpha_out, void* ws, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!shell_inout || !ws) return fail(AMX_EINVAL, "null pointer");
+  if (mode < 0 || mode > 3) return fail(AMX_EINVAL, "shell mode must be 0 .. 3");
+  if ((mode == 0 && (!u0 || !u1)) || (mode == 1 && (!u0 || !bv0 || !bv1)) || (mode == 3 && !u1))
+    return fail(AMX_EINVAL, "shell update: missing input array for this mode");
+  if ((rc = amx_device_check())) return rc;
+  Engine E(d, ws, stream);
+  int pad[3] = {0, 0, 0};
+  for (int a = 0; a < d->ndim; ++a) pad[a] = d->num_ghost;
+  const View sh = make_view(shell_inout, d, pad, 0, 0);
+  View v0 = sh, v1 = sh, X[2] = {sh, sh};
+  if (u0) v0 = E.user_internal(u0);
+  if (u1) v1 = E.user_internal(u1);
+  if (bv0) X[0] = E.user_internal(bv0);
+  if (bv1) X[1] = E.user_internal(bv1);
+  CK(E.shell(mode, sh, sh, &v0, &v1, X, alpha_out != nullptr, false));
+  if (alpha_out) CK(E.finalize_alpha(alpha_out, false));
+  return AMX_OK;
+}
+
 int amx_peer_push_supported(const amx_desc* d) {
   if (validate(d)) return 0;
   if (d->bc[0][0] != AMX_BC_HALO && d->bc[0][1] != AMX_BC_HALO) return 0;

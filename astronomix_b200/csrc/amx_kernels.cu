@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(256) shell_kernel(const ShellArgs a) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) { e[k] = k < ND ? a.g.n[k] + 2 * a.ng : 1; tot *= e[k]; }
   const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool ghost = false;
+  bool ghost = false, halo = false;
   if (lin < tot) {
     long long r = lin;
     Idx3 gi, si;
@@ -692,11 +692,14 @@ __global__ void __launch_bounds__(256) shell_kernel(const ShellArgs a) {
         gi.i[k] -= a.ng;
         si.i[k] = map_index<ND>(gi.i[k], a.g.n[k], a.g.bc[k][0], a.g.bc[k][1], flip[k]);
         ghost = ghost || gi.i[k] < 0 || gi.i[k] >= a.g.n[k];
+        // slab rank: the planes beyond a BC_HALO side are the neighbour's cells (and its shell), not ghost cells
+        if ((gi.i[k] < 0 && a.g.bc[k][0] == BC_HALO) || (gi.i[k] >= a.g.n[k] && a.g.bc[k][1] == BC_HALO)) halo = true;
       } else {
         gi.i[k] = 0;
         si.i[k] = 0;
       }
     }
+    if (halo) ghost = false;
     if (ghost) {
       bool jet = false;  // MHD jet inflow cell: its fills are constants, not images
       if constexpr (ND == 2) jet = jet_cell(a.g, gi.i[0], gi.i[1]);

@@ -1167,7 +1167,7 @@ bool vec_stage_supported(const StageArgs& a) {
   }
   if (a.g.n[0] < 4 || (a.g.n[nd - 1] & 1) || a.g.n[nd - 1] < 8) return false;
   if (nd == 3 && a.g.n[1] < 4) return false;
-  if (a.np.rs != RS_HLL && a.np.rs != RS_HLLC && a.np.rs != RS_LF) return false;
+  if (a.np.rs != RS_HLL && a.np.rs != RS_HLLC && a.np.rs != RS_LF && a.np.rs != RS_HLLC_LM) return false;
   if (a.np.rs == RS_LF && !a.alpha_lf) return false;
   return true;
 }
@@ -1186,10 +1186,12 @@ cudaError_t launch_hydro_stage_vec(const StageArgs& a, cudaStream_t st) {
   // alpha of each axis comes in through StageArgs::alpha_lf)
   if (a.g.nd == 3) {
     if (a.np.rs == RS_LF) return launch_stage_vec_l<3, RS_LF>(a, st);
+    if (a.np.rs == RS_HLLC_LM) return launch_stage_vec_l<3, RS_HLLC_LM>(a, st);
     return a.np.rs == RS_HLL ? launch_stage_vec_l<3, RS_HLL>(a, st) : launch_stage_vec_l<3, RS_HLLC>(a, st);
   }
   if (a.g.nd == 2) {
     if (a.np.rs == RS_LF) return launch_stage_vec_l<2, RS_LF>(a, st);
+    if (a.np.rs == RS_HLLC_LM) return launch_stage_vec_l<2, RS_HLLC_LM>(a, st);
     return a.np.rs == RS_HLL ? launch_stage_vec_l<2, RS_HLL>(a, st) : launch_stage_vec_l<2, RS_HLLC>(a, st);
   }
   return cudaErrorInvalidValue;

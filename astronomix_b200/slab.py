@@ -59,6 +59,12 @@ class AmxBackend:
     def _s(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    def shell_update(self, mode, shell, u0=None, u1=None, bv0=None, bv1=None, alpha_out=None):
+        """ghost shell of the gas state on this rank (include/amx.h amx_shell_update)"""
+        _lib.check(self.lib.amx_shell_update(C.byref(self.desc), int(mode), self._p(shell), self._p(u0), self._p(u1),
+                                             self._p(bv0), self._p(bv1), self._p(alpha_out), self.ws_ptr, self._s()))
+        self.launches += 2 if alpha_out is not None else 1
+
     # ---- peer memory (include/amx.h "peer-memory plumbing")
     def set_peers(self, flags, delta_lo, delta_hi):
         """Arrays handed to the stage entry points from now on live in peer-mapped memory: kernels also
@@ -184,12 +190,10 @@ class SlabDriver:
         codes = oc.boundary_codes(config)
         if any(oc.MHD_JET_BOUNDARY in codes[a] for a in range(self.dim)):
             raise NotImplementedError("slab decomposition with the MHD jet boundary is not built")
-        if (config.mhd and config.split == oc.UNSPLIT and config.boundary_handling == oc.GHOST_CELLS
-                and any(oc.REFLECTIVE_BOUNDARY in codes[a] for a in range(self.dim))):
-            # the reference's ghost gas cells set dt in this configuration (DESIGN.md "ghost shell");
-            # the single-GPU library carries them, the slab loop does not yet
-            raise NotImplementedError("slab decomposition of unsplit MHD with a reflective side is not built: "
-                                      "the ghost shell that enters the CFL reduction lives in amx_integrate only")
+        # the reference's ghost gas cells set dt in this configuration (DESIGN.md "ghost shell"): every rank
+        # carries the shell of its own cells (y / z faces of its x range, the x faces on the edge ranks)
+        self.shell_mode = (config.mhd and config.split == oc.UNSPLIT and config.boundary_handling == oc.GHOST_CELLS
+                           and any(oc.REFLECTIVE_BOUNDARY in codes[a] for a in range(self.dim)))
         self.dtype, self.device = dtype, device
         self.ng = self.dim + 2
         self.nv = registered_variables.num_vars
@@ -282,6 +286,13 @@ class SlabDriver:
                 self._comm = None
                 self.push = 0
         self.forcing = None  # forcing.SlabForcing: turbulent driving between dt and the step
+        self.shell = None
+        if self.shell_mode:
+            if not hasattr(self.backend, "shell_update"):
+                raise NotImplementedError("this backend does not carry the ghost shell (unsplit MHD with a reflective side)")
+            self.shell = torch.zeros((self.ng, self.nxl + 2 * NG) + tuple(v + 2 * NG for v in self.global_n[1:]),
+                                     dtype=dtype, device=device)
+            self.alpha_shell = torch.zeros(3, dtype=dtype, device=device)
         self.alpha = torch.zeros(3, dtype=dtype, device=device)
         self.change = torch.zeros(2, dtype=dtype, device=device)
         self.change4 = torch.zeros(4, dtype=dtype, device=device)
@@ -484,6 +495,7 @@ class SlabDriver:
         self.S[0][:, NG:NG + self.nxl].copy_(loc)
         self.reset()
         self.time.zero_()
+        self._init_shell(self.S[0][: self.ng])
         self._alpha_of(self.S[0][: self.ng])
 
     def reset(self):
@@ -503,9 +515,17 @@ class SlabDriver:
         return torch.cat(parts, dim=1)
 
     # ------------------------------------------------------------------ step pieces
-    def _alpha_of(self, gas):
+    def _alpha_of(self, gas, with_shell=True):
         self.backend.alpha(gas, self.alpha)
+        if self.shell is not None and with_shell:
+            self.backend.shell_update(2, self.shell, alpha_out=self.alpha_shell)
+            torch.maximum(self.alpha, self.alpha_shell, out=self.alpha)
         self._allreduce_max(self.alpha)
+
+    def _init_shell(self, gas):
+        """time_integration.py:274-286: the padded initial state's ghost gas cells are images of interior cells"""
+        if self.shell is not None:
+            self.backend.shell_update(3, self.shell, u1=gas)  # (source cells are this rank's own active cells)
 
     def _stage_alpha(self, want):
         """alpha_out argument + all-reduce for kernels that also produce wave bounds"""
@@ -515,6 +535,10 @@ class SlabDriver:
         b = self.backend
         cfg = self.config
         if cfg.split == oc.UNSPLIT:
+            if self.shell is not None and self.lf:
+                # Lax-Friedrichs / PP stages want the bounds of the ghost-FILLED state, i.e. of the interior
+                # (self.alpha holds those of the padded array, which dt needed)
+                self._alpha_of(gas_in, with_shell=False)
             self.exchange(gas_in, flip_rows=(1,))
             b.hydro_stage(gas_in, None, self.A, self.dt, scale, self.alpha, self.alpha if self.lf else None)
             self._wrote(self.A, 1)
@@ -524,6 +548,11 @@ class SlabDriver:
             want = final_alpha or self.lf
             b.hydro_stage(self.A, gas_in, gas_out, self.dt, scale, self.alpha, self.alpha if want else None)
             self._wrote(gas_out, 1)
+            if self.shell is not None:
+                # evolve_state.py:456-469 at the ghost cells; the bounds the next CFL reads are those of the padded array
+                b.shell_update(0, self.shell, u0=gas_in, u1=gas_out, alpha_out=self.alpha_shell if final_alpha else None)
+                if final_alpha:
+                    torch.maximum(self.alpha, self.alpha_shell, out=self.alpha)
             if want:
                 self._allreduce_max(self.alpha)
             return
@@ -564,7 +593,7 @@ class SlabDriver:
                 # ends on the first of them, that one is re-run alone into the same buffer.  The
                 # launch expected to end the loop also writes the write-back of its result
                 # (gas -> Gf, B -> B_out), which makes magnetic_final a no-op when it does end there.
-                emit = self.pairs and not self.lf and c + 2 == self.expect_evals
+                emit = self.pairs and not self.lf and self.shell is None and c + 2 == self.expect_evals
                 b.magnetic_pair_guarded(B0, gas, src, dst, self.dt, self.change4, c,
                                         self.Gf if emit else None, B_out if emit else None)
                 self._wrote(dst, 2)
@@ -597,6 +626,8 @@ class SlabDriver:
         b.magnetic_final_guarded(gas, self.Gf, self.X[0], self.X[1], B_out, self.alpha if self.lf else None)
         self._wrote(self.Gf, 4)
         self._wrote(B_out, 4)
+        if self.shell is not None:  # _magnetic_field_update.py:208-240 at the ghost cells (Q12 flip rule)
+            b.shell_update(1, self.shell, u0=gas, bv0=self.X[0], bv1=self.X[1])
         if self.lf:
             self._allreduce_max(self.alpha)
         return it

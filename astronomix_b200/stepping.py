@@ -252,6 +252,7 @@ def _time_integration_sharded(primitive_state, config, params, registered_variab
         drv.S[0][:, NG:NG + drv.nxl].copy_(src.to(device))
         drv.reset()
         drv.time.zero_()
+        drv._init_shell(drv.S[0][: drv.ng])
         drv._alpha_of(drv.S[0][: drv.ng])
     else:
         drv.scatter(src)

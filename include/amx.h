@@ -252,6 +252,18 @@ AMX_API int amx_magnetic_fix_guarded(const amx_desc* d, const void* B0, const vo
 AMX_API int amx_magnetic_state(const amx_desc* d, void* ws, void* stream, int32_t* active_out,
                       int32_t* iterations_out);
 
+/* Ghost shell of the gas state on a slab rank: in unsplit MHD with a reflective side the
+ * reference's ghost gas cells follow their own recurrence (evolve_state.py:456-469 without a ghost fill,
+ * _magnetic_field_update.py:208-240 with the 3-vector flip rule) and enter the CFL reduction
+ * (_timestep_estimator.py:118-128 runs over the padded array).  shell_inout: this rank's padded gas array
+ * [ndim+2][n0+4][n1+4][n2+4] (only its ghost cells are used; planes beyond an AMX_BC_HALO side are skipped:
+ * they belong to the neighbour).  mode 0: after a hydro half step u0 -> u1 (internal layout); mode 1: after
+ * the fixed point (u0 = gas before the write-back, bv0 / bv1 = iterate buffers, the final one is taken from
+ * the control block in ws); mode 2: wave bounds only; mode 3: shell <- ghost fill of u1 (initial state, split
+ * sweeps).  alpha_out (nullable, 3 values of dtype): max |u_axis| + c over the shell cells. */
+AMX_API int amx_shell_update(const amx_desc* d, int mode, void* shell_inout, const void* u0, const void* u1,
+                      const void* bv0, const void* bv1, void* alpha_out, void* ws, void* stream);
+
 /* ---- peer-memory plumbing of a slab run (one process per GPU, arrays in peer-mapped memory) ----
  * Which stage entry points honour amx_desc::peer_* for this descriptor (the kernels that would run):
  * bit 0 amx_hydro_stage, bit 1 amx_magnetic_iter* / _pair_guarded / _fix_guarded, bit 2

@@ -420,26 +420,29 @@ def test_vec_hydro_stage_equals_generic_bitwise_in_strict_mode(cuda, dim, n, bnd
     assert np.array_equal(skewed, generic)
 
 
+@pytest.mark.parametrize("rs", ["oc.LAX_FRIEDRICHS", "oc.HLLC_LM"])
 @pytest.mark.parametrize("dim,n,bnd", [(3, 32, "periodic"), (3, 48, "reflective"), (2, 512, "open")])
-def test_vec_lax_friedrichs_stage_equals_generic_bitwise_in_strict_mode(cuda, dim, n, bnd):
-    """hydro_stage_vec<RS_LF> (global alpha per axis from the control block) against the generic kernel."""
+def test_vec_lax_friedrichs_and_hllc_lm_stage_equal_generic_bitwise_in_strict_mode(cuda, dim, n, bnd, rs):
+    """hydro_stage_vec<RS_LF> (global alpha per axis from the control block) and <RS_HLLC_LM> (low-Mach rescaling
+    of the wave speeds in the dissipation term, hll.py:190-228) against the generic kernel."""
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = (
         "import sys, numpy as np; sys.path.insert(0, %r);"
         "from astronomix_b200 import problems as pr, stepping as ti, _lib, option_classes as oc;"
         "s = pr.smooth_random(%d, %d, seed=9, dtype=np.float32);"
-        "c, p, rv = pr.make(%d, %d, boundaries=%r, riemann_solver=oc.LAX_FRIEDRICHS, limiter=oc.MINMOD);"
+        "c, p, rv = pr.make(%d, %d, boundaries=%r, riemann_solver=%s, limiter=oc.MINMOD);"
         "out = ti.integrate_steps(s, c, p, rv, 3, arithmetic=_lib.AMX_ARITH_STRICT);"
         "np.save(sys.argv[1], out)"
-    ) % (root, dim, n, dim, n, bnd)
+    ) % (root, dim, n, dim, n, bnd, rs)
     vec, generic = _run_subprocess_variants(code, [{}, {"AMX_FORCE_GENERIC": "1"}])
     assert np.isfinite(vec).all()
     assert np.array_equal(vec, generic)
 
 
 @pytest.mark.parametrize("arith", ["fast", "strict"])
-@pytest.mark.parametrize("dim,n,rs", [(3, 64, oc.HLLC), (2, 512, oc.HLLC), (3, 32, oc.HLL), (3, 48, oc.LAX_FRIEDRICHS)])
+@pytest.mark.parametrize("dim,n,rs", [(3, 64, oc.HLLC), (2, 512, oc.HLLC), (3, 32, oc.HLL), (3, 48, oc.LAX_FRIEDRICHS),
+                                      (3, 48, oc.HLLC_LM)])
 def test_vec_hydro_fp32_vs_oracle(cuda, dim, n, rs, arith):
     s = pr.smooth_random(dim, n, seed=61 + dim, dtype=np.float32)
     config, params, rv = pr.make(dim, n, riemann_solver=rs)

@@ -21,9 +21,14 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 ok = True
 for dim, n, mhd, rs, steps in [(3, 64, True, oc.HLL, 6), (2, 512, True, oc.HLL, 6), (3, 64, False, oc.HLLC, 6),
-                               (3, 64, True, oc.LAX_FRIEDRICHS, 4), (3, 64, True, oc.HLLC_LM, 3)]:
+                               (3, 64, True, oc.LAX_FRIEDRICHS, 4), (3, 64, True, oc.HLLC_LM, 3),
+                               (3, 32, True, (oc.HLL, "reflective"), 5), (2, 64, True, (oc.HLL, "reflective"), 5),
+                               (3, 32, True, (oc.LAX_FRIEDRICHS, "reflective"), 4), (3, 32, True, (oc.HLL, "open"), 4)]:
     s = pr.smooth_random(dim, n, mhd=mhd, seed=3, dtype=np.float32)
-    config, params, rv = pr.make(dim, n, mhd=mhd, riemann_solver=rs)
+    bnd = "periodic"
+    if isinstance(rs, tuple):  # (Riemann solver, boundaries): reflective sides in unsplit MHD = ghost-shell mode
+        rs, bnd = rs
+    config, params, rv = pr.make(dim, n, mhd=mhd, riemann_solver=rs, boundaries=bnd)
     drv = SlabDriver(config, params, rv, (n,) * dim, torch.float32, dev, arithmetic=_lib.AMX_ARITH_STRICT)
     drv.scatter(torch.from_numpy(s))
     info = drv.run(max_steps=steps)
@@ -32,7 +37,7 @@ for dim, n, mhd, rs, steps in [(3, 64, True, oc.HLL, 6), (2, 512, True, oc.HLL, 
         ref = ti.integrate_steps(s, config, params, rv, steps, arithmetic=_lib.AMX_ARITH_STRICT)
         same = np.array_equal(out, ref)
         ok &= same and info.magnetic_iterations == ti.last_info.magnetic_iterations
-        print(f"dim={dim} n={n} mhd={mhd} rs={rs}: {dist.get_world_size()}-GPU slab == 1-GPU bitwise: {same}; "
+        print(f"dim={dim} n={n} mhd={mhd} rs={rs} {bnd}: {dist.get_world_size()}-GPU slab == 1-GPU bitwise: {same}; "
               f"fixed-point iterations {info.magnetic_iterations} vs {ti.last_info.magnetic_iterations}; "
               f"max|diff| = {np.abs(out - ref).max():.3e}", flush=True)
     dist.barrier()
