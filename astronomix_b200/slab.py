@@ -59,9 +59,20 @@ class AmxBackend:
     def _s(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    def set_shell_sides(self, left_code, right_code):
+        """The stage kernels see AMX_BC_HALO on both x sides (the driver fills the ghost planes of a physical side
+        itself); the ghost shell has to know which x side of this rank is a physical boundary: its ghost cells
+        there are shell cells, whereas the planes beyond a halo side belong to the neighbour."""
+        self.desc_shell = _lib.AmxDesc.from_buffer_copy(self.desc)
+        self.desc_shell.peer_flags = 0
+        if left_code is not None:
+            self.desc_shell.bc[0][0] = int(left_code)
+        if right_code is not None:
+            self.desc_shell.bc[0][1] = int(right_code)
+
     def shell_update(self, mode, shell, u0=None, u1=None, bv0=None, bv1=None, alpha_out=None):
         """ghost shell of the gas state on this rank (include/amx.h amx_shell_update)"""
-        _lib.check(self.lib.amx_shell_update(C.byref(self.desc), int(mode), self._p(shell), self._p(u0), self._p(u1),
+        _lib.check(self.lib.amx_shell_update(C.byref(self.desc_shell), int(mode), self._p(shell), self._p(u0), self._p(u1),
                                              self._p(bv0), self._p(bv1), self._p(alpha_out), self.ws_ptr, self._s()))
         self.launches += 2 if alpha_out is not None else 1
 
@@ -293,6 +304,8 @@ class SlabDriver:
             self.shell = torch.zeros((self.ng, self.nxl + 2 * NG) + tuple(v + 2 * NG for v in self.global_n[1:]),
                                      dtype=dtype, device=device)
             self.alpha_shell = torch.zeros(3, dtype=dtype, device=device)
+            self.backend.set_shell_sides(self.bcx[0] if self.rank == 0 else None,
+                                         self.bcx[1] if self.rank == self.world - 1 else None)
         self.alpha = torch.zeros(3, dtype=dtype, device=device)
         self.change = torch.zeros(2, dtype=dtype, device=device)
         self.change4 = torch.zeros(4, dtype=dtype, device=device)
