@@ -199,12 +199,17 @@ class SlabDriver:
             raise ValueError("slab too thin: need at least 4 planes per rank")
         self.local_n = (self.nxl,) + self.global_n[1:]
         codes = oc.boundary_codes(config)
-        if any(oc.MHD_JET_BOUNDARY in codes[a] for a in range(self.dim)):
-            raise NotImplementedError("slab decomposition with the MHD jet boundary is not built")
+        # MHD jet inflow (boundaries.py:399-441): constants in a window of the x-LEFT ghost rows, i.e. on rank 0 only;
+        # the y-left side that carries the code is an open copy.  The kernels test for those cells before any
+        # boundary rule, so rank 0 needs nothing but the shell; the other ranks see a plain open side.
+        self.jet = any(oc.MHD_JET_BOUNDARY in codes[a] for a in range(self.dim))
+        if self.jet and (config.riemann_solver == oc.LAX_FRIEDRICHS or config.limiter == oc.VAN_ALBADA_PP):
+            raise NotImplementedError("the MHD jet boundary with LAX_FRIEDRICHS / VAN_ALBADA_PP is not built")
         # the reference's ghost gas cells set dt in this configuration (DESIGN.md "ghost shell"): every rank
         # carries the shell of its own cells (y / z faces of its x range, the x faces on the edge ranks)
-        self.shell_mode = (config.mhd and config.split == oc.UNSPLIT and config.boundary_handling == oc.GHOST_CELLS
-                           and any(oc.REFLECTIVE_BOUNDARY in codes[a] for a in range(self.dim)))
+        self.shell_mode = config.boundary_handling == oc.GHOST_CELLS and (self.jet or (
+            config.mhd and config.split == oc.UNSPLIT
+            and any(oc.REFLECTIVE_BOUNDARY in codes[a] for a in range(self.dim))))
         self.dtype, self.device = dtype, device
         self.ng = self.dim + 2
         self.nv = registered_variables.num_vars
@@ -220,6 +225,8 @@ class SlabDriver:
         self.tol = 1e-5 if config.numerical_precision == oc.SINGLE_PRECISION else 1e-10
         self.backend = backend if backend is not None else AmxBackend(config, params, self.local_n, dtype, device,
                                                                      arithmetic)
+        if self.jet and self.rank > 0 and hasattr(self.backend, "desc"):
+            self.backend.desc.bc[1][0] = oc.OPEN_BOUNDARY
         shape = (self.nxl + 2 * NG,) + self.global_n[1:]
         import os
         # Peer-to-peer halo exchange: the slab arrays live in symmetric memory (every rank maps its
@@ -577,6 +584,11 @@ class SlabDriver:
             self.exchange(src, flip_rows=(1,))
             want = (last and final_alpha) or self.lf
             b.split_sweep(src, dst, axis, self.dt, scale * frac, self.alpha, self.alpha if want else None)
+            if last and self.shell is not None:
+                # a sweep ends with a ghost fill: the shell is the fill of the result (images / jet constants)
+                b.shell_update(3, self.shell, u1=dst, alpha_out=self.alpha_shell if final_alpha else None)
+                if final_alpha:
+                    torch.maximum(self.alpha, self.alpha_shell, out=self.alpha)
             if want:
                 self._allreduce_max(self.alpha)
             src = dst
@@ -639,7 +651,8 @@ class SlabDriver:
         b.magnetic_final_guarded(gas, self.Gf, self.X[0], self.X[1], B_out, self.alpha if self.lf else None)
         self._wrote(self.Gf, 4)
         self._wrote(B_out, 4)
-        if self.shell is not None:  # _magnetic_field_update.py:208-240 at the ghost cells (Q12 flip rule)
+        if self.shell is not None and self.config.split == oc.UNSPLIT:
+            # _magnetic_field_update.py:208-240 at the ghost cells (Q12 flip rule)
             b.shell_update(1, self.shell, u0=gas, bv0=self.X[0], bv1=self.X[1])
         if self.lf:
             self._allreduce_max(self.alpha)

@@ -23,12 +23,22 @@ ok = True
 for dim, n, mhd, rs, steps in [(3, 64, True, oc.HLL, 6), (2, 512, True, oc.HLL, 6), (3, 64, False, oc.HLLC, 6),
                                (3, 64, True, oc.LAX_FRIEDRICHS, 4), (3, 64, True, oc.HLLC_LM, 3),
                                (3, 32, True, (oc.HLL, "reflective"), 5), (2, 64, True, (oc.HLL, "reflective"), 5),
-                               (3, 32, True, (oc.LAX_FRIEDRICHS, "reflective"), 4), (3, 32, True, (oc.HLL, "open"), 4)]:
+                               (3, 32, True, (oc.LAX_FRIEDRICHS, "reflective"), 4), (3, 32, True, (oc.HLL, "open"), 4),
+                               (2, 64, True, (oc.HLL, "jet"), 4), (2, 64, False, (oc.HLLC, "jet"), 4),
+                               (2, 64, True, (oc.HLL, "jet_split"), 3)]:
     s = pr.smooth_random(dim, n, mhd=mhd, seed=3, dtype=np.float32)
     bnd = "periodic"
     if isinstance(rs, tuple):  # (Riemann solver, boundaries): reflective sides in unsplit MHD = ghost-shell mode
         rs, bnd = rs
-    config, params, rv = pr.make(dim, n, mhd=mhd, riemann_solver=rs, boundaries=bnd)
+    kw = {}
+    if bnd in ("jet", "jet_split"):  # MHD jet inflow: constants in a window of the x-left ghost rows (rank 0)
+        b1 = oc.BoundarySettings1D
+        if bnd == "jet_split":
+            kw = dict(split=oc.SPLIT, time_integrator=oc.MUSCL)
+        bnd = oc.BoundarySettings(b1(oc.REFLECTIVE_BOUNDARY, oc.OPEN_BOUNDARY), b1(oc.MHD_JET_BOUNDARY, oc.REFLECTIVE_BOUNDARY),
+                                  b1(oc.OPEN_BOUNDARY, oc.OPEN_BOUNDARY))
+    config, params, rv = pr.make(dim, n, mhd=mhd, riemann_solver=rs, boundaries=bnd, **kw)
+    bnd = bnd if isinstance(bnd, str) else "jet"
     drv = SlabDriver(config, params, rv, (n,) * dim, torch.float32, dev, arithmetic=_lib.AMX_ARITH_STRICT)
     drv.scatter(torch.from_numpy(s))
     info = drv.run(max_steps=steps)
