@@ -43,7 +43,7 @@ class AmxDesc(C.Structure):
         ("use_max_adaptive_timestep", C.c_int32),
         ("arithmetic", C.c_int32),
         ("peer_flags", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("slab_flags", C.c_int32),
         ("peer_delta_lo", C.c_int64),
         ("peer_delta_hi", C.c_int64),
         ("reserved", C.c_int32 * 2),

@@ -219,6 +219,7 @@ Geom geom_of(const amx_desc* d) {
     g.bc[a][1] = d->bc[a][1];
   }
   g.jet_lo = g.jet_hi = 0;
+  g.jet_off = d->slab_flags & 1;
   if (d->ndim == 2 && d->bc[1][0] == 3) {
     // boundaries.py:412-413,424-428: half_inj_cell_num = int(0.025 / grid_spacing); padded y indices
     // [num_cells // 2 - h, num_cells // 2 + h) -> unpadded coordinates
@@ -534,8 +535,9 @@ template <typename T>
 __global__ void __launch_bounds__(64) peer_allreduce_max_kernel(PeerBufs bufs, int rank, int world, T* vals, int count) {
   char* const mine = reinterpret_cast<char*>(bufs.p[rank]);
   __shared__ unsigned e_s;
+  __shared__ int timed_out;
   const int tid = threadIdx.x;
-  if (tid == 0) e_s = *reinterpret_cast<volatile unsigned*>(mine) + 1u;
+  if (tid == 0) { e_s = *reinterpret_cast<volatile unsigned*>(mine) + 1u; timed_out = 0; }
   __syncthreads();
   const unsigned e = e_s, par = e & 1u;
   const int r = tid >> 3, i = tid & 7;
@@ -550,9 +552,12 @@ __global__ void __launch_bounds__(64) peer_allreduce_max_kernel(PeerBufs bufs, i
     unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(bufs.p[tid]) + kPeerFlagsOff) + (par * 8 + rank);
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(e) : "memory");
     const unsigned* own = reinterpret_cast<const unsigned*>(mine + kPeerFlagsOff) + (par * 8 + tid);
+    // (bounded: ranks that do not make the same sequence of calls must produce NaNs, not a hung GPU)
     unsigned seen;
+    const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(own) : "memory");
+      if (clock64() - t0 > 20000000000ll) { timed_out = 1; break; }
     } while (seen != e);
   }
   __syncthreads();
@@ -560,7 +565,7 @@ __global__ void __launch_bounds__(64) peer_allreduce_max_kernel(PeerBufs bufs, i
     const volatile double* src = reinterpret_cast<const volatile double*>(mine + kPeerValsOff) + par * 64 + tid;
     double m = src[0];
     for (int q = 1; q < world; ++q) m = fmax(m, src[q * 8]);
-    vals[tid] = (T)m;
+    vals[tid] = timed_out ? (T)NAN : (T)m;
   }
   if (tid == 0) *reinterpret_cast<volatile unsigned*>(mine) = e;
 }

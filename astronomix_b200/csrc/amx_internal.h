@@ -27,11 +27,13 @@ struct Geom {
   // x-LEFT side whose y index lies in [jet_lo, jet_hi) (unpadded coordinates) hold constants; the
   // y-left side itself is an open side.  jet_hi <= jet_lo: no jet.
   int jet_lo, jet_hi;
+  int jet_off;  // slab rank that does not own the x-left boundary: the window exists (same kernel family on every
+                // rank) but no cell of this rank is an inflow cell
 };
 
 // the reference writes state[:, 0:ng, N/2-h : N/2+h] on the padded array, i.e. after every other fill
 __host__ __device__ inline bool jet_cell(const Geom& g, int ix, int iy) {
-  return g.jet_hi > g.jet_lo && ix < 0 && iy >= g.jet_lo && iy < g.jet_hi;
+  return g.jet_hi > g.jet_lo && !g.jet_off && ix < 0 && iy >= g.jet_lo && iy < g.jet_hi;
 }
 // boundaries.py:418-421: gas rows (rho, v_x, v_y, p) = (5/3, 800, 0, 1); velocity (800, 0, 0); B (sqrt(200), 0, 0)
 template <typename T>

@@ -226,7 +226,7 @@ class SlabDriver:
         self.backend = backend if backend is not None else AmxBackend(config, params, self.local_n, dtype, device,
                                                                      arithmetic)
         if self.jet and self.rank > 0 and hasattr(self.backend, "desc"):
-            self.backend.desc.bc[1][0] = oc.OPEN_BOUNDARY
+            self.backend.desc.slab_flags |= 1  # same kernels as rank 0, but none of this rank's cells is an inflow cell
         shape = (self.nxl + 2 * NG,) + self.global_n[1:]
         import os
         # Peer-to-peer halo exchange: the slab arrays live in symmetric memory (every rank maps its
@@ -299,6 +299,10 @@ class SlabDriver:
                 dist.barrier(group=group)  # every rank's communication buffer is zeroed before anybody signals
                 self.push = self.backend.set_peers(flags, ptrs[left] - ptrs[self.rank], ptrs[right] - ptrs[self.rank])
                 self._push_flags = flags
+                # every rank must make the same sequence of collectives: agree on what the kernels push
+                agreed = torch.tensor([(self.push >> k) & 1 for k in range(3)], dtype=torch.int32, device=device)
+                dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=group)
+                self.push = sum(int(v) << k for k, v in enumerate(agreed.tolist()))
             except Exception as e:  # pragma: no cover
                 print(f"[slab] peer-memory plumbing unavailable ({e!r}); copies + NCCL all-reduce", flush=True)
                 self._comm = None

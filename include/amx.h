@@ -90,7 +90,7 @@ typedef struct amx_desc {
    * launch), so that a halo exchange is only a barrier.  peer_flags: bit 0 = lower neighbour, bit 1 =
    * upper neighbour; 0 = off.  amx_peer_push_supported() tells which stage entry points honour it. */
   int32_t peer_flags;
-  int32_t reserved0;
+  int32_t slab_flags;         /* bit 0: this slab rank does not own the x-left boundary (no MHD-jet inflow cells here) */
   int64_t peer_delta_lo, peer_delta_hi;
   int32_t reserved[2];
   double dx;                  /* config.grid_spacing */
