@@ -102,8 +102,15 @@ def _to_device(state):
     if src.is_pinned():
         return src.cuda(non_blocking=True), kind
     stage, ent = _pinned(src.shape, src.dtype, "in")
-    stage.copy_(src)
-    t = stage.cuda(non_blocking=True)
+    t = torch.empty(src.shape, dtype=src.dtype, device="cuda")
+    if src.dim() > 1 and src.shape[0] > 1 and src.numel() > (1 << 22):
+        # row by row: the host copy of row r + 1 into the staging buffer overlaps the H2D copy of row r
+        for r in range(src.shape[0]):
+            stage[r].copy_(src[r])
+            t[r].copy_(stage[r], non_blocking=True)
+    else:
+        stage.copy_(src)
+        t.copy_(stage, non_blocking=True)
     ent[1] = torch.cuda.Event()
     ent[1].record()
     return t, kind
@@ -113,9 +120,23 @@ def _from_device(t, kind):
     if kind == "torch_cuda":
         return t
     host, ent = _pinned(t.shape, t.dtype, "out")
-    host.copy_(t, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    return host.numpy().copy() if kind == "numpy" else host.clone()
+    out = torch.empty(t.shape, dtype=t.dtype)
+    if t.dim() > 1 and t.shape[0] > 1 and t.numel() > (1 << 22):
+        # row by row: the D2H copy of row r + 1 overlaps the host copy of row r into the result
+        evs = []
+        for r in range(t.shape[0]):
+            host[r].copy_(t[r], non_blocking=True)
+            e = torch.cuda.Event()
+            e.record()
+            evs.append(e)
+        for r in range(t.shape[0]):
+            evs[r].synchronize()
+            out[r].copy_(host[r])
+    else:
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out.copy_(host)
+    return out.numpy() if kind == "numpy" else out
 
 
 def _stream_ptr():
