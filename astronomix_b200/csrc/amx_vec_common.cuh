@@ -79,7 +79,22 @@ AMX_DI void mbar_arrive(unsigned long long* b) {
 AMX_DI void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
   asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
+// AMX_MBAR_HINT_NS > 0: suspend-time hint of try_wait (a waiting warp sleeps that long before it polls again
+// instead of the default, so that waiters -- the halo warp most of all -- take fewer issue slots from the warps
+// that work)
+#ifndef AMX_MBAR_HINT_NS
+#define AMX_MBAR_HINT_NS 0
+#endif
 AMX_DI void mbar_wait(unsigned long long* b, unsigned parity) {
+#if AMX_MBAR_HINT_NS > 0
+  asm volatile(
+      "{ .reg .pred p;\n"
+      "W_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=: }"
+      ::"r"(smem_u32(b)), "r"(parity), "r"((unsigned)AMX_MBAR_HINT_NS) : "memory");
+#else
   asm volatile(
       "{ .reg .pred p;\n"
       "W_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
@@ -87,6 +102,7 @@ AMX_DI void mbar_wait(unsigned long long* b, unsigned parity) {
       "bra W_%=;\n"
       "D_%=: }"
       ::"r"(smem_u32(b)), "r"(parity) : "memory");
+#endif
 }
 // one arrival per warp: the lanes' shared-memory writes are ordered before lane 0's (releasing) arrive
 AMX_DI void mbar_arrive_warp(unsigned long long* b) {
