@@ -153,15 +153,17 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
 #else
   const float dpar = 0.5f * (float)(1.0 / a.np.dx);
 #endif
-  const long long sx = a.B0.s[0], sy = a.B0.s[1];
+  // element offsets are 32-bit here (pair_mag_supported checks that every array fits): one IMAD.WIDE per global
+  // access instead of a 64-bit add chain -- integer work was 36 % of the executed instructions of this kernel
+  const int sx = (int)a.B0.s[0], sy = (int)a.B0.s[1];
   const float* const fB0 = static_cast<const float*>(a.B0.p);
   const float* const fG = static_cast<const float*>(a.gas0.p);
   const float* const fBk = static_cast<const float*>(a.Bk.p);
   const float* const fvk = static_cast<const float*>(a.vk.p);
-  const long long vB0 = a.B0.vs, vG = a.gas0.vs, vBk = a.Bk.vs, vvk = a.vk.vs;
+  const int vB0 = (int)a.B0.vs, vG = (int)a.gas0.vs, vBk = (int)a.Bk.vs, vvk = (int)a.vk.vs;
   float* const fB1 = static_cast<float*>(a.Bk1.p);
   float* const fv1 = static_cast<float*>(a.vk1.p);
-  const long long vB1 = a.Bk1.vs, vv1 = a.vk1.vs;
+  const int vB1 = (int)a.Bk1.vs, vv1 = (int)a.vk1.vs;
   const bool xwrap = g.bc[0][0] == BC_PERIODIC;
 
   F2 n1B = bc2(0.f), n1v = bc2(0.f), n2B = bc2(0.f), n2v = bc2(0.f);
@@ -198,14 +200,14 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
   int gy = y0 - 2 + j, gz = z0 - 2 + c;
   gy += gy < 0 ? g.n[1] : (gy >= g.n[1] ? -g.n[1] : 0);
   gz += gz < 0 ? g.n[2] : (gz >= g.n[2] ? -g.n[2] : 0);
-  const Col col = gz + (long long)gy * sy;
+  const int col = gz + gy * sy;
   const int smA = j * RS + 2 * c + 4;        // chunk c/2 + 1
   const int smB = (j - 1) * RS + 2 * c + 4;
   float* const stash = stash0 + 4 * (wid * 32 + lane);  // tile threads only
 
-  auto plane_off = [&](int p) -> long long {
+  auto plane_off = [&](int p) -> int {
     if (xwrap) p += p < 0 ? g.n[0] : (p >= g.n[0] ? -g.n[0] : 0);
-    return col + (long long)p * sx;
+    return col + p * sx;
   };
   // One block per SM and one barrier per plane leave nothing to overlap a DRAM miss with: the
   // lines of plane p + pf are pulled into L2 while plane p is loaded into registers (one lane per
@@ -230,37 +232,33 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
     }
     if (!exists) return;
     if (pf > 0 && pf_lane && p + pf <= xe + 1) {
-      const long long q = plane_off(p + pf);
+      const int q = plane_off(p + pf);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(fB0 + q + k * vB0));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(fG + q + (k + 1) * vG));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(fB0 + (q + k * vB0)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(fG + (q + (k + 1) * vG)));
       }
       if (need_rho) asm volatile("prefetch.global.L2 [%0];" ::"l"(fG + q));
       if constexpr (!FIRST) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(fBk + q + k * vBk));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(fvk + q + k * vvk));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fBk + (q + k * vBk)));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fvk + (q + k * vvk)));
         }
       }
     }
-    const long long o = plane_off(p);
-    const float* pb = fB0 + o;
-    const float* pg = fG + o;
+    const int o = plane_off(p);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      r.B0[k] = ldg2<0>(pb + k * vB0);
-      r.v0[k] = ldg2<0>(pg + (k + 1) * vG);
+      r.B0[k] = ldg2<0>(fB0 + (o + k * vB0));
+      r.v0[k] = ldg2<0>(fG + (o + (k + 1) * vG));
     }
-    if (need_rho) r.rho = ldg2<0>(pg);
+    if (need_rho) r.rho = ldg2<0>(fG + o);
     if constexpr (!FIRST) {
-      const float* pbk = fBk + o;
-      const float* pvk = fvk + o;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        r.Bk[k] = ldg2<0>(pbk + k * vBk);
-        r.vk[k] = ldg2<0>(pvk + k * vvk);
+        r.Bk[k] = ldg2<0>(fBk + (o + k * vBk));
+        r.vk[k] = ldg2<0>(fvk + (o + k * vvk));
       }
     }
   };
@@ -364,11 +362,11 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
       psi_ring<PLB, RS>(ringB + sC * SLOTB + smB, ringB + sM * SLOTB + smB, Bx, Ex, dpar, curlE, cr);
       advance(curlE, cr, B0, v0, rho, Bn, vn);
       change(B1, v1, Bn, vn, n2B, n2v);
-      const long long o = col + (long long)i * sx;
+      const int o = col + i * sx;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        stg2(fB1 + o + k * vB1, Bn[k]);
-        stg2(fv1 + o + k * vv1, vn[k]);
+        stg2(fB1 + (o + k * vB1), Bn[k]);
+        stg2(fv1 + (o + k * vv1), vn[k]);
       }
       // slab rank: the edge planes also go into the neighbours' ghost planes (stores over NVLink)
       long long pbd[2];
@@ -379,11 +377,11 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
         for (int side = 0; side < 2; ++side) {
           pon[side] = peer_target(a.peers, i, g.n[0], side, pbd[side], pps[side]);
           if (pon[side]) {
-            const long long po = o + (long long)pps[side] * sx;
+            const int po = o + pps[side] * sx;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              stg2(reinterpret_cast<float*>(reinterpret_cast<char*>(fB1 + po + k * vB1) + pbd[side]), Bn[k]);
-              stg2(reinterpret_cast<float*>(reinterpret_cast<char*>(fv1 + po + k * vv1) + pbd[side]), vn[k]);
+              stg2(reinterpret_cast<float*>(reinterpret_cast<char*>(fB1 + (po + k * vB1)) + pbd[side]), Bn[k]);
+              stg2(reinterpret_cast<float*>(reinterpret_cast<char*>(fv1 + (po + k * vv1)) + pbd[side]), vn[k]);
             }
           }
         }
@@ -392,7 +390,7 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
         // this launch is expected to end the loop: write what mag_final would from R_{k+2}
         // (rho, v_n, p_2 -> emit_gas; B_n -> emit_B); valid only if the while-condition agrees
         // (Ctl::final_emitted), else mag_final runs as usual
-        const F2 pr = ldg2<0>(fG + o + 4 * vG);
+        const F2 pr = ldg2<0>(fG + (o + 4 * vG));
         F2 n0 = bc2(0.f), nn = bc2(0.f);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -401,21 +399,23 @@ mag_pair_vec(const MagIterArgs a, const int xchunk, const int pf, const __grid_c
         }
         const F2 p2 = mk2(magnetic_writeback_pressure(rho.x, pr.x, n0.x, nn.x),
                           magnetic_writeback_pressure(rho.y, pr.y, n0.y, nn.y));
-        float* const eg = static_cast<float*>(a.emit_gas.p) + o;
-        float* const eb = static_cast<float*>(a.emit_B.p) + o;
-        const long long veg = a.emit_gas.vs, veb = a.emit_B.vs;
+        float* const eg0 = static_cast<float*>(a.emit_gas.p);
+        float* const eb0 = static_cast<float*>(a.emit_B.p);
+        float* const eg = eg0 + o;
+        float* const eb = eb0 + o;
+        const int veg = (int)a.emit_gas.vs, veb = (int)a.emit_B.vs;
         stg2(eg, rho);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          stg2(eg + (k + 1) * veg, vn[k]);
-          stg2(eb + k * veb, Bn[k]);
+          stg2(eg0 + (o + (k + 1) * veg), vn[k]);
+          stg2(eb0 + (o + k * veb), Bn[k]);
         }
-        stg2(eg + 4 * veg, p2);
+        stg2(eg0 + (o + 4 * veg), p2);
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
           if (pon[side]) {
-            float* const pg = reinterpret_cast<float*>(reinterpret_cast<char*>(eg) + pbd[side]) + (long long)pps[side] * sx;
-            float* const pb = reinterpret_cast<float*>(reinterpret_cast<char*>(eb) + pbd[side]) + (long long)pps[side] * sx;
+            float* const pg = reinterpret_cast<float*>(reinterpret_cast<char*>(eg) + pbd[side]) + pps[side] * sx;
+            float* const pb = reinterpret_cast<float*>(reinterpret_cast<char*>(eb) + pbd[side]) + pps[side] * sx;
             stg2(pg, rho);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -519,6 +519,14 @@ bool pair_mag_supported(const MagIterArgs& a) {
     for (int ax = 0; ax < 2; ++ax)
       if (a.emit_gas.s[ax] != a.B0.s[ax] || a.emit_B.s[ax] != a.B0.s[ax]) return false;
   }
+  // 32-bit element offsets inside the kernel: rows * row stride (+ the ghost planes) of every array below 2^31
+  auto fits = [&](const View& v, int rows) {
+    const long long ext = (long long)(rows - 1) * v.vs + (long long)(a.g.n[0] + 4) * v.s[0];
+    return v.vs >= 0 && ext < 2147483647LL && (long long)rows * v.vs < 2147483647LL;
+  };
+  if (!fits(a.B0, 3) || !fits(a.gas0, 5) || !fits(a.Bk1, 3) || !fits(a.vk1, 3)) return false;
+  if (a.Bk.p && (!fits(a.Bk, 3) || !fits(a.vk, 3))) return false;
+  if (a.emit && (!fits(a.emit_gas, 5) || !fits(a.emit_B, 3))) return false;
   return a.g.n[0] >= 4 && a.g.n[1] >= 4 && a.g.n[2] >= 8;
 }
 
