@@ -307,3 +307,56 @@ def test_slab_forcing_equals_single_domain_forcing(world, tmp_path):
                            fo.Opts.from_config(config, params), config.box_size)
     assert pr.rel_l1(got, ref, 3, True) <= 1e-12
     assert np.array_equal(got[0], s[0]) and np.array_equal(got[4:], s[4:])
+
+
+def _forced_driver_worker(rank, world, port, n, steps, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from astronomix_b200.forcing import SlabForcing
+        from oracle import threefry as tf
+        tfc = oc.TurbulentForcingConfig(turbulent_forcing=True)
+        config, params, rv = pr.make(3, n, mhd=True, dtype=np.float64, boundary_handling=oc.PERIODIC_ROLL,
+                                     turbulent_forcing_config=tfc)
+        params = params._replace(t_end=1.0e9)
+        noises, key = [], tf.seed_key(42)
+        for _ in range(steps):
+            key, sk1, sk2 = tf.split(key, 3)
+            noises.append(torch.complex(torch.from_numpy(tf.normal(sk1, (3, n, n, n), np.float64)),
+                                        torch.from_numpy(tf.normal(sk2, (3, n, n, n), np.float64))))
+        s = pr.smooth_random(3, n, mhd=True, seed=21, dtype=np.float64)
+        drv = SlabDriver(config, params, rv, (n,) * 3, torch.float64, torch.device("cpu"),
+                         backend=OracleBackend(config, params, torch.float64))
+        drv.forcing = SlabForcing(config, params, rv, torch.float64, torch.device("cpu"), rank, world,
+                                  noise_fn=lambda step: noises[step])
+        drv.scatter(torch.from_numpy(s))
+        drv.run(max_steps=steps)
+        full = drv.gather()
+        if rank == 0:
+            np.save(out_path, full.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_driven_loop_equals_single_domain(tmp_path):
+    """dt from the unforced state -> driving (slab FFT, all-reduced sums) -> MHD step, on two slab ranks against
+    the oracle's whole-domain loop (time_integration.py:699-711): the ghost planes of the forced state are
+    exchanged again, not taken from what the previous step's kernels stored."""
+    n, steps = 8, 2
+    out = str(tmp_path / "forced_loop.npy")
+    mp.spawn(_forced_driver_worker, args=(2, _free_port(), n, steps, out), nprocs=2, join=True)
+    got = np.load(out)
+    from oracle import threefry as tf
+    tfc = oc.TurbulentForcingConfig(turbulent_forcing=True)
+    config, params, rv = pr.make(3, n, mhd=True, dtype=np.float64, boundary_handling=oc.PERIODIC_ROLL,
+                                 turbulent_forcing_config=tfc)
+    params = params._replace(t_end=1.0e9)
+    noises, key = [], tf.seed_key(42)
+    for _ in range(steps):
+        key, sk1, sk2 = tf.split(key, 3)
+        noises.append(tf.normal(sk1, (3, n, n, n), np.float64) + 1j * tf.normal(sk2, (3, n, n, n), np.float64))
+    s = pr.smooth_random(3, n, mhd=True, seed=21, dtype=np.float64)
+    ref, nsteps, _ = fo.time_integration_forced(s, fo.Opts.from_config(config, params), noises,
+                                                params.turbulent_forcing_params.energy_injection_rate, config.box_size)
+    assert nsteps == steps
+    assert pr.rel_l1(got, ref, 3, True) <= 1e-11
