@@ -558,9 +558,10 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
     mbar_init(barP, kHydroCW + 1);
   }
   const float dts = *static_cast<const float*>(a.dt) * (float)a.dt_scale;
-  const long long sx = a.in.s[0], sy = ND == 3 ? a.in.s[1] : 0;  // common strides (vec_stage_supported)
+  // common strides (vec_stage_supported); element offsets are 32-bit (the same check): one IMAD.WIDE per access
+  const int sx = (int)a.in.s[0], sy = ND == 3 ? (int)a.in.s[1] : 0;
   const float* const fin = static_cast<const float*>(a.in.p);
-  const long long vin = a.in.vs;
+  const int vin = (int)a.in.vs;
   F2 alpha_lf[ND];
 #pragma unroll
   for (int k = 0; k < ND; ++k) alpha_lf[k] = RS == RS_LF ? F2(static_cast<const float*>(a.alpha_lf)[k]) : F2(0.f);
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
     // ================= halo warp
     const int l = tid - kCompute;
     // items: A0 / A1 = y-halo pairs (3-D), B = lane-axis halo pair of one row (two mapped cells)
-    long long colA0 = 0, colA1 = 0, colB0 = 0, colB1 = 0;
+    int colA0 = 0, colA1 = 0, colB0 = 0, colB1 = 0;
     bool haveA = false, haveB = false, fA0 = false, fA1 = false, fB0 = false, fB1 = false;
     int smA0 = 0, smA1 = 0, smB = 0;
     if constexpr (ND == 3) {
@@ -639,8 +640,8 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
       haveA = q < tqa;
       const int my0 = map_index(y0 - 2 + jr, g.n[1], g.bc[1][0], g.bc[1][1], fA0);
       const int my1 = map_index(y0 + ta + jr, g.n[1], g.bc[1][0], g.bc[1][1], fA1);
-      colA0 = z0 + 2 * q + (long long)my0 * sy;
-      colA1 = z0 + 2 * q + (long long)my1 * sy;
+      colA0 = z0 + 2 * q + my0 * sy;
+      colA1 = z0 + 2 * q + my1 * sy;
       smA0 = jr * RSW + 4 + 2 * q;
       smA1 = (ta + 2 + jr) * RSW + 4 + 2 * q;
       const int r = l % 16, side = l / 16;
@@ -648,8 +649,8 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
       const int zc = side == 0 ? z0 - 2 : z0 + 2 * tqa;
       const int mz0 = map_index(zc, g.n[2], g.bc[2][0], g.bc[2][1], fB0);
       const int mz1 = map_index(zc + 1, g.n[2], g.bc[2][0], g.bc[2][1], fB1);
-      colB0 = mz0 + (long long)(y0 + r) * sy;
-      colB1 = mz1 + (long long)(y0 + r) * sy;
+      colB0 = mz0 + (y0 + r) * sy;
+      colB1 = mz1 + (y0 + r) * sy;
       smB = (r + YO) * RSW + (side == 0 ? 2 : 4 + 2 * tqa);
     } else {
       haveB = l < 2;
@@ -662,20 +663,20 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
     }
     auto issue = [&](int p, int slot) {
       bool fx;
-      const long long o = (long long)plane_map(p, fx) * sx;
+      const int o = plane_map(p, fx) * sx;
       float* w = win + slot * WSLOT;
       if (haveA) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-          cp_async8(w + k * PLW + smA0, fin + k * vin + o + colA0);
-          cp_async8(w + k * PLW + smA1, fin + k * vin + o + colA1);
+          cp_async8(w + k * PLW + smA0, fin + (k * vin + o + colA0));
+          cp_async8(w + k * PLW + smA1, fin + (k * vin + o + colA1));
         }
       }
       if (haveB) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-          cp_async4(w + k * PLW + smB, fin + k * vin + o + colB0);
-          cp_async4(w + k * PLW + smB + 1, fin + k * vin + o + colB1);
+          cp_async4(w + k * PLW + smB, fin + (k * vin + o + colB0));
+          cp_async4(w + k * PLW + smB + 1, fin + (k * vin + o + colB1));
         }
       }
       cp_async_commit();
@@ -808,19 +809,19 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
     // ================= compute threads: pair (ty, tq)
     const int tq = tid % TQ, ty = tid / TQ;
     const bool active = tq < tqa && ty < ta;
-    const long long col = z0 + 2 * tq + (ND == 3 ? (long long)(y0 + ty) * sy : 0);
+    const int col = z0 + 2 * tq + (ND == 3 ? (y0 + ty) * sy : 0);
     const int smW = (ty + YO) * RSW + 4 + 2 * tq;  // own pair inside a window plane
     float* const fout = static_cast<float*>(a.out.p);
     const float* const fin0 = static_cast<const float*>(a.in0.p);
-    const long long vout = a.out.vs, vin0 = a.in0.vs;
+    const int vout = (int)a.out.vs, vin0 = (int)a.in0.vs;
 
     auto issue = [&](int p, int slot) {
       if (active) {
         bool fx;
-        const float* src = fin + (long long)plane_map(p, fx) * sx + col;
+        const int src = plane_map(p, fx) * sx + col;
         float* w = win + slot * WSLOT + smW;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) cp_async8(w + k * PLW, src + k * vin);
+        for (int k = 0; k < NV; ++k) cp_async8(w + k * PLW, fin + (src + k * vin));
       }
       cp_async_commit();
     };
@@ -835,9 +836,9 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
     };
     auto load_direct = [&](int p, F2 (&v)[NV]) {
       bool fx;
-      const float* src = fin + (long long)plane_map(p, fx) * sx + col;
+      const int src = plane_map(p, fx) * sx + col;
 #pragma unroll
-      for (int k = 0; k < NV; ++k) v[k] = active ? ldg2<0>(src + k * vin) : F2(1.f);
+      for (int k = 0; k < NV; ++k) v[k] = active ? ldg2<0>(fin + (src + k * vin)) : F2(1.f);
       if (fx) v[1] = -v[1];
     };
     auto read_own = [&](int slot, F2 (&v)[NV]) {
@@ -994,9 +995,9 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
       // RK2 combine input (centre pair of s0), consumed after the barrier
       F2 s0v[NV];
       if constexpr (COMBINE) {
-        const float* p0 = fin0 + (long long)x * sx + col;
+        const int p0 = x * sx + col;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) s0v[k] = active ? ldg2<0>(p0 + k * vin0) : F2(1.f);
+        for (int k = 0; k < NV; ++k) s0v[k] = active ? ldg2<0>(fin0 + (p0 + k * vin0)) : F2(1.f);
       }
       mbar_arrive_warp(barP);  // own part of plane x+2 landed, y face states of plane x+1 published
       mbar_wait(barF, fs ^ pb);     // fluxes of plane x published by everybody; nobody reads window slot sCs any more
@@ -1034,16 +1035,17 @@ __global__ void __launch_bounds__(32 * kHydroCW + 32, AMX_HYDRO_MINB) hydro_stag
             for (int k = 0; k < NV; ++k) Um.q[k] = F2(0.5f) * (U0.q[k] + U2.q[k]);
             s = prim_from_cons(Um, c);
           }
-          float* po = fout + (long long)x * sx + col;
+          const int po32 = x * sx + col;
+          float* po = fout + po32;
 #pragma unroll
-          for (int k = 0; k < NV; ++k) stg2(po + k * vout, s.q[k]);
+          for (int k = 0; k < NV; ++k) stg2(fout + (po32 + k * vout), s.q[k]);
           if (a.peers.flags) {  // slab rank: the edge planes also go into the neighbours' ghost planes (NVLink stores)
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
               long long bd;
               int ps;
               if (peer_target(a.peers, x, g.n[0], side, bd, ps)) {
-                float* pp = reinterpret_cast<float*>(reinterpret_cast<char*>(po) + bd) + (long long)ps * sx;
+                float* pp = reinterpret_cast<float*>(reinterpret_cast<char*>(po) + bd) + ps * sx;
 #pragma unroll
                 for (int k = 0; k < NV; ++k) stg2(pp + k * vout, s.q[k]);
               }
@@ -1168,6 +1170,13 @@ bool vec_stage_supported(const StageArgs& a) {
   if (a.g.n[0] < 4 || (a.g.n[nd - 1] & 1) || a.g.n[nd - 1] < 8) return false;
   if (nd == 3 && a.g.n[1] < 4) return false;
   if (a.np.rs != RS_HLL && a.np.rs != RS_HLLC && a.np.rs != RS_LF && a.np.rs != RS_HLLC_LM) return false;
+  {  // 32-bit element offsets inside the kernel: rows * row stride (+ look-ahead planes) of every array below 2^31
+    auto fits = [&](const View& v) {
+      const long long ext = (long long)(nd + 1) * v.vs + (long long)(a.g.n[0] + 4) * v.s[0];
+      return v.vs >= 0 && ext < 2147483647LL;
+    };
+    if (!fits(a.in) || !fits(a.out) || (a.in0.p && !fits(a.in0))) return false;
+  }
   if (a.np.rs == RS_LF && !a.alpha_lf) return false;
   return true;
 }
